@@ -1,0 +1,127 @@
+"""The oracle (numpy restatement) against the goldens minted from the unmodified reference, and — when
+/root/reference is mounted — against the live reference module. CPU only."""
+import itertools
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import mpl_oracle, ref_loader
+from oracle.cases import CASES, GRID_FLAGS, GRID_BASE, make_inputs
+from openmpl_b200 import spec
+
+SMALL = [n for n in CASES if not n.endswith("_d12")]
+FULL = [n for n in CASES if n.endswith("_d12")]
+
+
+def _check(name):
+    case = CASES[name]
+    g = load_golden(name)
+    cfg, weights, batch = make_inputs(case)
+    # the regenerated inputs are the stored ones (generator determinism across machines)
+    for k in ("poses", "rays", "centers"):
+        np.testing.assert_array_equal(batch[k], g[k])
+    out = mpl_oracle.forward(weights, cfg, batch["poses"], batch["rays"], batch["centers"])
+    outs = [out[0]] + list(out[1]) if isinstance(out, tuple) else [out]
+    for i, o in enumerate(outs):
+        scale = np.abs(g[f"out64_{i}"]).max()
+        assert np.abs(o - g[f"out64_{i}"]).max() <= 1e-12 * max(scale, 1.0), name       # fp64 vs fp64 reference
+        assert np.abs(o - g[f"out32_{i}"]).max() <= 2e-5 * max(scale, 1.0), name        # fp32 reference round-off
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_oracle_matches_golden_small(name):
+    _check(name)
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_oracle_matches_golden_full_arch(name):
+    _check(name)
+
+
+def test_oracle_fp32_mode_close():
+    cfg, weights, batch = make_inputs(CASES["flag_hm0flags_small"])
+    a = mpl_oracle.forward(weights, cfg, batch["poses"], batch["rays"], batch["centers"], dtype=np.float32)
+    b = mpl_oracle.forward(weights, cfg, batch["poses"], batch["rays"], batch["centers"])
+    assert a.dtype == np.float32 and np.abs(a - b).max() < 1e-4
+
+
+def test_validity_matches_reference_grid():
+    """spec.make_config().error reproduces exactly which of the 4096 flag combinations the reference runs."""
+    g = load_golden("validity_grid")
+    assert g["meta"]["flags"] == GRID_FLAGS and g["meta"]["base"] == GRID_BASE
+    ok = g["ok"]
+    assert int(ok.sum()) == 1776
+    for idx, bits in enumerate(itertools.product((False, True), repeat=len(GRID_FLAGS))):
+        cfg = spec.make_config(**dict(GRID_BASE, **dict(zip(GRID_FLAGS, bits))))
+        assert (cfg.error is None) == bool(ok[idx]), (bits, cfg.error)
+
+
+def test_oracle_runs_every_valid_grid_combo_sampled():
+    """The oracle executes (shape-wise) on a sample of valid combinations and raises on invalid ones."""
+    g = load_golden("validity_grid")
+    rng = np.random.default_rng(0)
+    from openmpl_b200 import synth
+    rig = synth.make_rig(GRID_BASE["num_views"])
+    batch = synth.make_batch(2, rig, seed=5)
+    combos = list(itertools.product((False, True), repeat=len(GRID_FLAGS)))
+    for idx in rng.choice(len(combos), size=96, replace=False):
+        cfg = spec.make_config(**dict(GRID_BASE, **dict(zip(GRID_FLAGS, combos[idx]))))
+        w = synth.named_weights(spec.param_spec(cfg), seed=1)
+        if g["ok"][idx]:
+            out = mpl_oracle.forward(w, cfg, batch["poses"], batch["rays"], batch["centers"])
+            assert out.shape == (2, 17, 3) and np.isfinite(out).all()
+        else:
+            with pytest.raises((RuntimeError, IndexError)):
+                mpl_oracle.forward(w, cfg, batch["poses"], batch["rays"], batch["centers"])
+
+
+def test_metric_matches_reference_semantics():
+    rng = np.random.default_rng(1)
+    pred, gt = rng.normal(size=(50, 17, 3)), rng.normal(size=(50, 17, 3))
+    r = mpl_oracle.evaluate(pred, gt, output_in_meter=True, relative=False)
+    d = np.sqrt((((pred - gt) * 100) ** 2).sum(-1))
+    np.testing.assert_allclose(r["pjpe"], d.mean(0))
+    np.testing.assert_allclose(r["mpjpe"], d.mean())
+    rr = mpl_oracle.evaluate(pred, gt, output_in_meter=True, relative=True)
+    pr, gr = pred - pred[:, :1], gt - gt[:, :1]
+    np.testing.assert_allclose(rr["mpjpe"], np.sqrt((((pr - gr) * 100) ** 2).sum(-1)).mean())
+    conf = np.ones((50, 17, 3))
+    conf[3, 5] = 0
+    rm = mpl_oracle.evaluate(pred, gt, conf_3d=conf)
+    d2 = d.copy()
+    d2[3, 5] = 0                                       # nansum -> 0 inside the joint norm, still counted in the mean
+    np.testing.assert_allclose(rm["pjpe"], d2.mean(0))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_oracle_vs_live_reference():
+    import torch
+    m = ref_loader.load_model_module()
+    for name in ("flag_hm0flags_small", "flag_confattn_multi", "flag_kadkhod", "cmu0_v2_d2"):
+        case = CASES[name]
+        cfg, weights, batch = make_inputs(case)
+        model = m.MultiView_MPL(**case["kw"]).eval().double()
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+        V = cfg.V
+        with torch.no_grad():
+            ref = model([torch.from_numpy(batch["poses"][:, v]).double() for v in range(V)],
+                        rays=[torch.from_numpy(batch["rays"][:, v]).double() for v in range(V)],
+                        centers=[torch.from_numpy(batch["centers"][:, v]).double() for v in range(V)])
+        ref = ref[0] if isinstance(ref, tuple) else ref
+        out = mpl_oracle.forward(weights, cfg, batch["poses"], batch["rays"], batch["centers"])
+        out = out[0] if isinstance(out, tuple) else out
+        assert np.abs(out - ref.numpy()).max() < 1e-12
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_metric_vs_live_reference():
+    ev = ref_loader.load_evaluate_module()
+    rng = np.random.default_rng(2)
+    pred, gt = rng.normal(size=(40, 17, 3)), rng.normal(size=(40, 17, 3))
+    for mode in ("absolute", "relative"):
+        a = ev.calc_mpjpe(pred, gt, mode=mode)
+        b = mpl_oracle.calc_mpjpe(pred, gt, mode=mode)
+        np.testing.assert_allclose(a[0], b[0])
+        np.testing.assert_allclose(a[1], b[1])
+    np.testing.assert_allclose(ev.calc_distance_per_dim(pred, gt)[0], mpl_oracle.calc_distance_per_dim(pred, gt)[0])
