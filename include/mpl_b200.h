@@ -1,0 +1,175 @@
+/*
+ * mpl_b200.h — C ABI of the B200-native MPL lifter forward.
+ *
+ * One shared library (libmpl_b200.so, hand-written CUDA for sm_100a) replaces the PyTorch-eager forward of the
+ * reference's lifting network.  Every entry point cites the reference interface it stands in for
+ * (paths relative to the reference checkout, aghasemzadeh/OpenMPL):
+ *
+ *   MPL/lib/models/multiview_mpl.py:95-317   MultiView_MPL.__init__  (constructor kwargs  -> MplDesc / mpl_create)
+ *   MPL/lib/models/multiview_mpl.py:450-525  MultiView_MPL.forward   (poses, rays, centers -> mpl_forward)
+ *   MPL/lib/utils/utils.py:148-153           load_state_dict of checkpoints (-> mpl_param_* / mpl_pack_weights)
+ *   MPL/lib/core/evaluate.py:91-125          calc_mpjpe / calc_distance_per_dim (-> mpl_mpjpe_accumulate)
+ *   MPL/lib/dataset/joints_dataset_mpl.py:615-648,701-715,762-772,817-820,872-904
+ *                                            per-sample input construction (-> mpl_build_inputs)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - the library never allocates user-visible device memory: inputs, outputs, the packed weight blob and the
+ *     workspace are caller-owned device buffers, borrowed for the duration of the call;
+ *   - all work is enqueued on the caller's stream on the caller's current device; no hidden synchronisation;
+ *   - every function returns MPL_OK (0) or a negative MplStatus; mpl_last_error() gives the thread-local message;
+ *   - entry points are re-entrant; a handle may be used from one thread at a time (one handle per device replica,
+ *     like one nn.Module replica per GPU in the reference's DataParallel, MPL/run/valid_mpl.py:177-178).
+ */
+#ifndef MPL_B200_H_
+#define MPL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPL_ABI_VERSION 1
+
+typedef enum MplStatus {
+  MPL_OK = 0,
+  MPL_ERR_INVALID_ARGUMENT = -1, /* bad pointer / size / struct_size                                             */
+  MPL_ERR_CONFIG_RUNTIME = -2,   /* flag combination whose first forward raises RuntimeError in the reference    */
+  MPL_ERR_CONFIG_INDEX = -3,     /* flag combination whose first forward raises IndexError in the reference      */
+  MPL_ERR_CUDA = -4,             /* a CUDA runtime / driver call failed                                           */
+  MPL_ERR_WORKSPACE = -5,        /* workspace or packed buffer too small                                          */
+  MPL_ERR_UNSUPPORTED = -6       /* requested precision mode cannot serve this shape (no silent fallback)         */
+} MplStatus;
+
+/* Arithmetic of the Linear layers.  LayerNorm, softmax, residual stream and all accumulators are fp32 in every mode. */
+typedef enum MplPrecision {
+  MPL_PREC_FP32 = 0, /* fp32 operands, fp32 FMA (CUDA cores)                                        */
+  MPL_PREC_TF32 = 1, /* FPT projections: tcgen05 kind::tf32 (operands rounded to tf32), rest fp32   */
+  MPL_PREC_BF16 = 2  /* FPT projections: tcgen05 kind::f16 bf16 operands; SPT: bf16 mma; fp32 accum */
+} MplPrecision;
+
+/* POD mirror of the keyword arguments of MultiView_MPL.__init__ (multiview_mpl.py:95-117).
+ * Dropout / drop-path rates are omitted: the path is inference only (identity in eval, multiview_mpl.py:79). */
+typedef struct MplDesc {
+  int32_t struct_size; /* = sizeof(MplDesc); ABI guard */
+  int32_t num_joints;
+  int32_t in_chans;
+  int32_t embed_dim_ratio;
+  int32_t depth;
+  int32_t num_heads;
+  int32_t num_views;
+  int32_t hidden_dim;
+  float mlp_ratio;
+  float qk_scale; /* 0 = None -> head_dim^-0.5 (multiview_mpl.py:46) */
+  int32_t qkv_bias;
+  int32_t add_confidence_input;
+  int32_t mult_confidence_emb;
+  int32_t concat_confidence_emb;
+  int32_t confidence_input_as_third;
+  int32_t pose_3d_emb_learnable;
+  int32_t linear_weighted_mean;
+  int32_t add_3D_pos_encoding_in_Spatial;
+  int32_t input_rays_as_token;
+  int32_t add_3D_pos_encoding_to_rays;
+  int32_t confidence_as_attention_uncertainty_weight;
+  int32_t multiple_spatial_blocks;
+  int32_t no_transformer_spt;
+  int32_t no_transformer_fpt;
+  int32_t confidence_in_FPT;
+  int32_t deep_head;
+  int32_t head_kadkhod;
+  int32_t FPT_blocks_view_keypoint_tokens;
+  int32_t precision; /* MplPrecision */
+} MplDesc;
+
+typedef struct MplModel MplModel;          /* opaque host-side handle */
+typedef struct CUstream_st* mpl_stream_t;  /* == cudaStream_t */
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* mpl_last_error(void);
+int mpl_abi_version(void);
+
+/* MultiView_MPL.__init__ (multiview_mpl.py:95-317).  Host only.  Invalid flag combinations fail here with the
+ * status class of the exception the reference raises at its first forward. */
+int mpl_create(const MplDesc* desc, MplModel** out);
+void mpl_destroy(MplModel* m);
+
+/* state_dict contract (utils.py:148-153): entry i has the reference's key (without the `features.` prefix of
+ * MultiView_MPL_G) and element count; order = registration order of the reference module. */
+int mpl_num_params(const MplModel* m);
+int mpl_param_info(const MplModel* m, int index, const char** name, int64_t* numel, int32_t* is_int64);
+
+/* Derived dims (multiview_mpl.py:140-142,272-274): which = 0 tok_w, 1 fpt_dim, 2 fpt_tokens, 3 E, 4 spt_hidden,
+ * 5 fpt_hidden, 6 outputs (1, or 3 for head_kadkhod). */
+int64_t mpl_dim(const MplModel* m, int which);
+
+/* Weight repack: fp32 state_dict tensors (device pointers, in mpl_param_info order) -> one caller-owned blob
+ * holding what the kernels read (fp32 copies, BatchNorm folded into the preceding Linear, bf16 / tf32 operand
+ * copies of the FPT projection matrices).  Call again after the parameters change. */
+size_t mpl_packed_bytes(const MplModel* m);
+int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, void* packed, size_t packed_bytes,
+                     mpl_stream_t stream);
+
+/* Workspace for batches of up to `max_batch` poses (the forward processes larger batches in chunks of
+ * mpl_chunk_poses(), so the workspace stops growing there). */
+size_t mpl_workspace_bytes(const MplModel* m, int64_t max_batch);
+int64_t mpl_chunk_poses(const MplModel* m);
+int mpl_set_chunk_poses(MplModel* m, int64_t chunk);
+
+/* MultiView_MPL.forward (multiview_mpl.py:450-525), eval mode.
+ *   poses[v]   -> view v 2D joints (x, y, conf)  [B, J, 3] fp32, consecutive poses `pose_stride` floats apart
+ *   rays[v]    -> view v ray points              [B, J, 3] fp32, same stride
+ *   centers[v] -> view v camera centre           [B, 1, 3] fp32, consecutive poses `center_stride` floats apart
+ *                 (the reference's list-of-views convention, core/function_mpl.py:344-350, is V separate
+ *                  tensors: stride J*3 and 3; one packed [B,V,J,3] tensor is the same call with stride V*J*3)
+ *   out        -> [B, J, 3] fp32;  aux1/aux2 -> the two intermediate predictions of head_kadkhod (else NULL)
+ * The pointer arrays are host arrays of V device pointers. */
+int mpl_forward(MplModel* m, const void* packed, const float* const* poses, const float* const* rays,
+                const float* const* centers, int64_t pose_stride, int64_t center_stride, float* out, float* aux1,
+                float* aux2, int64_t batch, void* workspace, size_t workspace_bytes, mpl_stream_t stream);
+
+/* Number of kernel launches the last mpl_forward on this handle enqueued (bench.py's gpu_launches). */
+int64_t mpl_last_launch_count(const MplModel* m);
+
+/* Optional per-launch timing with CUDA events on the caller's stream (the reference's only profiling hook is an
+ * unsynchronised time.time() around the model call, core/function_mpl.py:346-351).  While enabled, every kernel
+ * launch of mpl_forward is bracketed by two events; mpl_profile_collect waits for the last forward's events and
+ * returns milliseconds and launch counts per kernel category (mpl_profile_category_name). */
+int mpl_set_profile(MplModel* m, int enabled);
+int mpl_profile_categories(void);
+const char* mpl_profile_category_name(int category);
+int mpl_profile_collect(MplModel* m, double* ms_per_category, int64_t* launches_per_category, int n);
+
+/* calc_mpjpe / calc_distance_per_dim (evaluate.py:91-125) + the unit / root-centring / confidence-mask rules of
+ * core/function_mpl.py:674-687, as running fp64 sums so ranks can be combined with one all-reduce.
+ *   acc layout (doubles): [0,J) sum_b ||pred-gt|| per joint (absolute); [J,2J) same, root-relative;
+ *   [2J,5J) sum_b |pred-gt| per joint-dim over unmasked entries (absolute); [5J,8J) same, root-relative;
+ *   [8J,11J) unmasked count per joint-dim; [11J] pose count.
+ *   conf3d may be NULL (no masking); unit_scale = 100 if OUTPUT_IN_METER else 1. */
+#define MPL_METRIC_ACC_LEN(J) (11 * (J) + 1)
+int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t batch, int num_joints,
+                         float unit_scale, double* acc, mpl_stream_t stream);
+
+/* Per-sample input construction of the dataset (joints_dataset_mpl.py:615-648,701-715,762-772,817-820,872-904),
+ * batched: raw detector output (u, v, conf) in pixels + per-view calibration -> the model's poses / rays / centers.
+ *   pix   [B, V, J, 3] fp32 (u, v, conf);  calib [V, 18] fp64 = R (9, row-major world->cam), t (3), fx, fy, cx, cy, w, h
+ *   poses / rays [B, V, J, 3], centers [B, V, 1, 3] fp32 (packed layout accepted by mpl_forward). */
+int mpl_build_inputs(const float* pix, const double* calib, int64_t batch, int num_views, int num_joints, float* poses,
+                     float* rays, float* centers, mpl_stream_t stream);
+
+/* ---- unit-test hooks for the building blocks (used by tests/ only) ------------------------------------------- */
+/* Y[M,N] = epilogue(A[M,K] . W[N,K]^T): the tcgen05 projection kernel in isolation.
+ *   dtype: MPL_PREC_BF16 (A, W bf16) or MPL_PREC_TF32 (A, W fp32 pre-rounded to tf32)
+ *   epilogue: 0 bias -> bf16/fp32 out per `out_fp32`; 1 bias+GELU; 2 bias + residual(fp32, in place in Y). */
+int mpl_test_gemm(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
+                  int epilogue, int out_fp32, mpl_stream_t stream);
+/* 1: one CTA per 128x256 tile (cta_group::1); 2: CTA pair per 256x256 tile (cta_group::2, cluster 2x1x1). Process-wide. */
+int mpl_set_gemm_cta_group(int cta_group);
+int mpl_get_gemm_cta_group(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPL_B200_H_ */

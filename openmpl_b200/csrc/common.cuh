@@ -1,0 +1,66 @@
+// Shared host/device helpers of libmpl_b200 (B200 / sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/mpl_b200.h"
+
+namespace mpl {
+
+// thread-local error text behind mpl_last_error()
+void set_error(const char* fmt, ...);
+
+#define MPL_CUDA(expr)                                                                               \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      ::mpl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return MPL_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+#define MPL_LAUNCH_CHECK()                                                                                \
+  do {                                                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                                 \
+    if (e__ != cudaSuccess) {                                                                             \
+      ::mpl::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return MPL_ERR_CUDA;                                                                                \
+    }                                                                                                     \
+  } while (0)
+
+#define MPL_TRY(expr)          \
+  do {                         \
+    int s__ = (expr);          \
+    if (s__ != MPL_OK) return s__; \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// nn.GELU() default: exact erf form (multiview_mpl.py:22,27)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_GELU) return gelu_erf(x);
+  if (act == ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace mpl

@@ -1,0 +1,115 @@
+// Launchers of the CUDA kernels behind mpl_forward.  Shapes use the reference's names:
+// B poses, V views, J joints, d = embed_dim_ratio, H heads, D = FPT width.
+#pragma once
+#include "common.cuh"
+
+namespace mpl {
+
+constexpr int kMaxViews = 16;
+
+// ---- K1: joint embedding (multiview_mpl.py:349-398) -------------------------------------------------------------
+struct EmbedArgs {
+  const float* poses[kMaxViews];
+  const float* rays[kMaxViews];
+  const float* centers[kMaxViews];
+  const float* We[kMaxViews];  // Spatial_patch_to_embedding[.v].weight [d, in_ch]
+  const float* be[kMaxViews];  //                                 .bias [d]
+  const float* Wc[kMaxViews];  // confidence_to_embedding[.v].weight [d, 1] (or null)
+  const float* bc[kMaxViews];
+  const float* Ps[kMaxViews];  // Spatial_pos_embed[.v] [J, d]
+  const float* pos3d;          // add_3D_pos_encoding_in_Spatial: learnable table [J, pos3d_ld] ...
+  const float* Wl;             // ... or pos_3d_linear.weight [d, 3] / .bias
+  const float* bl;
+  int64_t pose_stride, center_stride, B;
+  int pos3d_ld, in_ch, add_conf, mult_conf, spatial_pos_mode;  // 0 none, 1 learnable, 2 linear(normalize(ray-center))
+  int V, J, d;
+  float* x;     // [V, B, J, d]
+  float* conf;  // [V, B, J] or null (confidence_as_attention_uncertainty_weight)
+};
+int launch_embed(const EmbedArgs& a, cudaStream_t s);
+
+// ---- FPT token build (multiview_mpl.py:463-499) ------------------------------------------------------------------
+struct TokenArgs {
+  const float* xn;  // Spatial_norm output [V, B, J, d]
+  const float* poses[kMaxViews];
+  const float* rays[kMaxViews];
+  const float* centers[kMaxViews];
+  int64_t pose_stride, center_stride, B;
+  const float* Wcf;  // confidence_to_embedding_FPT weight [d,1] / bias (or null)
+  const float* bcf;
+  const float* Wr;  // ray_to_embedding [d,3] / bias (or null)
+  const float* br;
+  const float* pos_table;  // learnable pos_3d_embed / pos_3d_view_coding [J, pos_w] (or null)
+  const float* Wl;         // pos_3d_linear [pos_w, 3] / bias (used when pos_table == null)
+  const float* bl;
+  int pos_w;
+  int ray_layout;  // 0 none, 1 interleave (cat dim=2), 2 append (cat dim=1)
+  int V, J, d, tok_w;
+  float* tok;           // [B, V, tok_w] fp32
+};
+int launch_token_build(const TokenArgs& a, cudaStream_t s);
+
+// ---- LayerNorm over the last dim; column e of the output reads input column (e / seg_len) * seg_stride + e % seg_len
+int launch_layernorm(const float* x, int64_t ldx, int seg_len, int seg_stride, const float* w, const float* b, float eps,
+                     float* y, int64_t ldy, int64_t rows, int C, cudaStream_t s);
+// same, bf16 output (A operand of the tcgen05 projections)
+int launch_layernorm_bf16(const float* x, int64_t ldx, const float* w, const float* b, float eps, __nv_bfloat16* y,
+                          int64_t ldy, int64_t rows, int C, cudaStream_t s);
+// same, fp32 output rounded to tf32 (A operand of the kind::tf32 projections)
+int launch_layernorm_tf32(const float* x, int64_t ldx, const float* w, const float* b, float eps, float* y, int64_t ldy,
+                          int64_t rows, int C, cudaStream_t s);
+
+// ---- fp32 CUDA-core Linear: Y = act(X W^T + bias) (+ R) ------------------------------------------------------------
+int launch_linear_f32(const float* X, int64_t lda, const float* W, const float* bias, const float* R, int64_t ldr,
+                      float* Y, int64_t ldc, int64_t M, int N, int K, int act, cudaStream_t s);
+
+// ---- generic attention core over sets of N tokens (multiview_mpl.py:53-64): qkv [sets*N, 3C] -> out [sets*N, C] ---
+// conf (or null): [sets*N] post-softmax query-row scale (multiview_mpl.py:61-62)
+int launch_attention_f32(const float* qkv, float* out, int64_t sets, int N, int H, int hd, float scale, const float* conf,
+                         cudaStream_t s);
+// bf16 in / bf16 out variant used behind the tensor-core QKV projection
+int launch_attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t sets, int N, int H, int hd, float scale,
+                          cudaStream_t s);
+// fp32 in / tf32-rounded fp32 out variant
+int launch_attention_tf32(const float* qkv, float* out, int64_t sets, int N, int H, int hd, float scale, cudaStream_t s);
+
+// ---- Conv1d(V -> 1, k = 1) over the view axis (multiview_mpl.py:281,445): y[b,e] = sum_v w[v] x[b,v,e] + bias -------
+int launch_view_mean(const float* x, const float* w, const float* bias, float* y, int64_t B, int V, int E, cudaStream_t s);
+
+// ---- K5: fused head for the default head (multiview_mpl.py:425-446,517-523):
+//      strip ray channels -> View_norm -> view-weighted mean -> LayerNorm(1e-5) -> Linear(E -> 3J) ------------------
+struct HeadArgs {
+  const float* tok;  // [B, V, tok_w] fp32 residual stream after the FPT
+  int64_t B;
+  int V, tok_w, E, seg_len, seg_stride, out_dim;
+  const float* vn_w; const float* vn_b;  // View_norm
+  const float* wm_w; const float* wm_b;  // weighted_mean (Conv1d) [V], [1]
+  const float* hn_w; const float* hn_b;  // head.0 LayerNorm
+  const float* hw;   const float* hb;    // head.1 Linear [out_dim, E]
+  float* out;                            // [B, out_dim]
+};
+int launch_head_fused(const HeadArgs& a, cudaStream_t s);
+
+// ---- pack helpers ---------------------------------------------------------------------------------------------------
+// Linear followed by eval-mode BatchNorm1d folded into one Linear: W' = W * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(var+eps) + beta
+int launch_fold_bn(const float* W, const float* b, const float* g, const float* beta, const float* mean, const float* var,
+                   float eps, float* Wf, float* bf, int N, int K, cudaStream_t s);
+int launch_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);
+int launch_to_tf32(const float* src, float* dst, int64_t n, cudaStream_t s);
+
+// ---- tcgen05 projection GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
+enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESIDUAL = 2 };
+// A [M,K] row-major (lda = K), W [N,K] row-major, both bf16 (dtype MPL_PREC_BF16) or tf32-rounded fp32 (MPL_PREC_TF32).
+// EPI_BIAS / EPI_BIAS_GELU write Y [M,N] in the operand dtype (or fp32 if out_fp32); EPI_BIAS_RESIDUAL does
+// Y(fp32) += A W^T + bias in place.
+int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
+                        int epilogue, int out_fp32, cudaStream_t s);
+bool gemm_tcgen05_supports(int N, int K, int dtype);
+
+// ---- metric + input builder -----------------------------------------------------------------------------------------
+int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t B, int J, float unit_scale,
+                            double* acc, cudaStream_t s);
+int launch_build_inputs(const float* pix, const double* calib, int64_t B, int V, int J, float* poses, float* rays,
+                        float* centers, cudaStream_t s);
+
+}  // namespace mpl

@@ -1,0 +1,570 @@
+// Shape-generic CUDA kernels of the MPL lifter forward: every constructor flag of the reference is served by these
+// (fp32 CUDA-core arithmetic).  The hot configurations additionally have tensor-core kernels (gemm_tcgen05.cu,
+// spt_fused.cu) that replace the Linear / attention launches.
+#include "kernels.cuh"
+
+namespace mpl {
+
+__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 joint embedding.  One thread per output element of x [V, B, J, d]; the 12-byte pose record is a warp broadcast.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
+  const int64_t total = (int64_t)a.V * a.B * a.J * a.d;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % a.d);
+  int64_t row = idx / a.d;
+  const int j = (int)(row % a.J);
+  row /= a.J;
+  const int64_t b = row % a.B;
+  const int v = (int)(row / a.B);
+  const float* p = a.poses[v] + b * a.pose_stride + j * 3;
+  const float px = __ldg(p), py = __ldg(p + 1), pc = __ldg(p + 2);
+  const float* W = a.We[v] + c * a.in_ch;
+  float val = __ldg(a.be[v] + c);
+  val = fmaf(__ldg(W), px, val);
+  val = fmaf(__ldg(W + 1), py, val);
+  if (a.in_ch == 3) val = fmaf(__ldg(W + 2), pc, val);
+  if (a.add_conf || a.mult_conf) {
+    const float ce = fmaf(__ldg(a.Wc[v] + c), pc, __ldg(a.bc[v] + c));
+    if (a.add_conf) val += ce;
+    if (a.mult_conf) val *= ce;
+  }
+  val += __ldg(a.Ps[v] + j * a.d + c);
+  if (a.spatial_pos_mode == 1) {
+    val += __ldg(a.pos3d + j * a.pos3d_ld + c);
+  } else if (a.spatial_pos_mode == 2) {
+    const float* r = a.rays[v] + b * a.pose_stride + j * 3;
+    const float* ce = a.centers[v] + b * a.center_stride;
+    const float dx = __ldg(r) - __ldg(ce), dy = __ldg(r + 1) - __ldg(ce + 1), dz = __ldg(r + 2) - __ldg(ce + 2);
+    const float inv = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);  // F.normalize eps
+    float pe = __ldg(a.bl + c);
+    pe = fmaf(__ldg(a.Wl + c * 3), dx * inv, pe);
+    pe = fmaf(__ldg(a.Wl + c * 3 + 1), dy * inv, pe);
+    pe = fmaf(__ldg(a.Wl + c * 3 + 2), dz * inv, pe);
+    val += pe;
+  }
+  a.x[idx] = val;
+  if (a.conf != nullptr && c == 0) a.conf[(v * a.B + b) * a.J + j] = pc;
+}
+
+int launch_embed(const EmbedArgs& a, cudaStream_t s) {
+  const int64_t total = (int64_t)a.V * a.B * a.J * a.d;
+  if (total == 0) return MPL_OK;
+  embed_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(a);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FPT token build: one thread per element of tok [B, V, tok_w].
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ray_dir(const TokenArgs& a, int v, int64_t b, int j, float& dx, float& dy, float& dz) {
+  const float* r = a.rays[v] + b * a.pose_stride + j * 3;
+  const float* ce = a.centers[v] + b * a.center_stride;
+  dx = __ldg(r) - __ldg(ce);
+  dy = __ldg(r + 1) - __ldg(ce + 1);
+  dz = __ldg(r + 2) - __ldg(ce + 2);
+}
+
+__global__ void __launch_bounds__(256) token_build_kernel(const TokenArgs a) {
+  const int64_t total = a.B * a.V * (int64_t)a.tok_w;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int e = (int)(idx % a.tok_w);
+  const int64_t bv = idx / a.tok_w;
+  const int v = (int)(bv % a.V);
+  const int64_t b = bv / a.V;
+  const int d = a.d, J = a.J;
+  int j, c;             // joint, channel inside the (possibly 2d-wide) joint slot
+  bool is_ray = false;  // this element is a ray-embedding channel
+  bool add_pos = true;
+  int pos_c;  // channel inside the positional table row
+  if (a.ray_layout == 1) {  // [J, 2d]: [x | ray]
+    j = e / (2 * d);
+    c = e % (2 * d);
+    pos_c = c;
+    if (c >= d) { is_ray = true; c -= d; }
+  } else if (a.ray_layout == 2) {  // [2J, d]: J pose tokens then J ray tokens
+    const int t = e / d;
+    c = e % d;
+    pos_c = c;
+    if (t >= J) { is_ray = true; j = t - J; add_pos = false; } else { j = t; }
+  } else {
+    j = e / d;
+    c = e % d;
+    pos_c = c;
+  }
+  float val;
+  float dx = 0.f, dy = 0.f, dz = 0.f;
+  const bool need_dir = is_ray || (add_pos && a.pos_table == nullptr);
+  if (need_dir) ray_dir(a, v, b, j, dx, dy, dz);
+  if (is_ray) {
+    val = __ldg(a.br + c);
+    val = fmaf(__ldg(a.Wr + c * 3), dx, val);
+    val = fmaf(__ldg(a.Wr + c * 3 + 1), dy, val);
+    val = fmaf(__ldg(a.Wr + c * 3 + 2), dz, val);
+  } else {
+    val = a.xn[(((int64_t)v * a.B + b) * J + j) * d + c];
+    if (a.Wcf != nullptr) {
+      const float pc = __ldg(a.poses[v] + b * a.pose_stride + j * 3 + 2);
+      val += fmaf(__ldg(a.Wcf + c), pc, __ldg(a.bcf + c));
+    }
+  }
+  if (add_pos) {
+    if (a.pos_table != nullptr) {
+      val += __ldg(a.pos_table + j * a.pos_w + pos_c);
+    } else {
+      const float inv = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+      float pe = __ldg(a.bl + pos_c);
+      pe = fmaf(__ldg(a.Wl + pos_c * 3), dx * inv, pe);
+      pe = fmaf(__ldg(a.Wl + pos_c * 3 + 1), dy * inv, pe);
+      pe = fmaf(__ldg(a.Wl + pos_c * 3 + 2), dz * inv, pe);
+      val += pe;
+    }
+  }
+  a.tok[idx] = val;
+}
+
+int launch_token_build(const TokenArgs& a, cudaStream_t s) {
+  const int64_t total = a.B * a.V * (int64_t)a.tok_w;
+  if (total == 0) return MPL_OK;
+  token_build_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(a);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, two passes over the row (second one hits L1), biased variance like nn.LayerNorm.
+// MODE 0: fp32 out, 1: bf16 out, 2: tf32-rounded fp32 out.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MODE, typename TO>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx, int seg_len, int seg_stride,
+                                                        const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                                        TO* __restrict__ y, int64_t ldy, int64_t rows, int C) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * ldx;
+  const bool plain = (seg_len == seg_stride);
+  float s = 0.f;
+  for (int e = lane; e < C; e += 32) {
+    const int col = plain ? e : (e / seg_len) * seg_stride + (e % seg_len);
+    s += xr[col];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int e = lane; e < C; e += 32) {
+    const int col = plain ? e : (e / seg_len) * seg_stride + (e % seg_len);
+    const float t = xr[col] - mean;
+    q = fmaf(t, t, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  TO* yr = y + row * ldy;
+  for (int e = lane; e < C; e += 32) {
+    const int col = plain ? e : (e / seg_len) * seg_stride + (e % seg_len);
+    float o = (xr[col] - mean) * rstd * __ldg(w + e) + __ldg(b + e);
+    if (MODE == 2) o = round_tf32(o);
+    stf(yr + e, o);
+  }
+}
+
+// Vectorised LayerNorm for the FPT widths (C % 128 == 0 is not required; C % 4 == 0 and C <= 32*4*MAXV4): the row
+// lives in registers, one pass over HBM.  Used for the bf16 / tf32 operand-producing LayerNorms.
+template <int MODE, typename TO, int MAXV4>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                            const float* __restrict__ b, float eps, TO* __restrict__ y,
+                                                            int64_t ldy, int64_t rows, int C) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const int n4 = C >> 2;
+  float4 v[MAXV4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int e4 = lane + i * 32;
+    if (e4 < n4) {
+      v[i] = xr[e4];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int e4 = lane + i * 32;
+    if (e4 < n4) {
+      const float t0 = v[i].x - mean, t1 = v[i].y - mean, t2 = v[i].z - mean, t3 = v[i].w - mean;
+      q += t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int e4 = lane + i * 32;
+    if (e4 < n4) {
+      const float4 g = __ldg(w4 + e4), bb = __ldg(b4 + e4);
+      float o0 = (v[i].x - mean) * rstd * g.x + bb.x;
+      float o1 = (v[i].y - mean) * rstd * g.y + bb.y;
+      float o2 = (v[i].z - mean) * rstd * g.z + bb.z;
+      float o3 = (v[i].w - mean) * rstd * g.w + bb.w;
+      if constexpr (MODE == 1) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(y + row * ldy)[e4] = pk;
+      } else {
+        if (MODE == 2) { o0 = round_tf32(o0); o1 = round_tf32(o1); o2 = round_tf32(o2); o3 = round_tf32(o3); }
+        reinterpret_cast<float4*>(y + row * ldy)[e4] = make_float4(o0, o1, o2, o3);
+      }
+    }
+  }
+}
+
+template <int MODE, typename TO>
+static int launch_ln_any(const float* x, int64_t ldx, int seg_len, int seg_stride, const float* w, const float* b, float eps,
+                         TO* y, int64_t ldy, int64_t rows, int C, cudaStream_t s) {
+  if (rows == 0) return MPL_OK;
+  const unsigned grid = (unsigned)ceil_div(rows, 8);
+  const bool vec_ok = (seg_len == seg_stride) && (C % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w) |
+                        reinterpret_cast<uintptr_t>(b)) % 16 == 0);
+  if (vec_ok && C <= 32 * 4 * 5) {
+    layernorm_vec_kernel<MODE, TO, 5><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C);
+  } else if (vec_ok && C <= 32 * 4 * 9) {
+    layernorm_vec_kernel<MODE, TO, 9><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C);
+  } else if (vec_ok && C <= 32 * 4 * 17) {
+    layernorm_vec_kernel<MODE, TO, 17><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C);
+  } else {
+    layernorm_kernel<MODE, TO><<<grid, 256, 0, s>>>(x, ldx, seg_len, seg_stride, w, b, eps, y, ldy, rows, C);
+  }
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+int launch_layernorm(const float* x, int64_t ldx, int seg_len, int seg_stride, const float* w, const float* b, float eps,
+                     float* y, int64_t ldy, int64_t rows, int C, cudaStream_t s) {
+  return launch_ln_any<0, float>(x, ldx, seg_len, seg_stride, w, b, eps, y, ldy, rows, C, s);
+}
+int launch_layernorm_bf16(const float* x, int64_t ldx, const float* w, const float* b, float eps, __nv_bfloat16* y,
+                          int64_t ldy, int64_t rows, int C, cudaStream_t s) {
+  return launch_ln_any<1, __nv_bfloat16>(x, ldx, C, C, w, b, eps, y, ldy, rows, C, s);
+}
+int launch_layernorm_tf32(const float* x, int64_t ldx, const float* w, const float* b, float eps, float* y, int64_t ldy,
+                          int64_t rows, int C, cudaStream_t s) {
+  return launch_ln_any<2, float>(x, ldx, C, C, w, b, eps, y, ldy, rows, C, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fp32 Linear on CUDA cores: 64x64 output tile, K step 16, 256 threads x (4x4) accumulators.  Any M, N, K, strides.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int LBM = 64, LBN = 64, LBK = 16;
+
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ X, int64_t lda, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, const float* R, int64_t ldr,
+                                                         float* Y, int64_t ldc, int64_t M, int N, int K, int act) {
+  __shared__ float As[LBK][LBM + 4];
+  __shared__ float Bs[LBK][LBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * LBM;
+  const int n0 = blockIdx.y * LBN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid >> 2;         // 0..63 : row of the tile this thread loads
+  const int lk = (tid & 3) * 4;    // 0,4,8,12 : first k of its 4 consecutive elements
+  for (int k0 = 0; k0 < K; k0 += LBK) {
+    {
+      const int64_t m = m0 + lr;
+      const float* src = X + m * lda + k0 + lk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[lk + i][lr] = (m < M && k0 + lk + i < K) ? src[i] : 0.f;
+      const int n = n0 + lr;
+      const float* wsrc = W + (int64_t)n * K + k0 + lk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[lk + i][lr] = (n < N && k0 + lk + i < K) ? __ldg(wsrc + i) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LBK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w};
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += __ldg(bias + n);
+      v = apply_act(v, act);
+      if (R != nullptr) v += R[m * ldr + n];
+      Y[m * ldc + n] = v;
+    }
+  }
+}
+
+int launch_linear_f32(const float* X, int64_t lda, const float* W, const float* bias, const float* R, int64_t ldr, float* Y,
+                      int64_t ldc, int64_t M, int N, int K, int act, cudaStream_t s) {
+  if (M == 0 || N == 0) return MPL_OK;
+  dim3 grid((unsigned)ceil_div(M, LBM), (unsigned)ceil_div(N, LBN));
+  linear_f32_kernel<<<grid, 256, 0, s>>>(X, lda, W, bias, R, ldr, Y, ldc, M, N, K, act);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Generic attention core.  One warp per (set, head, query row); probabilities staged in shared memory.
+// Narrow heads (hd <= 16: the 17-token spatial sets and the V*J keypoint-token sets): lanes sweep the keys.
+// Wide heads (view tokens, hd = D/H): lanes sweep the head channels, scores by warp reduction.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename TI, typename TO, bool TF32_OUT>
+__global__ void __launch_bounds__(128) attention_kernel(const TI* __restrict__ qkv, TO* __restrict__ out, int64_t sets, int N,
+                                                        int H, int hd, float scale, const float* __restrict__ conf) {
+  extern __shared__ float psm[];  // [4 warps][N]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t task = (int64_t)blockIdx.x * 4 + warp;
+  const int64_t total = sets * H * N;
+  if (task >= total) return;
+  const int i = (int)(task % N);
+  const int h = (int)((task / N) % H);
+  const int64_t set = task / ((int64_t)N * H);
+  const int C = H * hd;
+  const int64_t ld = 3 * (int64_t)C;
+  const TI* base = qkv + set * N * ld;
+  const TI* q = base + (int64_t)i * ld + h * hd;
+  const TI* kb = base + C + h * hd;
+  const TI* vb = base + 2 * C + h * hd;
+  float* p = psm + warp * N;
+  float mx = -INFINITY;
+  if (hd <= 16) {
+    float qr[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) qr[t] = (t < hd) ? ldf(q + t) : 0.f;
+    for (int j = lane; j < N; j += 32) {
+      const TI* kj = kb + (int64_t)j * ld;
+      float sc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        if (t < hd) sc = fmaf(qr[t], ldf(kj + t), sc);
+      sc *= scale;
+      p[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+  } else {
+    for (int j = 0; j < N; ++j) {
+      const TI* kj = kb + (int64_t)j * ld;
+      float part = 0.f;
+      for (int t = lane; t < hd; t += 32) part = fmaf(ldf(q + t), ldf(kj + t), part);
+      part = warp_sum(part) * scale;
+      if (lane == 0) p[j] = part;
+      mx = fmaxf(mx, part);
+    }
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    const float e = expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  float norm = 1.0f / sum;
+  if (conf != nullptr) norm *= __ldg(conf + set * N + i);  // post-softmax query-row scaling, multiview_mpl.py:61-62
+  __syncwarp();
+  TO* o = out + (set * N + i) * (int64_t)C + h * hd;
+  for (int t = lane; t < hd; t += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j) acc = fmaf(p[j], ldf(vb + (int64_t)j * ld + t), acc);
+    acc *= norm;
+    if (TF32_OUT) acc = round_tf32(acc);
+    stf(o + t, acc);
+  }
+}
+
+template <typename TI, typename TO, bool TF32_OUT>
+static int launch_attention_any(const TI* qkv, TO* out, int64_t sets, int N, int H, int hd, float scale, const float* conf,
+                                cudaStream_t s) {
+  const int64_t total = sets * H * N;
+  if (total == 0) return MPL_OK;
+  const size_t smem = 4 * (size_t)N * sizeof(float);
+  attention_kernel<TI, TO, TF32_OUT><<<(unsigned)ceil_div(total, 4), 128, smem, s>>>(qkv, out, sets, N, H, hd, scale, conf);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+int launch_attention_f32(const float* qkv, float* out, int64_t sets, int N, int H, int hd, float scale, const float* conf,
+                         cudaStream_t s) {
+  return launch_attention_any<float, float, false>(qkv, out, sets, N, H, hd, scale, conf, s);
+}
+int launch_attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t sets, int N, int H, int hd, float scale,
+                          cudaStream_t s) {
+  return launch_attention_any<__nv_bfloat16, __nv_bfloat16, false>(qkv, out, sets, N, H, hd, scale, nullptr, s);
+}
+int launch_attention_tf32(const float* qkv, float* out, int64_t sets, int N, int H, int hd, float scale, cudaStream_t s) {
+  return launch_attention_any<float, float, true>(qkv, out, sets, N, H, hd, scale, nullptr, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Conv1d(V -> 1, k = 1) over the view axis.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) view_mean_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int64_t B, int V,
+                                                        int E) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * E) return;
+  const int e = (int)(idx % E);
+  const int64_t b = idx / E;
+  float acc = __ldg(bias);
+  for (int v = 0; v < V; ++v) acc = fmaf(__ldg(w + v), x[(b * V + v) * E + e], acc);
+  y[idx] = acc;
+}
+
+int launch_view_mean(const float* x, const float* w, const float* bias, float* y, int64_t B, int V, int E, cudaStream_t s) {
+  if (B * E == 0) return MPL_OK;
+  view_mean_kernel<<<(unsigned)ceil_div(B * E, 256), 256, 0, s>>>(x, w, bias, y, B, V, E);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K5 fused default head.  One CTA (128 threads) per pose: the V rows of E channels are normalised (View_norm),
+// combined with the Conv1d weights, normalised again (eps 1e-5) in shared memory, then each warp computes output
+// channels of the E -> 3J Linear by warp-reduced dot products.  Reads V*E floats, writes 3J floats per pose.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(128) head_fused_kernel(const HeadArgs a) {
+  extern __shared__ float sm[];  // pooled [E]
+  __shared__ float red[4];
+  float* pooled = sm;
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int E = a.E;
+  for (int e = tid; e < E; e += 128) pooled[e] = __ldg(a.wm_b);
+  for (int v = 0; v < a.V; ++v) {
+    const float* row = a.tok + (b * a.V + v) * (int64_t)a.tok_w;
+    float s = 0.f;
+    for (int e = tid; e < E; e += 128) s += row[(e / a.seg_len) * a.seg_stride + (e % a.seg_len)];
+    const float mean = block_sum_128(s, red) / (float)E;
+    float q = 0.f;
+    for (int e = tid; e < E; e += 128) {
+      const float t = row[(e / a.seg_len) * a.seg_stride + (e % a.seg_len)] - mean;
+      q = fmaf(t, t, q);
+    }
+    const float rstd = rsqrtf(block_sum_128(q, red) / (float)E + 1e-6f);
+    const float wv = __ldg(a.wm_w + v);
+    for (int e = tid; e < E; e += 128) {
+      const float xv = row[(e / a.seg_len) * a.seg_stride + (e % a.seg_len)];
+      pooled[e] += wv * ((xv - mean) * rstd * __ldg(a.vn_w + e) + __ldg(a.vn_b + e));
+    }
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int e = tid; e < E; e += 128) s += pooled[e];
+  const float mean = block_sum_128(s, red) / (float)E;
+  float q = 0.f;
+  for (int e = tid; e < E; e += 128) {
+    const float t = pooled[e] - mean;
+    q = fmaf(t, t, q);
+  }
+  const float rstd = rsqrtf(block_sum_128(q, red) / (float)E + 1e-5f);  // head LayerNorm: default eps (multiview_mpl.py:284)
+  __syncthreads();
+  for (int e = tid; e < E; e += 128) pooled[e] = (pooled[e] - mean) * rstd * __ldg(a.hn_w + e) + __ldg(a.hn_b + e);
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int o = warp; o < a.out_dim; o += 4) {
+    const float* wr = a.hw + (int64_t)o * E;
+    float acc = 0.f;
+    for (int e = lane; e < E; e += 32) acc = fmaf(pooled[e], __ldg(wr + e), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) a.out[b * a.out_dim + o] = acc + __ldg(a.hb + o);
+  }
+}
+
+int launch_head_fused(const HeadArgs& a, cudaStream_t s) {
+  if (a.B == 0) return MPL_OK;
+  head_fused_kernel<<<(unsigned)a.B, 128, (size_t)a.E * sizeof(float), s>>>(a);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pack helpers
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void fold_bn_kernel(const float* W, const float* b, const float* g, const float* beta, const float* mean,
+                               const float* var, float eps, float* Wf, float* bf, int N, int K) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * K) return;
+  const int n = (int)(idx / K);
+  const float sc = g[n] / sqrtf(var[n] + eps);
+  Wf[idx] = W[idx] * sc;
+  if (idx % K == 0) bf[n] = (b[n] - mean[n]) * sc + beta[n];
+}
+int launch_fold_bn(const float* W, const float* b, const float* g, const float* beta, const float* mean, const float* var,
+                   float eps, float* Wf, float* bf, int N, int K, cudaStream_t s) {
+  fold_bn_kernel<<<(unsigned)ceil_div((int64_t)N * K, 256), 256, 0, s>>>(W, b, g, beta, mean, var, eps, Wf, bf, N, K);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+__global__ void to_bf16_kernel(const float* src, __nv_bfloat16* dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+int launch_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return MPL_OK;
+  to_bf16_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, dst, n);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+__global__ void to_tf32_kernel(const float* src, float* dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = round_tf32(src[i]);
+}
+int launch_to_tf32(const float* src, float* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return MPL_OK;
+  to_tf32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, dst, n);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+}  // namespace mpl

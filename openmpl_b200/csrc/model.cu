@@ -1,0 +1,912 @@
+// Host side of libmpl_b200: the constructor contract (parameter table, derived dims, validity), weight packing,
+// workspace layout and the forward orchestration (multiview_mpl.py:95-317, 349-525), plus the extern "C" boundary.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace mpl {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+void set_gemm_cta_group(int cg);
+int get_gemm_cta_group();
+
+struct ParamInfo {
+  std::string name;
+  int64_t numel;
+  bool is_int64;
+  size_t offset;  // byte offset of the fp32 copy inside the packed blob
+};
+
+struct Derived {  // extra packed tensors computed from the parameters
+  std::string name;
+  int64_t numel;
+  int esz;
+  size_t offset;
+};
+
+struct BnFold {
+  std::string lin, bn;
+  int N, K;
+};
+
+}  // namespace mpl
+
+using namespace mpl;
+
+struct MplModel {
+  MplDesc d;
+  // derived dims (spec.make_config)
+  int J, V, dim, H, depth, in_ch, tok_w, fpt_dim, fpt_tokens, E, pos3d_lin_out, pos3d_w, spt_hidden, fpt_hidden;
+  bool add_conf, mult_conf, conf_emb, multi;
+  int ray_layout;  // 0 none, 1 interleave, 2 append
+  int n_out;
+  bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
+  std::vector<ParamInfo> params;
+  std::unordered_map<std::string, int> index;
+  std::vector<Derived> derived;
+  std::unordered_map<std::string, int> dindex;
+  std::vector<BnFold> folds;
+  size_t packed_bytes = 0;
+  int64_t chunk = 32768;
+  int64_t launches = 0;
+  // optional per-launch CUDA-event profiling (bench.py's roofline numbers come from here)
+  bool profile = false;
+  struct ProfRec { int cat; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+};
+
+namespace mpl {
+
+static void add_param(MplModel* m, const std::string& name, int64_t numel, bool is_int64 = false) {
+  m->index[name] = (int)m->params.size();
+  m->params.push_back({name, numel, is_int64, 0});
+}
+static void add_linear(MplModel* m, const std::string& p, int out_f, int in_f) {
+  add_param(m, p + "weight", (int64_t)out_f * in_f);
+  add_param(m, p + "bias", out_f);
+}
+static void add_bn(MplModel* m, const std::string& p, int n) {
+  add_param(m, p + "weight", n);
+  add_param(m, p + "bias", n);
+  add_param(m, p + "running_mean", n);
+  add_param(m, p + "running_var", n);
+  add_param(m, p + "num_batches_tracked", 1, true);
+}
+static void add_block(MplModel* m, const std::string& p, int dim, int hidden, bool qkv_bias) {
+  add_param(m, p + "norm1.weight", dim);
+  add_param(m, p + "norm1.bias", dim);
+  add_param(m, p + "attn.qkv.weight", (int64_t)3 * dim * dim);
+  if (qkv_bias) add_param(m, p + "attn.qkv.bias", 3 * dim);
+  add_linear(m, p + "attn.proj.", dim, dim);
+  add_param(m, p + "norm2.weight", dim);
+  add_param(m, p + "norm2.bias", dim);
+  add_linear(m, p + "mlp.fc1.", hidden, dim);
+  add_linear(m, p + "mlp.fc2.", dim, hidden);
+}
+static void add_derived(MplModel* m, const std::string& name, int64_t numel, int esz) {
+  m->dindex[name] = (int)m->derived.size();
+  m->derived.push_back({name, numel, esz, 0});
+}
+
+// Flag combinations whose first forward raises in the reference; same order as spec._first_forward_error.
+static int validate(const MplModel* m) {
+  const MplDesc& d = m->d;
+  if (d.num_joints < 1 || d.embed_dim_ratio < 1 || d.num_heads < 1 || d.num_views < 1 || d.depth < 0) {
+    set_error("num_joints, embed_dim_ratio, num_heads, num_views must be positive and depth non-negative");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  if (d.num_views > kMaxViews) {
+    set_error("num_views = %d exceeds the supported maximum of %d", d.num_views, kMaxViews);
+    return MPL_ERR_UNSUPPORTED;
+  }
+  if (d.in_chans != 2) {
+    set_error("in_chans must be 2: the forward slices pose[:, :, 0:2|0:3] (multiview_mpl.py:359-364)");
+    return MPL_ERR_CONFIG_RUNTIME;
+  }
+  if (m->dim % m->H != 0 && !d.no_transformer_spt) {
+    set_error("embed_dim_ratio must be divisible by num_heads (reshape at multiview_mpl.py:55)");
+    return MPL_ERR_CONFIG_RUNTIME;
+  }
+  if (d.no_transformer_spt && d.multiple_spatial_blocks) {
+    set_error("index 0 is out of range (Spatial_blocks is empty, multiview_mpl.py:401)");
+    return MPL_ERR_CONFIG_INDEX;
+  }
+  if (d.add_3D_pos_encoding_to_rays && !d.input_rays_as_token) {
+    set_error("The size of tensor a (%d) must match the size of tensor b (%d) at non-singleton dimension 2 "
+              "(multiview_mpl.py:483)", m->dim, 2 * m->dim);
+    return MPL_ERR_CONFIG_RUNTIME;
+  }
+  if (d.input_rays_as_token && d.add_3D_pos_encoding_to_rays && d.add_3D_pos_encoding_in_Spatial && d.pose_3d_emb_learnable) {
+    set_error("The size of tensor a (%d) must match the size of tensor b (%d) at non-singleton dimension 2 "
+              "(multiview_mpl.py:396)", m->dim, 2 * m->dim);
+    return MPL_ERR_CONFIG_RUNTIME;
+  }
+  if (d.input_rays_as_token && d.FPT_blocks_view_keypoint_tokens && !d.no_transformer_fpt) {
+    set_error("Given normalized_shape=[%d], expected input with shape [*, %d], but got input of width %d "
+              "(multiview_mpl.py:75,497)", m->dim, m->dim, 2 * m->dim);
+    return MPL_ERR_CONFIG_RUNTIME;
+  }
+  if (!d.no_transformer_fpt && m->fpt_dim % m->H != 0) {
+    set_error("FPT width must be divisible by num_heads (reshape at multiview_mpl.py:55)");
+    return MPL_ERR_CONFIG_RUNTIME;
+  }
+  return MPL_OK;
+}
+
+static void build_tables(MplModel* m) {
+  const MplDesc& d = m->d;
+  const int J = m->J, V = m->V, dim = m->dim, E = m->E;
+  std::vector<std::string> views;
+  if (m->multi) for (int v = 0; v < V; ++v) views.push_back(std::to_string(v) + ".");
+  else views.push_back("");
+  if (!m->multi) add_param(m, "Spatial_pos_embed", (int64_t)J * dim);
+  add_param(m, "pos_3d_embed", (int64_t)J * m->pos3d_w);
+  add_param(m, "pos_3d_view_coding", (int64_t)J * m->pos3d_w);
+  for (auto& v : views) add_linear(m, "Spatial_patch_to_embedding." + v, dim, m->in_ch);
+  if (m->conf_emb) for (auto& v : views) add_linear(m, "confidence_to_embedding." + v, dim, 1);
+  if (m->multi) for (int v = 0; v < V; ++v) add_param(m, "Spatial_pos_embed." + std::to_string(v), (int64_t)J * dim);
+  add_linear(m, "pos_3d_linear.", m->pos3d_lin_out, 3);
+  if (d.input_rays_as_token) add_linear(m, "ray_to_embedding.", dim, 3);
+  if (d.confidence_in_FPT) add_linear(m, "confidence_to_embedding_FPT.", dim, 1);
+  if (!d.no_transformer_spt)
+    for (auto& v : views)
+      for (int l = 0; l < m->depth; ++l) add_block(m, "Spatial_blocks." + v + std::to_string(l) + ".", dim, m->spt_hidden, d.qkv_bias);
+  if (!d.no_transformer_fpt)
+    for (int l = 0; l < m->depth; ++l) add_block(m, "blocks." + std::to_string(l) + ".", m->fpt_dim, m->fpt_hidden, d.qkv_bias);
+  add_param(m, "Spatial_norm.weight", dim);
+  add_param(m, "Spatial_norm.bias", dim);
+  add_param(m, "View_norm.weight", E);
+  add_param(m, "View_norm.bias", E);
+  if (d.linear_weighted_mean) add_linear(m, "weighted_mean.", E, V * E);
+  else { add_param(m, "weighted_mean.weight", V); add_param(m, "weighted_mean.bias", 1); }
+  const int out_dim = 3 * J, Hd = d.hidden_dim;
+  if (d.head_kadkhod) {
+    for (int s = 0; s < 3; ++s) {
+      const int first_in = (s == 0) ? E : out_dim + E;
+      const std::string p = "head." + std::to_string(s) + ".";
+      if (s == 0) {
+        add_param(m, p + "0.0.weight", E);
+        add_param(m, p + "0.0.bias", E);
+        add_linear(m, p + "0.1.", Hd, first_in);
+        add_bn(m, p + "0.2.", Hd);
+        m->folds.push_back({p + "0.1.", p + "0.2.", Hd, first_in});
+      } else {
+        add_linear(m, p + "0.0.", Hd, first_in);
+        add_bn(m, p + "0.1.", Hd);
+        m->folds.push_back({p + "0.0.", p + "0.1.", Hd, first_in});
+      }
+      for (int k = 1; k <= 2; ++k) {
+        add_linear(m, p + std::to_string(k) + ".0.", Hd, Hd);
+        add_bn(m, p + std::to_string(k) + ".1.", Hd);
+        m->folds.push_back({p + std::to_string(k) + ".0.", p + std::to_string(k) + ".1.", Hd, Hd});
+      }
+      add_linear(m, p + "3.", out_dim, Hd);
+    }
+  } else if (d.deep_head) {
+    add_param(m, "head.0.weight", E);
+    add_param(m, "head.0.bias", E);
+    add_linear(m, "head.1.", Hd, E);
+    add_bn(m, "head.2.", Hd);
+    add_linear(m, "head.4.", Hd, Hd);
+    add_bn(m, "head.5.", Hd);
+    add_linear(m, "head.7.", Hd, Hd);
+    add_bn(m, "head.8.", Hd);
+    add_linear(m, "head.10.", out_dim, Hd);
+    m->folds.push_back({"head.1.", "head.2.", Hd, E});
+    m->folds.push_back({"head.4.", "head.5.", Hd, Hd});
+    m->folds.push_back({"head.7.", "head.8.", Hd, Hd});
+  } else {
+    add_param(m, "head.0.weight", E);
+    add_param(m, "head.0.bias", E);
+    add_linear(m, "head.1.", out_dim, E);
+  }
+  // derived tensors
+  for (auto& f : m->folds) {
+    add_derived(m, "fold:" + f.lin + "weight", (int64_t)f.N * f.K, 4);
+    add_derived(m, "fold:" + f.lin + "bias", f.N, 4);
+  }
+  const int maxdim = std::max(m->dim, m->fpt_dim);
+  add_derived(m, "zeros", 3 * (int64_t)maxdim, 4);
+  if (m->fpt_tc) {
+    const int esz = (d.precision == MPL_PREC_BF16) ? 2 : 4;
+    const char* tag = (d.precision == MPL_PREC_BF16) ? "bf16:" : "tf32:";
+    for (int l = 0; l < m->depth; ++l) {
+      const std::string p = "blocks." + std::to_string(l) + ".";
+      const int64_t D = m->fpt_dim, Hf = m->fpt_hidden;
+      add_derived(m, tag + p + "attn.qkv.weight", 3 * D * D, esz);
+      add_derived(m, tag + p + "attn.proj.weight", D * D, esz);
+      add_derived(m, tag + p + "mlp.fc1.weight", Hf * D, esz);
+      add_derived(m, tag + p + "mlp.fc2.weight", D * Hf, esz);
+    }
+  }
+  size_t off = 0;
+  for (auto& p : m->params) {
+    p.offset = off;
+    if (!p.is_int64) off = align_up(off + (size_t)p.numel * 4, 256);
+  }
+  for (auto& t : m->derived) {
+    t.offset = off;
+    off = align_up(off + (size_t)t.numel * t.esz, 256);
+  }
+  m->packed_bytes = off;
+}
+
+struct Packed {
+  const MplModel* m;
+  const uint8_t* base;
+  const float* f(const std::string& name) const {
+    auto it = m->index.find(name);
+    if (it == m->index.end()) throw std::runtime_error("internal: unknown parameter " + name);
+    return reinterpret_cast<const float*>(base + m->params[it->second].offset);
+  }
+  const void* dv(const std::string& name) const {
+    auto it = m->dindex.find(name);
+    if (it == m->dindex.end()) throw std::runtime_error("internal: unknown derived tensor " + name);
+    return base + m->derived[it->second].offset;
+  }
+  const float* df(const std::string& name) const { return reinterpret_cast<const float*>(dv(name)); }
+};
+
+// ---- workspace -------------------------------------------------------------------------------------------------------
+struct Workspace {
+  float *xs, *xn, *qkv, *att, *hid, *conf;       // SPT, [V*Bc*J, .]
+  float* tok;                                    // [Bc, V*tok_w] fp32 residual stream of the FPT
+  void *fxn, *fqkv, *fatt, *fhid;                // FPT activations (fp32 / bf16 per precision)
+  float *vn, *pooled, *hn, *h1, *h2, *cat;       // head
+  size_t bytes;
+};
+
+static Workspace layout_workspace(const MplModel* m, int64_t Bc, uint8_t* base) {
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off = align_up(off + bytes, 256);
+    return p;
+  };
+  const int64_t Rs = (int64_t)m->V * Bc * m->J;
+  const int d = m->dim;
+  w.xs = (float*)take(Rs * d * 4);
+  w.xn = (float*)take(Rs * d * 4);
+  if (!m->d.no_transformer_spt) {
+    w.qkv = (float*)take(Rs * 3 * d * 4);
+    w.att = (float*)take(Rs * d * 4);
+    w.hid = (float*)take(Rs * m->spt_hidden * 4);
+  }
+  if (m->d.confidence_as_attention_uncertainty_weight) w.conf = (float*)take(Rs * 4);
+  w.tok = (float*)take(Bc * (int64_t)m->V * m->tok_w * 4);
+  if (!m->d.no_transformer_fpt) {
+    const int64_t Rf = Bc * m->fpt_tokens;
+    const int64_t D = m->fpt_dim, Hf = m->fpt_hidden;
+    const int esz = (m->fpt_tc && m->d.precision == MPL_PREC_BF16) ? 2 : 4;
+    w.fxn = take(Rf * D * esz);
+    w.fqkv = take(Rf * 3 * D * esz);
+    w.fatt = take(Rf * D * esz);
+    w.fhid = take(Rf * Hf * esz);
+  }
+  const int E = m->E, Hd = m->d.hidden_dim, out_dim = 3 * m->J;
+  const bool fused_head = !m->d.linear_weighted_mean && !m->d.deep_head && !m->d.head_kadkhod;
+  if (!fused_head) {
+    w.vn = (float*)take(Bc * (int64_t)m->V * E * 4);
+    w.pooled = (float*)take(Bc * (int64_t)E * 4);
+    w.hn = (float*)take(Bc * (int64_t)E * 4);
+    if (m->d.deep_head || m->d.head_kadkhod) {
+      w.h1 = (float*)take(Bc * (int64_t)Hd * 4);
+      w.h2 = (float*)take(Bc * (int64_t)Hd * 4);
+    }
+    if (m->d.head_kadkhod) w.cat = (float*)take(Bc * (int64_t)(out_dim + E) * 4);
+  }
+  w.bytes = off;
+  return w;
+}
+
+// ---- forward ---------------------------------------------------------------------------------------------------------
+enum ProfCat {
+  CAT_EMBED = 0, CAT_SPT_LN, CAT_SPT_LINEAR, CAT_SPT_ATTN, CAT_TOKEN, CAT_FPT_LN, CAT_FPT_QKV, CAT_FPT_ATTN, CAT_FPT_PROJ,
+  CAT_FPT_FC1, CAT_FPT_FC2, CAT_HEAD, CAT_SPT_FUSED, CAT_COUNT
+};
+
+static cudaEvent_t prof_event(MplModel* m) {
+  if (m->ev_used == m->ev_pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    m->ev_pool.push_back(e);
+  }
+  return m->ev_pool[m->ev_used++];
+}
+
+// launch + count (+ bracket with events when profiling)
+#define LC(cat, expr)                                        \
+  do {                                                       \
+    cudaEvent_t e0__ = nullptr, e1__ = nullptr;              \
+    if (m->profile) {                                        \
+      e0__ = prof_event(m);                                  \
+      e1__ = prof_event(m);                                  \
+      if (e0__) cudaEventRecord(e0__, s);                    \
+    }                                                        \
+    MPL_TRY(expr);                                           \
+    ++m->launches;                                           \
+    if (m->profile && e0__ && e1__) {                        \
+      cudaEventRecord(e1__, s);                              \
+      m->prof.push_back({(cat), e0__, e1__});                \
+    }                                                        \
+  } while (0)
+
+struct BlockW {
+  const float *n1w, *n1b, *qkvw, *qkvb, *projw, *projb, *n2w, *n2b, *fc1w, *fc1b, *fc2w, *fc2b;
+  const void *qkvw_tc, *projw_tc, *fc1w_tc, *fc2w_tc;  // tensor-core operand copies (FPT, bf16 / tf32 modes)
+};
+
+static BlockW block_weights(const MplModel* m, const Packed& P, const std::string& p, bool tc) {
+  BlockW b{};
+  b.n1w = P.f(p + "norm1.weight");
+  b.n1b = P.f(p + "norm1.bias");
+  b.qkvw = P.f(p + "attn.qkv.weight");
+  b.qkvb = m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : P.df("zeros");
+  b.projw = P.f(p + "attn.proj.weight");
+  b.projb = P.f(p + "attn.proj.bias");
+  b.n2w = P.f(p + "norm2.weight");
+  b.n2b = P.f(p + "norm2.bias");
+  b.fc1w = P.f(p + "mlp.fc1.weight");
+  b.fc1b = P.f(p + "mlp.fc1.bias");
+  b.fc2w = P.f(p + "mlp.fc2.weight");
+  b.fc2b = P.f(p + "mlp.fc2.bias");
+  if (tc) {
+    const std::string tag = (m->d.precision == MPL_PREC_BF16) ? "bf16:" : "tf32:";
+    b.qkvw_tc = P.dv(tag + p + "attn.qkv.weight");
+    b.projw_tc = P.dv(tag + p + "attn.proj.weight");
+    b.fc1w_tc = P.dv(tag + p + "mlp.fc1.weight");
+    b.fc2w_tc = P.dv(tag + p + "mlp.fc2.weight");
+  }
+  return b;
+}
+
+// Block.forward (multiview_mpl.py:84-92), fp32 CUDA-core arithmetic; x [rows, C] is updated in place.
+static int block_f32(MplModel* m, bool fpt, const BlockW& w, float* x, int64_t rows, int64_t sets, int N, int C, int hidden,
+                     float scale, const float* conf, float* xn, float* qkv, float* att, float* hid, cudaStream_t s) {
+  const int c_ln = fpt ? CAT_FPT_LN : CAT_SPT_LN, c_at = fpt ? CAT_FPT_ATTN : CAT_SPT_ATTN;
+  const int c_qkv = fpt ? CAT_FPT_QKV : CAT_SPT_LINEAR, c_proj = fpt ? CAT_FPT_PROJ : CAT_SPT_LINEAR;
+  const int c_fc1 = fpt ? CAT_FPT_FC1 : CAT_SPT_LINEAR, c_fc2 = fpt ? CAT_FPT_FC2 : CAT_SPT_LINEAR;
+  LC(c_ln, launch_layernorm(x, C, C, C, w.n1w, w.n1b, 1e-6f, xn, C, rows, C, s));
+  LC(c_qkv, launch_linear_f32(xn, C, w.qkvw, w.qkvb, nullptr, 0, qkv, 3 * C, rows, 3 * C, C, ACT_NONE, s));
+  LC(c_at, launch_attention_f32(qkv, att, sets, N, m->H, C / m->H, scale, conf, s));
+  LC(c_proj, launch_linear_f32(att, C, w.projw, w.projb, x, C, x, C, rows, C, C, ACT_NONE, s));
+  LC(c_ln, launch_layernorm(x, C, C, C, w.n2w, w.n2b, 1e-6f, xn, C, rows, C, s));
+  LC(c_fc1, launch_linear_f32(xn, C, w.fc1w, w.fc1b, nullptr, 0, hid, hidden, rows, hidden, C, ACT_GELU, s));
+  LC(c_fc2, launch_linear_f32(hid, hidden, w.fc2w, w.fc2b, x, C, x, C, rows, C, hidden, ACT_NONE, s));
+  return MPL_OK;
+}
+
+// Same block with the four projections on tcgen05 (bf16 or tf32 operands); LayerNorm / softmax / residual stay fp32.
+static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_t sets, int N, int C, int hidden, float scale,
+                    void* xn, void* qkv, void* att, void* hid, cudaStream_t s) {
+  const int prec = m->d.precision;
+  const int hd = C / m->H;
+  if (prec == MPL_PREC_BF16) {
+    LC(CAT_FPT_LN, launch_layernorm_bf16(x, C, w.n1w, w.n1b, 1e-6f, (__nv_bfloat16*)xn, C, rows, C, s));
+    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkvb, qkv, rows, 3 * C, C, prec, EPI_BIAS, 0, s));
+    LC(CAT_FPT_ATTN, launch_attention_bf16((const __nv_bfloat16*)qkv, (__nv_bfloat16*)att, sets, N, m->H, hd, scale, s));
+    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_BIAS_RESIDUAL, 1, s));
+    LC(CAT_FPT_LN, launch_layernorm_bf16(x, C, w.n2w, w.n2b, 1e-6f, (__nv_bfloat16*)xn, C, rows, C, s));
+    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1b, hid, rows, hidden, C, prec, EPI_BIAS_GELU, 0, s));
+    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_BIAS_RESIDUAL, 1, s));
+  } else {
+    LC(CAT_FPT_LN, launch_layernorm_tf32(x, C, w.n1w, w.n1b, 1e-6f, (float*)xn, C, rows, C, s));
+    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkvb, qkv, rows, 3 * C, C, prec, EPI_BIAS, 1, s));
+    LC(CAT_FPT_ATTN, launch_attention_tf32((const float*)qkv, (float*)att, sets, N, m->H, hd, scale, s));
+    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_BIAS_RESIDUAL, 1, s));
+    LC(CAT_FPT_LN, launch_layernorm_tf32(x, C, w.n2w, w.n2b, 1e-6f, (float*)xn, C, rows, C, s));
+    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1b, hid, rows, hidden, C, prec, EPI_BIAS_GELU, 1, s));
+    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_BIAS_RESIDUAL, 1, s));
+  }
+  return MPL_OK;
+}
+
+static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses, const float* const* rays,
+                         const float* const* centers, int64_t pose_stride, int64_t center_stride, float* out, float* aux1,
+                         float* aux2, int64_t Bc, const Workspace& w, cudaStream_t s) {
+  const MplDesc& d = m->d;
+  const int J = m->J, V = m->V, dim = m->dim, E = m->E;
+  auto vs = [&](int v) { return m->multi ? std::to_string(v) + "." : std::string(""); };
+  // ---- K1 embed (multiview_mpl.py:349-398) ----
+  EmbedArgs ea{};
+  for (int v = 0; v < V; ++v) {
+    ea.poses[v] = poses[v];
+    ea.rays[v] = rays ? rays[v] : nullptr;
+    ea.centers[v] = centers ? centers[v] : nullptr;
+    ea.We[v] = P.f("Spatial_patch_to_embedding." + vs(v) + "weight");
+    ea.be[v] = P.f("Spatial_patch_to_embedding." + vs(v) + "bias");
+    if (m->conf_emb) {
+      ea.Wc[v] = P.f("confidence_to_embedding." + vs(v) + "weight");
+      ea.bc[v] = P.f("confidence_to_embedding." + vs(v) + "bias");
+    }
+    ea.Ps[v] = m->multi ? P.f("Spatial_pos_embed." + std::to_string(v)) : P.f("Spatial_pos_embed");
+  }
+  ea.pose_stride = pose_stride;
+  ea.center_stride = center_stride;
+  ea.B = Bc;
+  ea.in_ch = m->in_ch;
+  ea.add_conf = m->add_conf;
+  ea.mult_conf = m->mult_conf;
+  ea.spatial_pos_mode = 0;
+  if (d.add_3D_pos_encoding_in_Spatial && rays != nullptr && centers != nullptr) {
+    if (d.pose_3d_emb_learnable) {
+      ea.spatial_pos_mode = 1;
+      ea.pos3d = P.f("pos_3d_embed");
+      ea.pos3d_ld = m->pos3d_w;
+    } else {
+      ea.spatial_pos_mode = 2;
+      ea.Wl = P.f("pos_3d_linear.weight");
+      ea.bl = P.f("pos_3d_linear.bias");
+    }
+  }
+  ea.V = V; ea.J = J; ea.d = dim;
+  ea.x = w.xs;
+  ea.conf = w.conf;
+  LC(CAT_EMBED, launch_embed(ea, s));
+  // ---- SPT blocks (multiview_mpl.py:400-410): conf-weighted pass, last block twice ----
+  if (!d.no_transformer_spt && m->depth > 0) {
+    const int hd = dim / m->H;
+    const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
+    const int stacks = m->multi ? V : 1;
+    const int64_t rows_per_stack = (m->multi ? 1 : V) * Bc * J;
+    for (int st = 0; st < stacks; ++st) {
+      float* x = w.xs + (int64_t)st * rows_per_stack * dim;
+      const float* cf = w.conf ? w.conf + (int64_t)st * rows_per_stack : nullptr;
+      const std::string vp = m->multi ? std::to_string(st) + "." : std::string("");
+      for (int ix = 0; ix < m->depth; ++ix) {
+        const BlockW bw = block_weights(m, P, "Spatial_blocks." + vp + std::to_string(ix) + ".", false);
+        const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
+        if (cf != nullptr)
+          MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, cf, w.xn, w.qkv, w.att, w.hid, s));
+        for (int r = 0; r < reps; ++r)
+          MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, nullptr, w.xn, w.qkv, w.att, w.hid, s));
+      }
+    }
+  }
+  // ---- Spatial_norm (:412) + token build (:463-499) ----
+  const int64_t Rs = (int64_t)V * Bc * J;
+  LC(CAT_TOKEN, launch_layernorm(w.xs, dim, dim, dim, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"), 1e-6f, w.xn, dim, Rs, dim, s));
+  TokenArgs ta{};
+  ta.xn = w.xn;
+  for (int v = 0; v < V; ++v) {
+    ta.poses[v] = poses[v];
+    ta.rays[v] = rays ? rays[v] : nullptr;
+    ta.centers[v] = centers ? centers[v] : nullptr;
+  }
+  ta.pose_stride = pose_stride;
+  ta.center_stride = center_stride;
+  ta.B = Bc;
+  if (d.confidence_in_FPT) {
+    ta.Wcf = P.f("confidence_to_embedding_FPT.weight");
+    ta.bcf = P.f("confidence_to_embedding_FPT.bias");
+  }
+  if (d.input_rays_as_token) {
+    ta.Wr = P.f("ray_to_embedding.weight");
+    ta.br = P.f("ray_to_embedding.bias");
+  }
+  if (!d.add_3D_pos_encoding_in_Spatial) {
+    if (d.pose_3d_emb_learnable) {
+      ta.pos_table = P.f("pos_3d_embed");
+      ta.pos_w = m->pos3d_w;
+    } else {
+      ta.Wl = P.f("pos_3d_linear.weight");
+      ta.bl = P.f("pos_3d_linear.bias");
+      ta.pos_w = m->pos3d_lin_out;
+    }
+  } else {
+    ta.pos_table = P.f("pos_3d_view_coding");
+    ta.pos_w = m->pos3d_w;
+  }
+  ta.ray_layout = m->ray_layout;
+  ta.V = V; ta.J = J; ta.d = dim; ta.tok_w = m->tok_w;
+  ta.tok = w.tok;
+  LC(CAT_TOKEN, launch_token_build(ta, s));
+  // ---- FPT blocks (multiview_mpl.py:416-423) ----
+  if (!d.no_transformer_fpt && m->depth > 0) {
+    const int D = m->fpt_dim, N = m->fpt_tokens;
+    const int hd = D / m->H;
+    const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
+    const int64_t rows = Bc * N;
+    for (int ix = 0; ix < m->depth; ++ix) {
+      const BlockW bw = block_weights(m, P, "blocks." + std::to_string(ix) + ".", m->fpt_tc);
+      const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
+      for (int r = 0; r < reps; ++r) {
+        if (m->fpt_tc)
+          MPL_TRY(block_tc(m, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, w.fxn, w.fqkv, w.fatt, w.fhid, s));
+        else
+          MPL_TRY(block_f32(m, true, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, nullptr, (float*)w.fxn, (float*)w.fqkv, (float*)w.fatt, (float*)w.fhid, s));
+      }
+    }
+  }
+  // ---- ray strip + View_norm + weighted mean + head (multiview_mpl.py:425-446, 506-523) ----
+  int seg_len = E, seg_stride = E;
+  if (m->ray_layout == 1) { seg_len = dim; seg_stride = 2 * dim; }  // [J, 2d] -> first d of every joint slot
+  const int out_dim = 3 * J;
+  const bool fused_head = !d.linear_weighted_mean && !d.deep_head && !d.head_kadkhod;
+  if (fused_head) {
+    HeadArgs ha{};
+    ha.tok = w.tok; ha.B = Bc; ha.V = V; ha.tok_w = m->tok_w; ha.E = E; ha.seg_len = seg_len; ha.seg_stride = seg_stride;
+    ha.out_dim = out_dim;
+    ha.vn_w = P.f("View_norm.weight"); ha.vn_b = P.f("View_norm.bias");
+    ha.wm_w = P.f("weighted_mean.weight"); ha.wm_b = P.f("weighted_mean.bias");
+    ha.hn_w = P.f("head.0.weight"); ha.hn_b = P.f("head.0.bias");
+    ha.hw = P.f("head.1.weight"); ha.hb = P.f("head.1.bias");
+    ha.out = out;
+    LC(CAT_HEAD, launch_head_fused(ha, s));
+    return MPL_OK;
+  }
+  LC(CAT_HEAD, launch_layernorm(w.tok, m->tok_w, seg_len, seg_stride, P.f("View_norm.weight"), P.f("View_norm.bias"), 1e-6f, w.vn, E,
+                     Bc * V, E, s));
+  if (d.linear_weighted_mean)
+    LC(CAT_HEAD, launch_linear_f32(w.vn, (int64_t)V * E, P.f("weighted_mean.weight"), P.f("weighted_mean.bias"), nullptr, 0, w.pooled, E, Bc, E, V * E, ACT_NONE, s));
+  else
+    LC(CAT_HEAD, launch_view_mean(w.vn, P.f("weighted_mean.weight"), P.f("weighted_mean.bias"), w.pooled, Bc, V, E, s));
+  const int Hd = d.hidden_dim;
+  if (d.head_kadkhod) {
+    // three residual stages; stage s > 0 consumes cat([previous prediction, pooled]) (multiview_mpl.py:506-516)
+    float* stage_out[3] = {aux1, aux2, out};
+    for (int st = 0; st < 3; ++st) {
+      const std::string p = "head." + std::to_string(st) + ".";
+      const float* in;
+      int in_w;
+      if (st == 0) {
+        LC(CAT_HEAD, launch_layernorm(w.pooled, E, E, E, P.f(p + "0.0.weight"), P.f(p + "0.0.bias"), 1e-5f, w.hn, E, Bc, E, s));
+        in = w.hn;
+        in_w = E;
+        LC(CAT_HEAD, launch_linear_f32(in, in_w, P.df("fold:" + p + "0.1.weight"), P.df("fold:" + p + "0.1.bias"), nullptr, 0, w.h1, Hd, Bc, Hd, in_w, ACT_RELU, s));
+      } else {
+        // cat = [prev (3J) | pooled (E)]
+        MPL_CUDA(cudaMemcpy2DAsync(w.cat, (size_t)(out_dim + E) * 4, stage_out[st - 1], (size_t)out_dim * 4, (size_t)out_dim * 4, Bc, cudaMemcpyDeviceToDevice, s));
+        MPL_CUDA(cudaMemcpy2DAsync(w.cat + out_dim, (size_t)(out_dim + E) * 4, w.pooled, (size_t)E * 4, (size_t)E * 4, Bc, cudaMemcpyDeviceToDevice, s));
+        in = w.cat;
+        in_w = out_dim + E;
+        LC(CAT_HEAD, launch_linear_f32(in, in_w, P.df("fold:" + p + "0.0.weight"), P.df("fold:" + p + "0.0.bias"), nullptr, 0, w.h1, Hd, Bc, Hd, in_w, ACT_RELU, s));
+      }
+      LC(CAT_HEAD, launch_linear_f32(w.h1, Hd, P.df("fold:" + p + "1.0.weight"), P.df("fold:" + p + "1.0.bias"), nullptr, 0, w.h2, Hd, Bc, Hd, Hd, ACT_RELU, s));
+      LC(CAT_HEAD, launch_linear_f32(w.h2, Hd, P.df("fold:" + p + "2.0.weight"), P.df("fold:" + p + "2.0.bias"), nullptr, 0, w.h1, Hd, Bc, Hd, Hd, ACT_RELU, s));
+      LC(CAT_HEAD, launch_linear_f32(w.h1, Hd, P.f(p + "3.weight"), P.f(p + "3.bias"), nullptr, 0, stage_out[st], out_dim, Bc, out_dim, Hd, ACT_NONE, s));
+    }
+    return MPL_OK;
+  }
+  LC(CAT_HEAD, launch_layernorm(w.pooled, E, E, E, P.f("head.0.weight"), P.f("head.0.bias"), 1e-5f, w.hn, E, Bc, E, s));
+  if (d.deep_head) {
+    LC(CAT_HEAD, launch_linear_f32(w.hn, E, P.df("fold:head.1.weight"), P.df("fold:head.1.bias"), nullptr, 0, w.h1, Hd, Bc, Hd, E, ACT_RELU, s));
+    LC(CAT_HEAD, launch_linear_f32(w.h1, Hd, P.df("fold:head.4.weight"), P.df("fold:head.4.bias"), nullptr, 0, w.h2, Hd, Bc, Hd, Hd, ACT_RELU, s));
+    LC(CAT_HEAD, launch_linear_f32(w.h2, Hd, P.df("fold:head.7.weight"), P.df("fold:head.7.bias"), nullptr, 0, w.h1, Hd, Bc, Hd, Hd, ACT_RELU, s));
+    LC(CAT_HEAD, launch_linear_f32(w.h1, Hd, P.f("head.10.weight"), P.f("head.10.bias"), nullptr, 0, out, out_dim, Bc, out_dim, Hd, ACT_NONE, s));
+  } else {
+    LC(CAT_HEAD, launch_linear_f32(w.hn, E, P.f("head.1.weight"), P.f("head.1.bias"), nullptr, 0, out, out_dim, Bc, out_dim, E, ACT_NONE, s));
+  }
+  return MPL_OK;
+}
+
+}  // namespace mpl
+
+// =====================================================================================================================
+// extern "C" boundary
+// =====================================================================================================================
+#define MPL_API_BEGIN try {
+#define MPL_API_END                                  \
+  }                                                  \
+  catch (const std::exception& e) {                  \
+    mpl::set_error("%s", e.what());                  \
+    return MPL_ERR_INVALID_ARGUMENT;                 \
+  }
+
+extern "C" {
+
+const char* mpl_last_error(void) { return g_last_error.c_str(); }
+int mpl_abi_version(void) { return MPL_ABI_VERSION; }
+
+int mpl_create(const MplDesc* desc, MplModel** out) {
+  MPL_API_BEGIN
+  if (desc == nullptr || out == nullptr) {
+    set_error("mpl_create: null argument");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  if (desc->struct_size != (int32_t)sizeof(MplDesc)) {
+    set_error("mpl_create: MplDesc.struct_size = %d, library expects %d", desc->struct_size, (int)sizeof(MplDesc));
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  if (desc->precision < MPL_PREC_FP32 || desc->precision > MPL_PREC_BF16) {
+    set_error("mpl_create: unknown precision %d", desc->precision);
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  MplModel* m = new MplModel();
+  m->d = *desc;
+  const MplDesc& d = m->d;
+  m->J = d.num_joints; m->V = d.num_views; m->dim = d.embed_dim_ratio; m->H = d.num_heads; m->depth = d.depth;
+  m->in_ch = d.confidence_input_as_third ? d.in_chans + 1 : d.in_chans;
+  m->add_conf = d.add_confidence_input && !d.concat_confidence_emb;  // Q3 (multiview_mpl.py:173-176)
+  m->mult_conf = d.mult_confidence_emb && !d.concat_confidence_emb;
+  m->conf_emb = m->add_conf || m->mult_conf;
+  m->multi = d.multiple_spatial_blocks != 0;
+  m->E = m->dim * m->J;
+  m->tok_w = m->E * (d.input_rays_as_token ? 2 : 1);
+  m->ray_layout = !d.input_rays_as_token ? 0 : (d.add_3D_pos_encoding_to_rays ? 1 : 2);
+  if (d.FPT_blocks_view_keypoint_tokens) { m->fpt_dim = m->dim; m->fpt_tokens = m->V * m->J; }
+  else { m->fpt_dim = m->tok_w; m->fpt_tokens = m->V; }
+  m->pos3d_lin_out = (d.add_3D_pos_encoding_to_rays && !d.add_3D_pos_encoding_in_Spatial) ? 2 * m->dim : m->dim;
+  m->pos3d_w = d.add_3D_pos_encoding_to_rays ? 2 * m->dim : m->dim;
+  m->spt_hidden = (int)((double)m->dim * (double)d.mlp_ratio);
+  m->fpt_hidden = (int)((double)m->fpt_dim * (double)d.mlp_ratio);
+  m->n_out = d.head_kadkhod ? 3 : 1;
+  const int st = validate(m);
+  if (st != MPL_OK) {
+    delete m;
+    return st;
+  }
+  m->fpt_tc = false;
+  if (d.precision != MPL_PREC_FP32 && !d.no_transformer_fpt && m->depth > 0) {
+    const bool ok = gemm_tcgen05_supports(3 * m->fpt_dim, m->fpt_dim, d.precision) &&
+                    gemm_tcgen05_supports(m->fpt_dim, m->fpt_dim, d.precision) &&
+                    gemm_tcgen05_supports(m->fpt_hidden, m->fpt_dim, d.precision) &&
+                    gemm_tcgen05_supports(m->fpt_dim, m->fpt_hidden, d.precision);
+    if (!ok) {
+      delete m;
+      set_error("precision mode %d needs FPT widths that are multiples of 16 (fpt_dim=%d, hidden=%d); use MPL_PREC_FP32",
+                d.precision, m->fpt_dim, m->fpt_hidden);
+      return MPL_ERR_UNSUPPORTED;
+    }
+    m->fpt_tc = true;
+  }
+  build_tables(m);
+  *out = m;
+  return MPL_OK;
+  MPL_API_END
+}
+
+void mpl_destroy(MplModel* m) {
+  if (m == nullptr) return;
+  for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
+  delete m;
+}
+
+int mpl_set_profile(MplModel* m, int enabled) {
+  if (m == nullptr) {
+    set_error("mpl_set_profile: null handle");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  m->profile = enabled != 0;
+  m->prof.clear();
+  m->ev_used = 0;
+  return MPL_OK;
+}
+
+int mpl_profile_categories(void) { return CAT_COUNT; }
+
+const char* mpl_profile_category_name(int cat) {
+  static const char* names[CAT_COUNT] = {"embed", "spt_layernorm", "spt_linear", "spt_attention", "token_build", "fpt_layernorm",
+                                         "fpt_gemm_qkv", "fpt_attention", "fpt_gemm_proj", "fpt_gemm_fc1", "fpt_gemm_fc2", "head",
+                                         "spt_fused"};
+  return (cat >= 0 && cat < CAT_COUNT) ? names[cat] : "";
+}
+
+int mpl_profile_collect(MplModel* m, double* ms_per_category, int64_t* launches_per_category, int n) {
+  if (m == nullptr || ms_per_category == nullptr || launches_per_category == nullptr || n < CAT_COUNT) {
+    set_error("mpl_profile_collect: bad argument (need arrays of mpl_profile_categories() entries)");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  for (int i = 0; i < n; ++i) { ms_per_category[i] = 0.0; launches_per_category[i] = 0; }
+  for (auto& r : m->prof) {
+    MPL_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    MPL_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ms_per_category[r.cat] += ms;
+    launches_per_category[r.cat] += 1;
+  }
+  m->prof.clear();
+  m->ev_used = 0;
+  return MPL_OK;
+}
+
+int mpl_num_params(const MplModel* m) { return m ? (int)m->params.size() : 0; }
+
+int mpl_param_info(const MplModel* m, int index, const char** name, int64_t* numel, int32_t* is_int64) {
+  if (m == nullptr || index < 0 || index >= (int)m->params.size()) {
+    set_error("mpl_param_info: index out of range");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  if (name) *name = m->params[index].name.c_str();
+  if (numel) *numel = m->params[index].numel;
+  if (is_int64) *is_int64 = m->params[index].is_int64 ? 1 : 0;
+  return MPL_OK;
+}
+
+int64_t mpl_dim(const MplModel* m, int which) {
+  if (m == nullptr) return -1;
+  switch (which) {
+    case 0: return m->tok_w;
+    case 1: return m->fpt_dim;
+    case 2: return m->fpt_tokens;
+    case 3: return m->E;
+    case 4: return m->spt_hidden;
+    case 5: return m->fpt_hidden;
+    case 6: return m->n_out;
+    default: return -1;
+  }
+}
+
+size_t mpl_packed_bytes(const MplModel* m) { return m ? m->packed_bytes : 0; }
+
+int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, void* packed, size_t packed_bytes,
+                     mpl_stream_t stream) {
+  MPL_API_BEGIN
+  if (m == nullptr || params == nullptr || packed == nullptr) {
+    set_error("mpl_pack_weights: null argument");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  if (num_params != (int)m->params.size()) {
+    set_error("mpl_pack_weights: got %d parameter pointers, the model has %d", num_params, (int)m->params.size());
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  if (packed_bytes < m->packed_bytes) {
+    set_error("mpl_pack_weights: packed buffer has %zu bytes, %zu needed", packed_bytes, m->packed_bytes);
+    return MPL_ERR_WORKSPACE;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(packed);
+  for (size_t i = 0; i < m->params.size(); ++i) {
+    const ParamInfo& p = m->params[i];
+    if (p.is_int64) continue;
+    if (params[i] == nullptr) {
+      set_error("mpl_pack_weights: parameter %s is null", p.name.c_str());
+      return MPL_ERR_INVALID_ARGUMENT;
+    }
+    MPL_CUDA(cudaMemcpyAsync(base + p.offset, params[i], (size_t)p.numel * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  Packed P{m, base};
+  for (auto& f : m->folds) {
+    float* Wf = const_cast<float*>(P.df("fold:" + f.lin + "weight"));
+    float* bf = const_cast<float*>(P.df("fold:" + f.lin + "bias"));
+    MPL_TRY(launch_fold_bn(P.f(f.lin + "weight"), P.f(f.lin + "bias"), P.f(f.bn + "weight"), P.f(f.bn + "bias"),
+                           P.f(f.bn + "running_mean"), P.f(f.bn + "running_var"), 1e-5f, Wf, bf, f.N, f.K, s));
+  }
+  {
+    const Derived& z = m->derived[m->dindex.at("zeros")];
+    MPL_CUDA(cudaMemsetAsync(base + z.offset, 0, (size_t)z.numel * 4, s));
+  }
+  if (m->fpt_tc) {
+    const bool bf = m->d.precision == MPL_PREC_BF16;
+    const std::string tag = bf ? "bf16:" : "tf32:";
+    for (int l = 0; l < m->depth; ++l) {
+      const std::string p = "blocks." + std::to_string(l) + ".";
+      for (const char* wn : {"attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"}) {
+        const float* src = P.f(p + wn);
+        const Derived& dd = m->derived[m->dindex.at(tag + p + wn)];
+        if (bf) MPL_TRY(launch_to_bf16(src, reinterpret_cast<__nv_bfloat16*>(base + dd.offset), dd.numel, s));
+        else MPL_TRY(launch_to_tf32(src, reinterpret_cast<float*>(base + dd.offset), dd.numel, s));
+      }
+    }
+  }
+  return MPL_OK;
+  MPL_API_END
+}
+
+int64_t mpl_chunk_poses(const MplModel* m) { return m ? m->chunk : 0; }
+int mpl_set_chunk_poses(MplModel* m, int64_t chunk) {
+  if (m == nullptr || chunk < 1) {
+    set_error("mpl_set_chunk_poses: chunk must be >= 1");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  m->chunk = chunk;
+  return MPL_OK;
+}
+
+size_t mpl_workspace_bytes(const MplModel* m, int64_t max_batch) {
+  if (m == nullptr || max_batch < 0) return 0;
+  const int64_t Bc = std::min<int64_t>(std::max<int64_t>(max_batch, 1), m->chunk);
+  return layout_workspace(m, Bc, nullptr).bytes;
+}
+
+int mpl_forward(MplModel* m, const void* packed, const float* const* poses, const float* const* rays,
+                const float* const* centers, int64_t pose_stride, int64_t center_stride, float* out, float* aux1,
+                float* aux2, int64_t batch, void* workspace, size_t workspace_bytes, mpl_stream_t stream) {
+  MPL_API_BEGIN
+  if (m == nullptr || packed == nullptr || poses == nullptr || out == nullptr || batch < 0) {
+    set_error("mpl_forward: null argument or negative batch");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  const MplDesc& d = m->d;
+  // rays / centers are needed whenever a ray embedding or the ray-direction positional encoding is live
+  const bool need_rays = d.input_rays_as_token || (!d.add_3D_pos_encoding_in_Spatial && !d.pose_3d_emb_learnable);
+  if (need_rays && (rays == nullptr || centers == nullptr)) {
+    set_error("mpl_forward: this configuration consumes rays and centers (multiview_mpl.py:469-489); got null");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  if (d.head_kadkhod && (aux1 == nullptr || aux2 == nullptr)) {
+    set_error("mpl_forward: head_kadkhod returns (x, [x1, x2]); aux1/aux2 must be provided");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  for (int v = 0; v < m->V; ++v)
+    if (poses[v] == nullptr || (rays && rays[v] == nullptr) || (centers && centers[v] == nullptr)) {
+      set_error("mpl_forward: view %d pointer is null", v);
+      return MPL_ERR_INVALID_ARGUMENT;
+    }
+  m->launches = 0;
+  if (m->profile) { m->prof.clear(); m->ev_used = 0; }
+  if (batch == 0) return MPL_OK;
+  const int64_t Bc_max = std::min<int64_t>(batch, m->chunk);
+  const size_t need = layout_workspace(m, Bc_max, nullptr).bytes;
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("mpl_forward: workspace has %zu bytes, %zu needed for batch %lld", workspace_bytes, need, (long long)batch);
+    return MPL_ERR_WORKSPACE;
+  }
+  const Workspace w = layout_workspace(m, Bc_max, reinterpret_cast<uint8_t*>(workspace));
+  Packed P{m, reinterpret_cast<const uint8_t*>(packed)};
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int out_dim = 3 * m->J;
+  for (int64_t b0 = 0; b0 < batch; b0 += m->chunk) {
+    const int64_t Bc = std::min<int64_t>(m->chunk, batch - b0);
+    const float* pp[kMaxViews];
+    const float* rp[kMaxViews];
+    const float* cp[kMaxViews];
+    for (int v = 0; v < m->V; ++v) {
+      pp[v] = poses[v] + b0 * pose_stride;
+      rp[v] = rays ? rays[v] + b0 * pose_stride : nullptr;
+      cp[v] = centers ? centers[v] + b0 * center_stride : nullptr;
+    }
+    MPL_TRY(forward_chunk(m, P, pp, rays ? rp : nullptr, centers ? cp : nullptr, pose_stride, center_stride,
+                          out + b0 * out_dim, aux1 ? aux1 + b0 * out_dim : nullptr, aux2 ? aux2 + b0 * out_dim : nullptr, Bc,
+                          w, s));
+  }
+  return MPL_OK;
+  MPL_API_END
+}
+
+int64_t mpl_last_launch_count(const MplModel* m) { return m ? m->launches : 0; }
+
+int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t batch, int num_joints,
+                         float unit_scale, double* acc, mpl_stream_t stream) {
+  if (pred == nullptr || gt == nullptr || acc == nullptr || batch < 0 || num_joints < 1) {
+    set_error("mpl_mpjpe_accumulate: bad argument");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  return launch_mpjpe_accumulate(pred, gt, conf3d, batch, num_joints, unit_scale, acc, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpl_build_inputs(const float* pix, const double* calib, int64_t batch, int num_views, int num_joints, float* poses,
+                     float* rays, float* centers, mpl_stream_t stream) {
+  if (pix == nullptr || calib == nullptr || poses == nullptr || rays == nullptr || centers == nullptr || batch < 0) {
+    set_error("mpl_build_inputs: bad argument");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  return launch_build_inputs(pix, calib, batch, num_views, num_joints, poses, rays, centers, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpl_test_gemm(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype, int epilogue,
+                  int out_fp32, mpl_stream_t stream) {
+  return launch_gemm_tcgen05(A, W, bias, Y, M, N, K, dtype, epilogue, out_fp32, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpl_set_gemm_cta_group(int cta_group) {
+  if (cta_group != 1 && cta_group != 2) {
+    set_error("mpl_set_gemm_cta_group: cta_group must be 1 or 2");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  set_gemm_cta_group(cta_group);
+  return MPL_OK;
+}
+int mpl_get_gemm_cta_group(void) { return get_gemm_cta_group(); }
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+"""Drop-in replacement for `MPL/lib/models/multiview_mpl.py` of aghasemzadeh/OpenMPL — inference forward only.
+
+Same factory (`get_multiview_mpl_net(cfg, is_train)`, multiview_mpl.py:649-654), same wrapper
+(`MultiView_MPL_G(cfg)`, :528-585), same constructor keywords and defaults (`MultiView_MPL(...)`, :95-117), same
+parameter / buffer names and shapes (so reference checkpoints load, `MPL/lib/utils/utils.py:148-153`), same
+`forward(x, centers=None, rays=None)` list-of-views call convention (`MPL/lib/core/function_mpl.py:344-350`).
+Behind that boundary nothing of the reference is left: the module owns the parameters and hands device pointers to
+`libmpl_b200.so` (hand-written sm_100a CUDA, C ABI in `include/mpl_b200.h`).  PyTorch is used for device memory and
+streams only.  There is no CPU or eager fallback: without the library or without a CUDA device the forward raises.
+
+Selecting it from the reference's runner: `MODEL: multiview_mpl_b200` in the YAML.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import threading
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..spec import BUFFER_KINDS, CTOR_DEFAULTS, make_config, param_spec
+
+DEFAULT_PRECISION = os.environ.get("MPL_B200_PRECISION", "tf32")
+
+
+class _Node(nn.Module):
+    """Anonymous container giving parameters the reference's dotted state_dict names."""
+
+
+class _Handle:
+    """Owns one `MplModel*`; shared by reference between DataParallel replicas, never copied."""
+
+    def __init__(self):
+        self.ptr = None
+
+    def __deepcopy__(self, memo):
+        return _Handle()          # a deep-copied module lazily creates its own handle
+
+    def __del__(self):
+        try:
+            if self.ptr is not None:
+                _lib.lib().mpl_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+def _register(root: nn.Module, name: str, tensor: torch.Tensor, is_buffer: bool):
+    parts = name.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    if is_buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+def _default_init(shape, kind, fan_in):
+    """PyTorch default initialisation of the layer kinds the reference builds."""
+    if kind in ("linear_w", "linear_b"):
+        bound = 1.0 / math.sqrt(fan_in)
+        return torch.empty(shape).uniform_(-bound, bound)
+    if kind in ("norm_w", "bn_var"):
+        return torch.ones(shape)
+    if kind in ("norm_b", "pos", "bn_mean"):
+        return torch.zeros(shape)
+    if kind == "count":
+        return torch.zeros(shape, dtype=torch.long)
+    raise ValueError(kind)
+
+
+class MultiView_MPL(nn.Module):
+    """Same keyword arguments and defaults as the reference constructor (multiview_mpl.py:95-117)."""
+
+    def __init__(self, num_joints=17, in_chans=2, embed_dim_ratio=32, depth=4,
+                 num_heads=8, mlp_ratio=2., qkv_bias=True, qk_scale=None,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0.2, norm_layer=None, num_views=5,
+                 add_confidence_input=False,
+                 mult_confidence_emb=False,
+                 concat_confidence_emb=False,
+                 confidence_input_as_third=False,
+                 pose_3d_emb_learnable=False,
+                 linear_weighted_mean=False,
+                 pos_embedding_type="learnable",
+                 add_3D_pos_encoding_in_Spatial=False,
+                 input_rays_as_token=False,
+                 add_3D_pos_encoding_to_rays=False,
+                 confidence_as_attention_uncertainty_weight=False,
+                 multiple_spatial_blocks=False,
+                 no_transformer_spt=False,
+                 no_transformer_fpt=False,
+                 confidence_in_FPT=False,
+                 deep_head=False,
+                 head_kadkhod=False,
+                 hidden_dim=1024,
+                 FPT_blocks_view_keypoint_tokens=False, *, precision=None):
+        super().__init__()
+        kw = {k: v for k, v in locals().items() if k in CTOR_DEFAULTS}
+        self.cfg = make_config(**kw)
+        self.precision = precision or DEFAULT_PRECISION
+        self.num_joints, self.num_views, self.embed_dim_ratio = num_joints, num_views, embed_dim_ratio
+        self._spec = param_spec(self.cfg)
+        for name, (shape, kind, fan_in) in self._spec.items():
+            _register(self, name, _default_init(shape, kind, fan_in), kind in BUFFER_KINDS)
+        self._names = list(self._spec.keys())
+        self._h = _Handle()          # MplModel*, created at the first forward (the reference also fails there, Q6)
+        self._dev = {}               # device index -> dict(packed, stamp, workspace)
+        self._lock = threading.Lock()
+        self.last_launches = 0
+
+    # ---- handle / packing ------------------------------------------------------------------------------------------
+    def _get_handle(self):
+        if self._h.ptr is None:
+            L = _lib.lib()
+            desc = _lib.make_desc(self.cfg.kw, self.precision)
+            h = ctypes.c_void_p()
+            _lib.check(L.mpl_create(ctypes.byref(desc), ctypes.byref(h)))
+            n = L.mpl_num_params(h)
+            name, numel, is_int = ctypes.c_char_p(), ctypes.c_int64(), ctypes.c_int32()
+            lib_names = []
+            for i in range(n):
+                _lib.check(L.mpl_param_info(h, i, ctypes.byref(name), ctypes.byref(numel), ctypes.byref(is_int)))
+                lib_names.append(name.value.decode())
+                if numel.value != self._tensor(lib_names[-1]).numel():
+                    raise RuntimeError(f"parameter table mismatch for {lib_names[-1]}")
+            if lib_names != self._names:
+                raise RuntimeError("parameter table of libmpl_b200.so differs from the module's state_dict")
+            self._h.ptr = h
+        return self._h.ptr
+
+    def _tensor(self, name):
+        mod = self
+        parts = name.split(".")
+        for p in parts[:-1]:
+            mod = mod._modules[p]
+        t = mod._parameters.get(parts[-1])
+        return t if t is not None else mod._buffers[parts[-1]]
+
+    def _state(self, device):
+        """Per-device packed weights, repacked whenever a parameter's storage or version changes."""
+        L = _lib.lib()
+        h = self._get_handle()
+        tensors = [self._tensor(n) for n in self._names]
+        stamp = tuple((t.data_ptr(), t._version) for t in tensors)
+        with self._lock:
+            st = self._dev.get(device.index)
+            if st is None or st["stamp"] != stamp:
+                srcs = [t if (t.device == device and t.dtype in (torch.float32, torch.long) and t.is_contiguous())
+                        else t.to(device=device, dtype=torch.long if t.dtype == torch.long else torch.float32).contiguous()
+                        for t in tensors]
+                ptrs = (ctypes.c_void_p * len(srcs))(*[s.data_ptr() for s in srcs])
+                nbytes = L.mpl_packed_bytes(h)
+                packed = st["packed"] if st is not None else torch.empty(nbytes, dtype=torch.uint8, device=device)
+                stream = torch.cuda.current_stream(device).cuda_stream
+                _lib.check(L.mpl_pack_weights(h, ptrs, len(srcs), packed.data_ptr(), nbytes, stream))
+                for s in srcs:                      # temporaries must outlive the enqueued copies
+                    s.record_stream(torch.cuda.current_stream(device))
+                st = {"packed": packed, "stamp": stamp, "workspace": st["workspace"] if st else None}
+                self._dev[device.index] = st
+            return st
+
+    def set_chunk_poses(self, chunk: int):
+        _lib.check(_lib.lib().mpl_set_chunk_poses(self._get_handle(), int(chunk)))
+
+    def set_profile(self, enabled: bool):
+        """Bracket every kernel launch of the next forwards with CUDA events (see `profile()`)."""
+        _lib.check(_lib.lib().mpl_set_profile(self._get_handle(), int(bool(enabled))))
+
+    def profile(self) -> dict:
+        """{category: (milliseconds, launches)} of the last forward run with profiling enabled."""
+        L = _lib.lib()
+        n = L.mpl_profile_categories()
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        _lib.check(L.mpl_profile_collect(self._get_handle(), ms, cnt, n))
+        return {L.mpl_profile_category_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
+
+    # ---- nn.Module plumbing ------------------------------------------------------------------------------------------
+    def train(self, mode: bool = True):
+        # construction leaves the module in training mode like any nn.Module; only the forward refuses it
+        return super().train(mode)
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_dev":
+                new.__dict__[k] = {}
+            elif k == "_lock":
+                new.__dict__[k] = threading.Lock()
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    # ---- forward (multiview_mpl.py:450-525) --------------------------------------------------------------------------
+    def forward(self, poses, rays=None, centers=None):
+        if self.training:
+            raise RuntimeError("multiview_mpl_b200 is an inference-only forward: call model.eval() "
+                               "(training/backward is out of scope and there is no eager fallback)")
+        if self.cfg.error is not None:
+            raise {"IndexError": IndexError}.get(self.cfg.error[0], RuntimeError)(self.cfg.error[1])
+        if not torch.cuda.is_available():
+            raise RuntimeError("multiview_mpl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        V, J = self.cfg.V, self.cfg.J
+        device = self._tensor(self._names[0]).device
+        if device.type != "cuda":
+            first = poses[0] if isinstance(poses, (list, tuple)) else poses
+            device = first.device if first.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+
+        def prep(x, last_shape, what):
+            if x is None:
+                return None, 0
+            if isinstance(x, (list, tuple)):
+                if len(x) != V:
+                    raise RuntimeError(f"{what}: expected a list of {V} views, got {len(x)}")
+                ts = [t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous() for t in x]
+                for t in ts:
+                    if tuple(t.shape[1:]) != last_shape or t.shape[0] != ts[0].shape[0]:
+                        raise RuntimeError(f"{what}: every view must be [B, {last_shape[0]}, {last_shape[1]}], got {tuple(t.shape)}")
+                return ts, last_shape[0] * last_shape[1]
+            t = x.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+            if t.dim() != 4 or t.shape[1] != V or tuple(t.shape[2:]) != last_shape:
+                raise RuntimeError(f"{what}: packed input must be [B, {V}, {last_shape[0]}, {last_shape[1]}], got {tuple(t.shape)}")
+            n = last_shape[0] * last_shape[1]
+            return [t[:, v] for v in range(V)], V * n
+
+        p_list, p_stride = prep(poses, (J, 3), "poses")
+        r_list, r_stride = prep(rays, (J, 3), "rays")
+        c_list, c_stride = prep(centers, (1, 3), "centers")
+        if r_list is not None and r_stride != p_stride:
+            raise RuntimeError("poses and rays must use the same layout (both lists of views or both packed)")
+        B = p_list[0].shape[0]
+        L = _lib.lib()
+        with torch.cuda.device(device):
+            st = self._state(device)
+            h = self._h.ptr
+            out = torch.empty((B, J, 3), dtype=torch.float32, device=device)
+            aux = [torch.empty_like(out), torch.empty_like(out)] if self.cfg.kw["head_kadkhod"] else [None, None]
+            need = L.mpl_workspace_bytes(h, B)
+            ws = st["workspace"]
+            if ws is None or ws.numel() < need:
+                st["workspace"] = ws = torch.empty(need, dtype=torch.uint8, device=device)
+            arr = lambda ts: (ctypes.c_void_p * V)(*[t.data_ptr() for t in ts]) if ts is not None else None
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(L.mpl_forward(h, st["packed"].data_ptr(), arr(p_list), arr(r_list), arr(c_list), p_stride, c_stride,
+                                     out.data_ptr(), aux[0].data_ptr() if aux[0] is not None else None,
+                                     aux[1].data_ptr() if aux[1] is not None else None, B, ws.data_ptr(), ws.numel(), stream))
+            self.last_launches = int(L.mpl_last_launch_count(h))
+        if self.cfg.kw["head_kadkhod"]:
+            return out, [aux[0], aux[1]]
+        return out
+
+
+class MultiView_MPL_G(nn.Module):
+    """cfg -> MultiView_MPL, with the reference's `num_views` rule (multiview_mpl.py:534-580)."""
+
+    def __init__(self, cfg, **kwargs):
+        super().__init__()
+        ds, net = cfg.DATASET, cfg.NETWORK
+        if ds.TEST_DATASET.startswith('multiview_cmu_panoptic') or ds.TEST_DATASET.startswith('multiview_amass_cmu_panoptic_mpl'):
+            num_views = 5
+        else:
+            num_views = 4
+        if ds.TRAIN_VIEWS is not None:
+            num_views = len(ds.TRAIN_VIEWS)
+            if ds.USE_HELPER_CAMERAS:
+                assert ds.TRAIN_VIEWS_HELPER is not None
+                num_views += len(ds.TRAIN_VIEWS_HELPER)
+        if ds.TRAIN_ON_ALL_CAMERAS and ds.TEST_ON_ALL_CAMERAS:
+            num_views = ds.N_VIEWS_TRAIN_TEST_ALL
+        self.init_weights_from = net.INIT_WEIGHTS_FROM
+        self.features = MultiView_MPL(
+            num_joints=net.NUM_JOINTS,
+            embed_dim_ratio=net.DIM,
+            depth=net.TRANSFORMER_DEPTH,
+            num_heads=net.TRANSFORMER_HEADS,
+            drop_rate=net.TRANSFORMER_DROP_RATE,
+            attn_drop_rate=net.TRANSFORMER_ATTN_DROP_RATE,
+            drop_path_rate=net.TRANSFORMER_DROP_PATH_RATE,
+            num_views=num_views,
+            add_confidence_input=net.TRANSFORMER_ADD_CONFIDENCE_INPUT,
+            mult_confidence_emb=net.TRANSFORMER_MULT_CONFIDENCE_EMB,
+            concat_confidence_emb=net.TRANSFORMER_CONCAT_CONFIDENCE_EMB,
+            confidence_input_as_third=net.TRANSFORMER_CONFIDENCE_INPUT_AS_THIRD,
+            pose_3d_emb_learnable=net.POSE_3D_EMB_LEARNABLE,
+            linear_weighted_mean=net.TRANSFORMER_LINEAR_WEIGHTED_MEAN,
+            add_3D_pos_encoding_in_Spatial=net.TRANSFORMER_ADD_3D_POS_ENCODING_IN_SPATIAL,
+            input_rays_as_token=net.TRANSFORMER_INPUT_RAYS_AS_TOKEN,
+            add_3D_pos_encoding_to_rays=net.TRANSFORMER_ADD_3D_POS_ENCODING_TO_RAYS,
+            confidence_as_attention_uncertainty_weight=net.TRANSFORMER_CONF_ATTENTION_UNCERTAINTY_WEIGHT,
+            multiple_spatial_blocks=net.TRANSFORMER_MULTIPLE_SPATIAL_BLOCKS,
+            no_transformer_spt=net.TRANSFORMER_NO_SPT,
+            no_transformer_fpt=net.TRANSFORMER_NO_FPT,
+            confidence_in_FPT=net.TRANSFORMER_CONFIDENCE_IN_FPT,
+            deep_head=net.TRANSFORMER_OUTPUT_HEAD_DEEP,
+            head_kadkhod=net.TRANSFORMER_OUTPUT_HEAD_KADKHOD,
+            hidden_dim=net.TRANSFORMER_OUTPUT_HEAD_HIDDEN_DIM,
+            FPT_blocks_view_keypoint_tokens=net.TRANSFORMER_FPT_BLOCKS_VIEW_KEYPOINT_TOKENS,
+            precision=kwargs.get("precision"),
+        )
+
+    def forward(self, x, centers=None, rays=None):
+        return self.features(x, rays=rays, centers=centers)
+
+    def init_weights(self, pretrained=''):
+        """Reference behaviour for the branches that work there (multiview_mpl.py:587-646): a checkpoint file is
+        loaded non-strictly; the default 'scratch' mode leaves the PyTorch default initialisation untouched."""
+        if os.path.isfile(pretrained):
+            sd = torch.load(pretrained, map_location='cpu')
+            if isinstance(sd, dict) and 'state_dict' in sd:
+                sd = sd['state_dict']
+            self.load_state_dict(sd, strict=False)
+
+
+def get_multiview_mpl_net(cfg, is_train, **kwargs):
+    model = MultiView_MPL_G(cfg, **kwargs)
+    if is_train and cfg.NETWORK.INIT_WEIGHTS:
+        model.init_weights(cfg.NETWORK.PRETRAINED)
+    return model

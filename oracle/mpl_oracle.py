@@ -237,3 +237,64 @@ def evaluate(pred, gt, output_in_meter=True, conf_3d=None, relative=False):
     pjpe, mpjpe = calc_mpjpe(gt, pred, mode="relative" if relative else "absolute")
     dist_kp, dist = calc_distance_per_dim(pred, gt)
     return {"pjpe": pjpe, "mpjpe": mpjpe, "dist_per_dim_per_kp": dist_kp, "dist_per_dim": dist}
+
+
+def metric_sums(pred, gt, conf_3d=None, output_in_meter=True):
+    """The running sums `mpl_mpjpe_accumulate` keeps (layout in include/mpl_b200.h), restated from evaluate() above:
+    finalising them must reproduce evaluate(relative=False/True) exactly."""
+    pred = np.array(pred, dtype=np.float64)
+    gt = np.array(gt, dtype=np.float64)
+    B, J, _ = pred.shape
+    if conf_3d is not None:
+        conf_3d = np.broadcast_to(np.asarray(conf_3d).reshape(B, J, -1), (B, J, 3))
+    a = evaluate(pred, gt, output_in_meter, conf_3d, relative=False)
+    r = evaluate(pred, gt, output_in_meter, conf_3d, relative=True)
+    cnt = np.full((J, 3), float(B)) if conf_3d is None else (conf_3d > 0).sum(axis=0).astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        return np.concatenate([a["pjpe"] * B, r["pjpe"] * B, np.nan_to_num(a["dist_per_dim_per_kp"] * cnt).ravel(),
+                               np.nan_to_num(r["dist_per_dim_per_kp"] * cnt).ravel(), cnt.ravel(), [float(B)]])
+
+
+# --------------------------------------------------------------------------------------------------
+# input construction: MPL/lib/dataset/joints_dataset_mpl.py:615-648,701-715,762-772,817-820,872-904
+# --------------------------------------------------------------------------------------------------
+
+def normalize_screen_coordinates(X, w, h):
+    """joints_dataset_mpl.py:817-820."""
+    return (X / w) * 2 - np.array([1, h / w])
+
+
+def build_inputs(pix, R, t, f, c, image_size):
+    """Per-view model inputs from raw 2D detections, float64 like the dataset code, cast to float32 at the end.
+
+    pix [B,V,J,3] (u, v, conf) pixels; R [V,3,3] world->cam; t [V,3] camera position (USE_T); f, c [V,2] pixels.
+    Clip + confidence zeroing :709-715 (NO_AUGMENTATION branch), screen normalisation :762-764, intrinsics
+    normalisation :615-623, rays R^T [(x-cx)/fx, (y-cy)/fy, 1] + t :872-898, centers = t^T :645-646.
+    """
+    pix = np.asarray(pix, dtype=np.float64)
+    w, h = image_size
+    B, V, J, _ = pix.shape
+    poses = np.zeros((B, V, J, 3))
+    rays = np.zeros((B, V, J, 3))
+    centers = np.zeros((B, V, 1, 3))
+    for v in range(V):
+        joints = pix[:, v, :, :2].copy()
+        vis = pix[:, v, :, 2].copy()
+        vis = np.where(0 < joints[..., 0], vis, 0)
+        vis = np.where(joints[..., 0] < w - 1, vis, 0)
+        vis = np.where(0 < joints[..., 1], vis, 0)
+        vis = np.where(joints[..., 1] < h - 1, vis, 0)
+        joints[..., 0] = np.clip(joints[..., 0], 0, w - 1)
+        joints[..., 1] = np.clip(joints[..., 1], 0, h - 1)
+        cc = normalize_screen_coordinates(np.asarray(c[v], dtype=np.float64), w, h)
+        ff = np.asarray(f[v], dtype=np.float64) / w * 2
+        joints = normalize_screen_coordinates(joints, w, h)
+        coords = joints.copy()
+        coords[..., 0] = (coords[..., 0] - cc[0]) / ff[0]
+        coords[..., 1] = (coords[..., 1] - cc[1]) / ff[1]
+        cam = np.concatenate([coords, np.ones(coords.shape[:-1] + (1,))], axis=-1)
+        world = cam @ np.asarray(R[v], dtype=np.float64) + np.asarray(t[v], dtype=np.float64)   # (R^T x)^T = x^T R
+        poses[:, v] = np.concatenate([joints, vis[..., None]], axis=-1)
+        rays[:, v] = world
+        centers[:, v, 0] = t[v]
+    return poses.astype(np.float32), rays.astype(np.float32), centers.astype(np.float32)

@@ -1,0 +1,73 @@
+"""K6 (MPJPE accumulators) and N2 (input builder) kernels against the oracle restatements."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpl_oracle
+from openmpl_b200 import inputs, metric, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,J,masked", [(1, 17, False), (50, 17, False), (50, 17, True), (4097, 17, True), (33, 40, True), (0, 17, False)])
+def test_mpjpe_accumulator_matches_reference_metric(B, J, masked):
+    rng = np.random.default_rng(B + J)
+    pred = rng.normal(size=(B, J, 3)).astype(np.float32)
+    gt = rng.normal(size=(B, J, 3)).astype(np.float32)
+    conf = None
+    if masked:
+        conf = (rng.random((B, J, 1)) > 0.2).astype(np.float32)
+        if B > 3:
+            conf[3, 0] = 0            # a masked root joint: blanks the pose in the root-relative metric
+    acc = metric.MpjpeAccumulator(J, output_in_meter=True)
+    half = B // 2                      # two updates must equal one: the sums are running
+    for sl in (slice(0, half), slice(half, B)):
+        acc.update(torch.from_numpy(pred[sl]).cuda(), torch.from_numpy(gt[sl]).cuda(),
+                   None if conf is None else torch.from_numpy(conf[sl]).cuda())
+    got = acc.acc.cpu().numpy()
+    if B == 0:
+        assert np.all(got == 0)
+        return
+    want = mpl_oracle.metric_sums(pred, gt, conf)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
+    res = acc.result()
+    a = mpl_oracle.evaluate(pred, gt, True, None if conf is None else np.broadcast_to(conf, (B, J, 3)), relative=False)
+    r = mpl_oracle.evaluate(pred, gt, True, None if conf is None else np.broadcast_to(conf, (B, J, 3)), relative=True)
+    np.testing.assert_allclose(res["pjpe_abs"], a["pjpe"], rtol=1e-9)
+    np.testing.assert_allclose(res["mpjpe_rel"], r["mpjpe"], rtol=1e-9)
+    np.testing.assert_allclose(np.nan_to_num(res["dist_abs"]), np.nan_to_num(a["dist_per_dim_per_kp"]), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(np.nan_to_num(res["dist_rel"]), np.nan_to_num(r["dist_per_dim_per_kp"]), rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind,V,B", [("h36m", 4, 64), ("cmu", 5, 257), ("h36m", 8, 3), ("cmu", 2, 0)])
+def test_input_builder_matches_dataset_math(kind, V, B):
+    rig = synth.make_rig(V, kind)
+    rng = np.random.default_rng(V * 100 + B)
+    w, h = rig.image_size
+    pix = np.concatenate([rng.uniform(-0.15 * w, 1.15 * w, (B, V, 17, 1)), rng.uniform(-0.15 * h, 1.15 * h, (B, V, 17, 1)),
+                          rng.uniform(0.05, 1.0, (B, V, 17, 1))], axis=-1).astype(np.float32)
+    if B:
+        pix[0, 0, 0, :2] = (0.0, 5.0)            # exactly on the border: "0 < x" is false -> confidence zeroed
+        pix[0, 0, 1, :2] = (w - 1.0, 5.0)
+    want = mpl_oracle.build_inputs(pix, rig.R, rig.t, rig.f, rig.c, rig.image_size)
+    calib = inputs.pack_calibration(rig.R, rig.t, rig.f, rig.c, rig.image_size)
+    got = inputs.build_inputs(torch.from_numpy(pix).cuda(), calib)
+    torch.cuda.synchronize()
+    for g, wv in zip(got, want):
+        np.testing.assert_allclose(g.cpu().numpy(), wv, rtol=0, atol=2e-7 * max(1.0, float(np.abs(wv).max()) if wv.size else 1.0))
+    if B:
+        assert float(got[0][0, 0, 0, 2]) == 0.0 and float(got[0][0, 0, 1, 2]) == 0.0
+        assert (got[0][..., 2] == 0).any() and (got[0][..., 2] > 0).any()
+
+
+def test_input_builder_reproduces_the_synthetic_generator():
+    """synth.make_batch (3D -> pixels -> inputs) and the kernel (pixels -> inputs) agree when fed the same pixels."""
+    rig = synth.make_rig(4, "h36m")
+    batch = synth.make_batch(200, rig, seed=5)
+    w, h = rig.image_size
+    # invert the screen normalisation to recover the (already clipped) pixels
+    px = (batch["poses"][..., :2].astype(np.float64) + np.array([1, h / w])) / 2 * w
+    pix = np.concatenate([px, batch["poses"][..., 2:3]], axis=-1).astype(np.float32)
+    got = inputs.build_inputs(torch.from_numpy(pix).cuda(), inputs.pack_calibration(rig.R, rig.t, rig.f, rig.c, rig.image_size))
+    np.testing.assert_allclose(got[1].cpu().numpy(), batch["rays"], atol=2e-3)     # pixel round-trip through fp32
+    np.testing.assert_allclose(got[2].cpu().numpy(), batch["centers"], atol=1e-6)

@@ -125,3 +125,17 @@ def test_metric_vs_live_reference():
         np.testing.assert_allclose(a[0], b[0])
         np.testing.assert_allclose(a[1], b[1])
     np.testing.assert_allclose(ev.calc_distance_per_dim(pred, gt)[0], mpl_oracle.calc_distance_per_dim(pred, gt)[0])
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if not (CASES[n]["kw"].get("deep_head") or CASES[n]["kw"].get("head_kadkhod")
+                                                            or CASES[n]["kw"].get("linear_weighted_mean"))])
+def test_torch_cpu_port_matches_golden(name):
+    """bench.py's CPU baseline (oracle/torch_port.py) is the reference's algorithm: fp32 round-off of the goldens."""
+    import torch
+    from oracle import torch_port
+    cfg, weights, batch = make_inputs(CASES[name])
+    g = load_golden(name)
+    p = {k: torch.from_numpy(v) for k, v in weights.items()}
+    out = torch_port.forward(p, cfg, *(torch.from_numpy(batch[k]) for k in ("poses", "rays", "centers"))).numpy()
+    assert np.abs(out - g["out64_0"]).max() <= 2e-5 * max(np.abs(g["out64_0"]).max(), 1.0)
+    assert np.abs(out - g["out32_0"]).max() <= 2e-5 * max(np.abs(g["out64_0"]).max(), 1.0)

@@ -1,0 +1,131 @@
+"""Parity of the CUDA path (through the nn.Module boundary and the C ABI) against the goldens minted from the
+unmodified reference and against the oracle on the same seeded inputs.  Run on the B200 box with `-m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import DMPJPE_MM, TOL, build_module, mpjpe_mm, oracle_outputs, rel_err, run_module
+from oracle.cases import CASES, make_inputs
+from openmpl_b200 import spec, synth
+
+pytestmark = pytest.mark.gpu
+
+TC_CASES = [n for n in CASES if not CASES[n]["kw"].get("no_transformer_fpt")]
+
+
+def _check_case(name, precision, packed=False):
+    case = CASES[name]
+    g = load_golden(name)
+    cfg, weights, batch = make_inputs(case)
+    m = build_module(case["kw"], weights, precision)
+    outs = run_module(m, batch, packed=packed)
+    assert m.last_launches > 0
+    n_out = 3 if case["kw"].get("head_kadkhod") else 1
+    assert len(outs) == n_out
+    for i, o in enumerate(outs):
+        ref = g[f"out64_{i}"]
+        assert o.shape == ref.shape and o.dtype == np.float32
+        e = rel_err(o, ref)
+        assert e <= TOL[precision], f"{name} [{precision}] out{i}: {e:.3e} of scale"
+    d = abs(mpjpe_mm(outs[0], batch["target"].astype(np.float64)) - mpjpe_mm(g["out64_0"], batch["target"].astype(np.float64)))
+    assert d <= DMPJPE_MM[precision], f"{name} [{precision}] dMPJPE {d:.4f} mm"
+    return outs
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fp32_path_matches_reference_goldens(name):
+    _check_case(name, "fp32")
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_tf32_path_matches_reference_goldens(name):
+    _check_case(name, "tf32")
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_bf16_path_matches_reference_goldens(name):
+    _check_case(name, "bf16")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_packed_and_list_inputs_agree_bitwise(precision):
+    for name in ("flag_hm0flags_small", "cmu0_v2_d2"):
+        a = _check_case(name, precision, packed=False)
+        b = _check_case(name, precision, packed=True)
+        np.testing.assert_array_equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_chunking_ragged_and_empty_batches(precision):
+    """Arbitrary B: the last chunk is ragged, B = 1 and B = 0 work, and chunking never changes a pose's result."""
+    case = CASES["flag_hm0flags_small"]
+    cfg = spec.make_config(**case["kw"])
+    weights = synth.named_weights(spec.param_spec(cfg), seed=3)
+    rig = synth.make_rig(cfg.V)
+    batch = synth.make_batch(37, rig, seed=11)
+    m = build_module(case["kw"], weights, precision)
+    full = run_module(m, batch)[0]
+    ref = oracle_outputs(cfg, weights, batch)[0]
+    assert rel_err(full, ref) <= TOL[precision]
+    m.set_chunk_poses(8)                                           # 37 = 4 * 8 + 5
+    chunked = run_module(m, batch)[0]
+    np.testing.assert_array_equal(chunked, full)
+    one = run_module(m, {k: v[5:6] for k, v in batch.items()})[0]
+    np.testing.assert_array_equal(one[0], full[5])
+    empty = run_module(m, {k: v[:0] for k, v in batch.items()})[0]
+    assert empty.shape == (0, 17, 3)
+
+
+def test_cpu_inputs_are_accepted_and_output_is_on_the_device():
+    case = CASES["flag_conf3rd"]
+    cfg, weights, batch = make_inputs(case)
+    m = build_module(case["kw"], weights, "fp32")
+    V = cfg.V
+    args = [[torch.from_numpy(np.ascontiguousarray(batch[k][:, v])) for v in range(V)] for k in ("poses", "rays", "centers")]
+    out = m(args[0], rays=args[1], centers=args[2])
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+    assert rel_err(out.cpu().numpy(), load_golden("flag_conf3rd")["out64_0"]) <= TOL["fp32"]
+
+
+def test_weights_are_repacked_after_load_state_dict():
+    case = CASES["flag_learn3d"]
+    cfg, weights, batch = make_inputs(case)
+    m = build_module(case["kw"], weights, "fp32")
+    a = run_module(m, batch)[0]
+    w2 = synth.named_weights(spec.param_spec(cfg), seed=99)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w2.items()})
+    b = run_module(m, batch)[0]
+    ref = oracle_outputs(cfg, w2, batch)[0]
+    assert rel_err(b, ref) <= TOL["fp32"] and rel_err(a, ref) > 1e-2
+
+
+@pytest.mark.parametrize("precision,name,B", [("bf16", "hm0_v4_d12", 2048), ("tf32", "hm0_v4_d12", 1024),
+                                             ("bf16", "chosen_v4_d12", 4096), ("bf16", "kptok_v4_d12", 2048),
+                                             ("bf16", "cmu_v5_d2_hm0flags", 3000)])
+def test_large_batch_pose_independence_against_oracle(precision, name, B):
+    """Size-independent property: a pose's output does not depend on the batch around it.  A few hundred poses
+    sampled from a large forward (several GEMM tiles, ragged tile tails) are checked against the oracle."""
+    case = CASES[name]
+    cfg = spec.make_config(**case["kw"])
+    weights = synth.named_weights(spec.param_spec(cfg), seed=case["wseed"])
+    rig = synth.make_rig(cfg.V, case["rig"])
+    batch = synth.make_batch(B, rig, seed=42)
+    m = build_module(case["kw"], weights, precision)
+    out = run_module(m, batch, packed=True)[0]
+    assert np.isfinite(out).all()
+    idx = np.unique(np.concatenate([np.arange(8), np.arange(B - 8, B), np.random.default_rng(0).choice(B, 48, replace=False)]))
+    sub = {k: v[idx] for k, v in batch.items()}
+    ref = oracle_outputs(cfg, weights, sub)[0]
+    e = rel_err(out[idx], ref)
+    assert e <= TOL[precision], f"{name} [{precision}] B={B}: {e:.3e}"
+    d = abs(mpjpe_mm(out[idx], sub["target"].astype(np.float64)) - mpjpe_mm(ref, sub["target"].astype(np.float64)))
+    assert d <= DMPJPE_MM[precision]
+    # and the same poses alone give the same numbers (bitwise: every kernel is row-independent)
+    alone = run_module(m, sub, packed=True)[0]
+    np.testing.assert_array_equal(alone, out[idx])
+
+
+def test_native_library_is_what_ran():
+    maps = open("/proc/self/maps").read()
+    assert "libmpl_b200.so" in maps
