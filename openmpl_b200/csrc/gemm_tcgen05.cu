@@ -5,7 +5,8 @@
 //   warp 0     TMA producer   cp.async.bulk.tensor 2D tiles (128B swizzle) into a ring of shared-memory stages
 //   warp 1     MMA issuer     one thread issues tcgen05.mma (kind::f16 bf16 or kind::tf32), accumulators in TMEM
 //   warp 2     TMEM allocator 512 columns = two 256-column accumulator stages (MMA of tile i+1 overlaps epilogue of i)
-//   warps 4-7  epilogue       tcgen05.ld -> registers -> bias / exact GELU / fp32 residual add -> global
+//   warps 4-11 epilogue       tcgen05.ld -> registers -> bias / GELU / fp32 residual add -> global (two warps per
+//                             TMEM lane quarter, two 32-column chunks in flight per warp)
 // CG = 1: one CTA per 128 x 256 output tile.  CG = 2: a CTA pair (cluster 2x1x1, cta_group::2) per 256 x 256 tile, each
 // CTA staging half of A and half of W, which halves the shared-memory and L2 operand traffic per MMA.
 // Every FPT width is a multiple of 17 (D = 1088 = 17*64): ragged N tiles use a narrower UMMA N (multiple of 16) and
@@ -25,7 +26,8 @@ constexpr int BM = 128;          // accumulator rows per CTA (TMEM lanes)
 constexpr int BN = 256;          // accumulator columns per tile
 constexpr int KB_BYTES = 128;    // bytes of K per stage row = one 128B swizzle span
 constexpr int UMMA_K_BYTES = 32; // bytes of K per tcgen05.mma
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter: even / odd 32-column chunks
+constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
 
 template <int CG>
@@ -77,7 +79,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&v)[NV], const fl
   }
   if constexpr (EPI == 1) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) f[i] = gelu_erf(f[i]);
+    for (int i = 0; i < NV; ++i) f[i] = (KIND == 0) ? gelu_erf_fast(f[i]) : gelu_erf(f[i]);
   }
   if (!row_ok) return;
   if constexpr (EPI == 2) {
@@ -145,12 +147,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), CG);  // leader's arrive.expect_tx (+ the peer producer's remote arrive)
+      ptx::mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx covers the bytes of both CTAs of a pair
       ptx::mbar_init(empty_bar(s), 1);  // one tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);        // one tcgen05.commit
-      ptx::mbar_init(tempty_bar(s), 4 * CG);  // one arrive per epilogue warp of every CTA of the pair
+      ptx::mbar_init(tempty_bar(s), NUM_EPI_WARPS * CG);  // one arrive per epilogue warp of every CTA of the pair
     }
     ptx::fence_barrier_init();
   }
@@ -192,8 +194,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
           } else {
             const uint32_t lbar = leader_full0 + 8u * stage;
+            // the peer's bytes may land before this expect_tx: the phase still cannot complete without this arrive
             if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-            else ptx::mbar_arrive_cluster(lbar);
             ptx::tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
             ptx::tma_load_2d_pair(b_dst, &tmB, lbar, kb * BK, n0);
           }
@@ -239,7 +241,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
-    const int q = warp - 4;  // TMEM lane quarter this warp may read (warp id % 4)
+    const int q = warp & 3;          // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 4) >> 2;  // 0: even 32-column chunks, 1: odd chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t leader_tempty0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : 0u;
@@ -249,21 +252,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n_size = min(BN, N - n_blk * BN);
       const int64_t row = m_blk * BM * CG + cta_rank * BM + q * 32 + lane;
       const bool row_ok = row < M;
+      const int ncol0 = n_blk * BN;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      int c = 0;
-      for (; c + 32 <= n_size; c += 32) {
+      int c = half * 32;
+      for (; c + 96 <= n_size; c += 128) {  // two chunks (c, c + 64) per wait
+        uint32_t va[32], vb[32];
+        ptx::tmem_ld_32x32(taddr + c, va);
+        ptx::tmem_ld_32x32(taddr + c + 64, vb);
+        ptx::tmem_ld_wait();
+        epilogue_store<KIND, EPI, 32>(va, bias, Y, row, N, ncol0 + c, row_ok);
+        epilogue_store<KIND, EPI, 32>(vb, bias, Y, row, N, ncol0 + c + 64, row_ok);
+      }
+      for (; c + 32 <= n_size; c += 64) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(taddr + c, v);
         ptx::tmem_ld_wait();
-        epilogue_store<KIND, EPI, 32>(v, bias, Y, row, N, n_blk * BN + c, row_ok);
+        epilogue_store<KIND, EPI, 32>(v, bias, Y, row, N, ncol0 + c, row_ok);
       }
-      if (c < n_size) {  // n_size % 32 == 16
+      if (c < n_size) {  // n_size % 32 == 16: the trailing half chunk belongs to the warp whose turn it is
         uint32_t v[16];
         ptx::tmem_ld_32x16(taddr + c, v);
         ptx::tmem_ld_wait();
-        epilogue_store<KIND, EPI, 16>(v, bias, Y, row, N, n_blk * BN + c, row_ok);
+        epilogue_store<KIND, EPI, 16>(v, bias, Y, row, N, ncol0 + c, row_ok);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -323,7 +335,7 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, i
   return MPL_OK;
 }
 
-int g_gemm_cta_group = 1;
+int g_gemm_cta_group = 2;  // CTA pairs by default: half the operand traffic per SM (measured faster on every FPT shape)
 
 template <int CG, int KIND, int EPI>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* Y, int64_t M, int N, int K,

@@ -1,6 +1,9 @@
 // Shape-generic CUDA kernels of the MPL lifter forward: every constructor flag of the reference is served by these
 // (fp32 CUDA-core arithmetic).  The hot configurations additionally have tensor-core kernels (gemm_tcgen05.cu,
 // spt_fused.cu) that replace the Linear / attention launches.
+#include <algorithm>
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace mpl {
@@ -413,11 +416,252 @@ __global__ void __launch_bounds__(128) attention_kernel(const TI* __restrict__ q
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Narrow heads (hd <= 8; the 17-token spatial sets and the V*J keypoint-token sets): a CTA stages the q|k|v rows of G
+// whole sets in shared memory with coalesced 16-byte loads, then one thread per (set, head, query) runs the exact
+// two-pass softmax (max, then exp / sum) over the N keys reading k_j / v_j as broadcast shared-memory vectors.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename TI, typename TO, bool TF32_OUT, int HD>
+__global__ void __launch_bounds__(256) attention_narrow_kernel(const TI* __restrict__ qkv, TO* __restrict__ out, int64_t sets,
+                                                               int N, int H, int G, float scale, const float* __restrict__ conf) {
+  extern __shared__ float sm[];  // [G][N][3C]
+  const int C = H * HD;
+  const int ld = 3 * C;
+  const int64_t set0 = (int64_t)blockIdx.x * G;
+  const int g_here = (int)min((int64_t)G, sets - set0);
+  const int64_t n_el = (int64_t)g_here * N * ld;
+  const TI* src = qkv + set0 * N * ld;
+  for (int64_t i = threadIdx.x; i < n_el; i += blockDim.x) sm[i] = ldf(src + i);
+  __syncthreads();
+  const int items = g_here * H * N;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int i = it % N;
+    const int h = (it / N) % H;
+    const int g = it / (N * H);
+    const float* base = sm + (size_t)g * N * ld;
+    const float* q = base + i * ld + h * HD;
+    const float* kb = base + C + h * HD;
+    const float* vb = base + 2 * C + h * HD;
+    float qr[HD];
+#pragma unroll
+    for (int t = 0; t < HD; ++t) qr[t] = q[t] * scale;
+    float mx = -INFINITY;
+    for (int j = 0; j < N; ++j) {
+      const float* kj = kb + j * ld;
+      float sc = 0.f;
+#pragma unroll
+      for (int t = 0; t < HD; ++t) sc = fmaf(qr[t], kj[t], sc);
+      mx = fmaxf(mx, sc);
+    }
+    float sum = 0.f, acc[HD];
+#pragma unroll
+    for (int t = 0; t < HD; ++t) acc[t] = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float* kj = kb + j * ld;
+      const float* vj = vb + j * ld;
+      float sc = 0.f;
+#pragma unroll
+      for (int t = 0; t < HD; ++t) sc = fmaf(qr[t], kj[t], sc);
+      const float e = expf(sc - mx);
+      sum += e;
+#pragma unroll
+      for (int t = 0; t < HD; ++t) acc[t] = fmaf(e, vj[t], acc[t]);
+    }
+    float norm = 1.0f / sum;
+    if (conf != nullptr) norm *= __ldg(conf + (set0 + g) * N + i);  // post-softmax query-row scaling, multiview_mpl.py:61-62
+    TO* o = out + ((set0 + g) * N + i) * (int64_t)C + h * HD;
+#pragma unroll
+    for (int t = 0; t < HD; ++t) {
+      float r = acc[t] * norm;
+      if (TF32_OUT) r = round_tf32(r);
+      stf(o + t, r);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4 view-token attention of the FPT (N = V tokens of width D, hd = D / H = 136 | 68): HBM-bound, 3 D in / D out per
+// row.  One CTA per pose, one thread per CE-element chunk of the row (D / CE threads): each thread loads its chunk of
+// q, k, v for all V views with 16- or 8-byte loads, forms partial V x V scores over its chunk, the chunks of a head are
+// summed through shared memory, softmax on V values, then the thread writes its chunk of all V output rows.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, int CE> struct ChunkIO;
+template <> struct ChunkIO<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct ChunkIO<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[4]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[4]) {
+    uint2 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+template <> struct ChunkIO<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+    const float4 u = *reinterpret_cast<const float4*>(p);
+    f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+
+template <typename T, int V, int CE, bool TF32_OUT>
+__global__ void __launch_bounds__(288) attention_views_kernel(const T* __restrict__ qkv, T* __restrict__ out, int64_t poses,
+                                                              int D, int hd, float scale) {
+  extern __shared__ float sm[];       // partial [nchunks][V*V] then probs [H][V*V]
+  const int nchunks = D / CE;         // == blockDim.x
+  const int cph = hd / CE;            // chunks per head
+  const int H = D / hd;
+  const int c = threadIdx.x;
+  float* part = sm;
+  float* prob = sm + (size_t)nchunks * V * V;
+  for (int64_t pose = blockIdx.x; pose < poses; pose += gridDim.x) {
+    const T* row0 = qkv + pose * V * 3 * (int64_t)D;
+    float q[V][CE], k[V][CE];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      ChunkIO<T, CE>::load(row0 + (int64_t)v * 3 * D + c * CE, q[v]);
+      ChunkIO<T, CE>::load(row0 + (int64_t)v * 3 * D + D + c * CE, k[v]);
+    }
+    float vv[V][CE];
+#pragma unroll
+    for (int v = 0; v < V; ++v) ChunkIO<T, CE>::load(row0 + (int64_t)v * 3 * D + 2 * D + c * CE, vv[v]);
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < CE; ++e) a = fmaf(q[i][e], k[j][e], a);
+        part[c * (V * V) + i * V + j] = a;
+      }
+    __syncthreads();
+    // H * V query rows: sum the head's chunk partials, softmax over the V keys
+    for (int r = threadIdx.x; r < H * V; r += blockDim.x) {
+      const int h = r / V, i = r % V;
+      float sc[V];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float a = 0.f;
+        for (int cc = 0; cc < cph; ++cc) a += part[(h * cph + cc) * (V * V) + i * V + j];
+        sc[j] = a * scale;
+        mx = fmaxf(mx, sc[j]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int j = 0; j < V; ++j) prob[h * (V * V) + i * V + j] = sc[j] * inv;
+    }
+    __syncthreads();
+    const int h = c / cph;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float o[CE];
+#pragma unroll
+      for (int e = 0; e < CE; ++e) o[e] = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float pj = prob[h * (V * V) + i * V + j];
+#pragma unroll
+        for (int e = 0; e < CE; ++e) o[e] = fmaf(pj, vv[j][e], o[e]);
+      }
+      if (TF32_OUT) {
+#pragma unroll
+        for (int e = 0; e < CE; ++e) o[e] = round_tf32(o[e]);
+      }
+      ChunkIO<T, CE>::store(out + (pose * V + i) * (int64_t)D + c * CE, o);
+    }
+    __syncthreads();  // prob / part are reused by the next pose
+  }
+}
+
+template <typename T, int CE, bool TF32_OUT>
+static int launch_attention_views(const T* qkv, T* out, int64_t poses, int V, int D, int hd, float scale, cudaStream_t s) {
+  const int threads = D / CE;
+  const int H = D / hd;
+  const size_t smem = ((size_t)threads + H) * V * V * sizeof(float);
+  const unsigned grid = (unsigned)std::min<int64_t>(poses, (int64_t)kNumSMs * 32);
+#define MPL_AV(VV)                                                                                                      \
+  case VV: {                                                                                                            \
+    auto kern = attention_views_kernel<T, VV, CE, TF32_OUT>;                                                            \
+    if (smem > 48 * 1024) MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, threads, smem, s>>>(qkv, out, poses, D, hd, scale);                                                    \
+  } break;
+  switch (V) {
+    MPL_AV(2) MPL_AV(3) MPL_AV(4) MPL_AV(5) MPL_AV(6) MPL_AV(7) MPL_AV(8)
+    default: return MPL_ERR_UNSUPPORTED;
+  }
+#undef MPL_AV
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
 template <typename TI, typename TO, bool TF32_OUT>
 static int launch_attention_any(const TI* qkv, TO* out, int64_t sets, int N, int H, int hd, float scale, const float* conf,
                                 cudaStream_t s) {
   const int64_t total = sets * H * N;
   if (total == 0) return MPL_OK;
+  const int C = H * hd;
+  // (1) view tokens with wide heads: the HBM-bound K4 kernel (same element type in and out, no confidence scaling)
+  if constexpr (std::is_same<TI, TO>::value) {
+    if (conf == nullptr && N >= 2 && N <= 8 && hd >= 16) {
+      constexpr bool is_bf16 = std::is_same<TI, __nv_bfloat16>::value;
+      const bool aligned = (reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+      if constexpr (is_bf16) {
+        if (aligned && hd % 8 == 0 && N <= 4 && C / 8 <= 288 && C / 8 >= H * N)
+          return launch_attention_views<TI, 8, TF32_OUT>(qkv, out, sets, N, C, hd, scale, s);
+        if (aligned && hd % 4 == 0 && C / 4 <= 288 && C / 4 >= H * N)
+          return launch_attention_views<TI, 4, TF32_OUT>(qkv, out, sets, N, C, hd, scale, s);
+      } else {
+        if (aligned && hd % 4 == 0 && C / 4 <= 288 && C / 4 >= H * N)
+          return launch_attention_views<TI, 4, TF32_OUT>(qkv, out, sets, N, C, hd, scale, s);
+      }
+    }
+  }
+  // (2) narrow heads: whole sets staged in shared memory
+  if (hd == 4 || hd == 8 || hd == 2) {
+    const size_t per_set = (size_t)N * 3 * C * sizeof(float);
+    if (per_set <= 96 * 1024) {
+      int G = (int)std::max<size_t>(1, std::min<size_t>(48 * 1024 / per_set, 16));
+      const size_t smem = per_set * G;
+      const unsigned grid = (unsigned)ceil_div(sets, G);
+#define MPL_AN(HD)                                                                                                   \
+  {                                                                                                                  \
+    auto kern = attention_narrow_kernel<TI, TO, TF32_OUT, HD>;                                                       \
+    if (smem > 48 * 1024) MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+    kern<<<grid, 256, smem, s>>>(qkv, out, sets, N, H, G, scale, conf);                                              \
+  }
+      if (hd == 4) MPL_AN(4) else if (hd == 8) MPL_AN(8) else MPL_AN(2)
+#undef MPL_AN
+      MPL_LAUNCH_CHECK();
+      return MPL_OK;
+    }
+  }
+  // (3) anything else: one warp per (set, head, query)
   const size_t smem = 4 * (size_t)N * sizeof(float);
   attention_kernel<TI, TO, TF32_OUT><<<(unsigned)ceil_div(total, 4), 128, smem, s>>>(qkv, out, sets, N, H, hd, scale, conf);
   MPL_LAUNCH_CHECK();

@@ -57,6 +57,7 @@ struct MplModel {
   int ray_layout;  // 0 none, 1 interleave, 2 append
   int n_out;
   bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
+  bool spt_fused;  // the SPT stack runs as the single fused bf16-mma kernel (bf16 mode, d=32, H=8, J=17)
   std::vector<ParamInfo> params;
   std::unordered_map<std::string, int> index;
   std::vector<Derived> derived;
@@ -225,6 +226,10 @@ static void build_tables(MplModel* m) {
   }
   const int maxdim = std::max(m->dim, m->fpt_dim);
   add_derived(m, "zeros", 3 * (int64_t)maxdim, 4);
+  if (m->spt_fused) {
+    const int stacks = m->multi ? V : 1;
+    for (int st = 0; st < stacks; ++st) add_derived(m, "sptpack:" + std::to_string(st), (int64_t)m->depth * spt_fused_layer_bytes(), 1);
+  }
   if (m->fpt_tc) {
     const int esz = (d.precision == MPL_PREC_BF16) ? 2 : 4;
     const char* tag = (d.precision == MPL_PREC_BF16) ? "bf16:" : "tf32:";
@@ -286,7 +291,7 @@ static Workspace layout_workspace(const MplModel* m, int64_t Bc, uint8_t* base) 
   const int d = m->dim;
   w.xs = (float*)take(Rs * d * 4);
   w.xn = (float*)take(Rs * d * 4);
-  if (!m->d.no_transformer_spt) {
+  if (!m->d.no_transformer_spt && !m->spt_fused) {
     w.qkv = (float*)take(Rs * 3 * d * 4);
     w.att = (float*)take(Rs * d * 4);
     w.hid = (float*)take(Rs * m->spt_hidden * 4);
@@ -462,29 +467,38 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   ea.x = w.xs;
   ea.conf = w.conf;
   LC(CAT_EMBED, launch_embed(ea, s));
-  // ---- SPT blocks (multiview_mpl.py:400-410): conf-weighted pass, last block twice ----
-  if (!d.no_transformer_spt && m->depth > 0) {
+  // ---- SPT blocks (multiview_mpl.py:400-410): conf-weighted pass, last block twice; then Spatial_norm (:412) ----
+  const int64_t Rs = (int64_t)V * Bc * J;
+  if (m->spt_fused) {
     const int hd = dim / m->H;
     const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
-    const int stacks = m->multi ? V : 1;
-    const int64_t rows_per_stack = (m->multi ? 1 : V) * Bc * J;
-    for (int st = 0; st < stacks; ++st) {
-      float* x = w.xs + (int64_t)st * rows_per_stack * dim;
-      const float* cf = w.conf ? w.conf + (int64_t)st * rows_per_stack : nullptr;
-      const std::string vp = m->multi ? std::to_string(st) + "." : std::string("");
-      for (int ix = 0; ix < m->depth; ++ix) {
-        const BlockW bw = block_weights(m, P, "Spatial_blocks." + vp + std::to_string(ix) + ".", false);
-        const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
-        if (cf != nullptr)
-          MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, cf, w.xn, w.qkv, w.att, w.hid, s));
-        for (int r = 0; r < reps; ++r)
-          MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, nullptr, w.xn, w.qkv, w.att, w.hid, s));
+    const void* wp[kMaxViews];
+    for (int v = 0; v < V; ++v) wp[v] = P.dv("sptpack:" + std::to_string(m->multi ? v : 0));
+    LC(CAT_SPT_FUSED, launch_spt_fused(w.xs, w.xn, wp, V, Bc, m->depth, scale, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"),
+                                       w.conf, s));
+  } else {
+    if (!d.no_transformer_spt && m->depth > 0) {
+      const int hd = dim / m->H;
+      const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
+      const int stacks = m->multi ? V : 1;
+      const int64_t rows_per_stack = (m->multi ? 1 : V) * Bc * J;
+      for (int st = 0; st < stacks; ++st) {
+        float* x = w.xs + (int64_t)st * rows_per_stack * dim;
+        const float* cf = w.conf ? w.conf + (int64_t)st * rows_per_stack : nullptr;
+        const std::string vp = m->multi ? std::to_string(st) + "." : std::string("");
+        for (int ix = 0; ix < m->depth; ++ix) {
+          const BlockW bw = block_weights(m, P, "Spatial_blocks." + vp + std::to_string(ix) + ".", false);
+          const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
+          if (cf != nullptr)
+            MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, cf, w.xn, w.qkv, w.att, w.hid, s));
+          for (int r = 0; r < reps; ++r)
+            MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, nullptr, w.xn, w.qkv, w.att, w.hid, s));
+        }
       }
     }
+    LC(CAT_TOKEN, launch_layernorm(w.xs, dim, dim, dim, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"), 1e-6f, w.xn, dim, Rs, dim, s));
   }
-  // ---- Spatial_norm (:412) + token build (:463-499) ----
-  const int64_t Rs = (int64_t)V * Bc * J;
-  LC(CAT_TOKEN, launch_layernorm(w.xs, dim, dim, dim, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"), 1e-6f, w.xn, dim, Rs, dim, s));
+  // ---- token build (:463-499) ----
   TokenArgs ta{};
   ta.xn = w.xn;
   for (int v = 0; v < V; ++v) {
@@ -656,6 +670,8 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
     delete m;
     return st;
   }
+  m->spt_fused = d.precision == MPL_PREC_BF16 && !d.no_transformer_spt && m->depth > 0 &&
+                 spt_fused_supports(m->J, m->dim, m->H, m->spt_hidden);
   m->fpt_tc = false;
   if (d.precision != MPL_PREC_FP32 && !d.no_transformer_fpt && m->depth > 0) {
     const bool ok = gemm_tcgen05_supports(3 * m->fpt_dim, m->fpt_dim, d.precision) &&
@@ -786,6 +802,20 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
     const Derived& z = m->derived[m->dindex.at("zeros")];
     MPL_CUDA(cudaMemsetAsync(base + z.offset, 0, (size_t)z.numel * 4, s));
   }
+  if (m->spt_fused) {
+    const int stacks = m->multi ? m->V : 1;
+    for (int st = 0; st < stacks; ++st) {
+      const Derived& dd = m->derived[m->dindex.at("sptpack:" + std::to_string(st))];
+      for (int l = 0; l < m->depth; ++l) {
+        const std::string p = "Spatial_blocks." + (m->multi ? std::to_string(st) + "." : std::string("")) + std::to_string(l) + ".";
+        MPL_TRY(launch_spt_pack_layer(P.f(p + "norm1.weight"), P.f(p + "norm1.bias"), P.f(p + "attn.qkv.weight"),
+                                      m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr, P.f(p + "attn.proj.weight"),
+                                      P.f(p + "attn.proj.bias"), P.f(p + "norm2.weight"), P.f(p + "norm2.bias"),
+                                      P.f(p + "mlp.fc1.weight"), P.f(p + "mlp.fc1.bias"), P.f(p + "mlp.fc2.weight"),
+                                      P.f(p + "mlp.fc2.bias"), base + dd.offset + (size_t)l * spt_fused_layer_bytes(), s));
+      }
+    }
+  }
   if (m->fpt_tc) {
     const bool bf = m->d.precision == MPL_PREC_BF16;
     const std::string tag = bf ? "bf16:" : "tf32:";
@@ -823,8 +853,16 @@ int mpl_forward(MplModel* m, const void* packed, const float* const* poses, cons
                 const float* const* centers, int64_t pose_stride, int64_t center_stride, float* out, float* aux1,
                 float* aux2, int64_t batch, void* workspace, size_t workspace_bytes, mpl_stream_t stream) {
   MPL_API_BEGIN
-  if (m == nullptr || packed == nullptr || poses == nullptr || out == nullptr || batch < 0) {
-    set_error("mpl_forward: null argument or negative batch");
+  if (m == nullptr || batch < 0) {
+    set_error("mpl_forward: null handle or negative batch");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  if (batch == 0) {  // empty batch: nothing to enqueue (device pointers of empty tensors are null)
+    m->launches = 0;
+    return MPL_OK;
+  }
+  if (packed == nullptr || poses == nullptr || out == nullptr) {
+    set_error("mpl_forward: null argument");
     return MPL_ERR_INVALID_ARGUMENT;
   }
   const MplDesc& d = m->d;
@@ -878,6 +916,7 @@ int64_t mpl_last_launch_count(const MplModel* m) { return m ? m->launches : 0; }
 
 int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t batch, int num_joints,
                          float unit_scale, double* acc, mpl_stream_t stream) {
+  if (batch == 0 && acc != nullptr) return MPL_OK;
   if (pred == nullptr || gt == nullptr || acc == nullptr || batch < 0 || num_joints < 1) {
     set_error("mpl_mpjpe_accumulate: bad argument");
     return MPL_ERR_INVALID_ARGUMENT;
@@ -887,6 +926,7 @@ int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d
 
 int mpl_build_inputs(const float* pix, const double* calib, int64_t batch, int num_views, int num_joints, float* poses,
                      float* rays, float* centers, mpl_stream_t stream) {
+  if (batch == 0) return MPL_OK;
   if (pix == nullptr || calib == nullptr || poses == nullptr || rays == nullptr || centers == nullptr || batch < 0) {
     set_error("mpl_build_inputs: bad argument");
     return MPL_ERR_INVALID_ARGUMENT;
