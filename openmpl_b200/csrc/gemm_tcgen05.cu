@@ -5,8 +5,9 @@
 //   warp 0     TMA producer   cp.async.bulk.tensor 2D tiles (128B swizzle) into a ring of shared-memory stages
 //   warp 1     MMA issuer     one thread issues tcgen05.mma (kind::f16 bf16 or kind::tf32), accumulators in TMEM
 //   warp 2     TMEM allocator 512 columns = two 256-column accumulator stages (MMA of tile i+1 overlaps epilogue of i)
-//   warps 4-11 epilogue       tcgen05.ld -> registers -> bias / GELU / fp32 residual add -> global (two warps per
-//                             TMEM lane quarter, two 32-column chunks in flight per warp)
+//   warps 4-11 epilogue       tcgen05.ld -> registers -> bias / GELU -> 128B-swizzled staging tile in shared memory ->
+//                             TMA store (bf16 / fp32) or TMA reduce-add (the fp32 residual stream is updated in L2,
+//                             never read by the SM).  Two warps per TMEM lane quarter, 64 columns per step.
 // CG = 1: one CTA per 128 x 256 output tile.  CG = 2: a CTA pair (cluster 2x1x1, cta_group::2) per 256 x 256 tile, each
 // CTA staging half of A and half of W, which halves the shared-memory and L2 operand traffic per MMA.
 // Every FPT width is a multiple of 17 (D = 1088 = 17*64): ragged N tiles use a narrower UMMA N (multiple of 16) and
@@ -36,9 +37,10 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CG;                    // W rows staged per CTA
   static constexpr int B_BYTES = B_ROWS * KB_BYTES;         // 32 KB / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // 48 KB / 32 KB
-  static constexpr int STAGES = (CG == 1) ? 4 : 6;          // 192 KB of operand ring either way
+  static constexpr int STAGES = (CG == 1) ? 4 : 6;          // 192 KB of operand ring: the kernel is load-latency bound
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096; // per epilogue warp: one 32-row x 128-byte output box
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
 };
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1 (sm_100)
@@ -65,13 +67,13 @@ __device__ __forceinline__ float round_tf32_dev(float x) {
 }
 
 // EPI: 0 bias -> operand dtype, 1 bias + GELU -> operand dtype, 2 Y(fp32) += acc + bias, 3 bias -> fp32
-template <int KIND, int EPI, int NV>
-__device__ __forceinline__ void epilogue_store(const uint32_t (&v)[NV], const float* __restrict__ bias, void* Y, int64_t row,
-                                               int N, int n, bool row_ok) {
-  float f[NV];
+// accumulator chunk (32 columns of this lane's row) -> + bias (-> GELU) as fp32
+template <int KIND, int EPI>
+__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], const float* __restrict__ bias, int n, int N, float (&f)[32]) {
+  // columns >= N (ragged last tile) are clipped by the TMA store; their bias reads are clamped into the array
 #pragma unroll
-  for (int i = 0; i < NV; i += 4) {
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + min(n + i, N - 4)));
     f[i] = __uint_as_float(v[i]) + b4.x;
     f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
     f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
@@ -79,63 +81,53 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&v)[NV], const fl
   }
   if constexpr (EPI == 1) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) f[i] = (KIND == 0) ? gelu_erf_fast(f[i]) : gelu_erf(f[i]);
+    for (int i = 0; i < 32; ++i) f[i] = (KIND == 0) ? gelu_erf_fast(f[i]) : round_tf32_dev(gelu_erf(f[i]));
   }
-  if (!row_ok) return;
-  if constexpr (EPI == 2) {
-    float4* y = reinterpret_cast<float4*>(reinterpret_cast<float*>(Y) + row * N + n);
+}
+
+// one lane's 32 fp32 values -> its 128-byte row of a 32-row SWIZZLE_128B box (16-byte chunk j lands at j ^ (row & 7))
+__device__ __forceinline__ void stage_row_f32(uint32_t box, int lane, const float (&f)[32]) {
+  const uint32_t rowaddr = box + lane * 128;
 #pragma unroll
-    for (int i = 0; i < NV / 4; ++i) {
-      float4 r = y[i];
-      r.x += f[4 * i]; r.y += f[4 * i + 1]; r.z += f[4 * i + 2]; r.w += f[4 * i + 3];
-      y[i] = r;
-    }
-  } else if constexpr (EPI == 3 || KIND == 1) {
-    float4* y = reinterpret_cast<float4*>(reinterpret_cast<float*>(Y) + row * N + n);
+  for (int j = 0; j < 8; ++j)
+    ptx::st_shared_v4(rowaddr + ((j ^ (lane & 7)) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                      __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+}
+// 32 fp32 values -> bf16, chunks j0 .. j0+3 of the lane's 128-byte row (a 64-column bf16 box takes two calls)
+__device__ __forceinline__ void stage_row_bf16(uint32_t box, int lane, int j0, const float (&f)[32]) {
+  const uint32_t rowaddr = box + lane * 128;
 #pragma unroll
-    for (int i = 0; i < NV / 4; ++i) {
-      float4 r = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-      if constexpr (KIND == 1 && EPI == 1) {  // feeds the next kind::tf32 GEMM: round-to-nearest once, here
-        r.x = round_tf32_dev(r.x); r.y = round_tf32_dev(r.y); r.z = round_tf32_dev(r.z); r.w = round_tf32_dev(r.w);
-      }
-      y[i] = r;
-    }
-  } else {
-    uint4* y = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(Y) + row * N + n);
-#pragma unroll
-    for (int i = 0; i < NV / 8; ++i) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * i], f[8 * i + 1]);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * i + 2], f[8 * i + 3]);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * i + 4], f[8 * i + 5]);
-      __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * i + 6], f[8 * i + 7]);
-      uint4 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&p0);
-      pk.y = *reinterpret_cast<uint32_t*>(&p1);
-      pk.z = *reinterpret_cast<uint32_t*>(&p2);
-      pk.w = *reinterpret_cast<uint32_t*>(&p3);
-      y[i] = pk;
-    }
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+    ptx::st_shared_v4(rowaddr + (((j0 + j) ^ (lane & 7)) << 4), *reinterpret_cast<uint32_t*>(&p0),
+                      *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
   }
 }
 
 template <int CG, int KIND, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const float* __restrict__ bias, void* Y, int64_t M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int64_t M, int N, int K,
+                    int bn) {  // bn: output-tile width (256 / 192 / 128), chosen so that no interior tile is narrow
   using C = Cfg<CG>;
   constexpr int ESZ = (KIND == 0) ? 2 : 4;
   constexpr int BK = KB_BYTES / ESZ;  // K elements per stage
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte aligned bases
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;  // 1024-aligned: stage sizes are multiples of 1 KB
+  const uint32_t bar_base = staging_base + C::STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + 8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
@@ -144,6 +136,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    ptx::prefetch_tensormap(&tmY);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -165,7 +158,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int n_tiles = (N + BN - 1) / BN;
+  const int n_tiles = (N + bn - 1) / bn;
+  const uint32_t stage_tx = (uint32_t)(C::A_BYTES + (bn / CG) * KB_BYTES);  // bytes one CTA's two TMA boxes deliver per stage
   const int64_t m_tiles = (M + (int64_t)BM * CG - 1) / ((int64_t)BM * CG);
   const int64_t total_tiles = m_tiles * n_tiles;
   const int64_t first_tile = blockIdx.x / CG;
@@ -181,21 +175,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int64_t m_blk = tile / n_tiles;
         const int n_blk = (int)(tile % n_tiles);
-        const int n_size = min(BN, N - n_blk * BN);
+        const int n_size = min(bn, N - n_blk * bn);
         const int32_t m0 = (int32_t)(m_blk * BM * CG + cta_rank * BM);
-        const int32_t n0 = n_blk * BN + (int32_t)cta_rank * (n_size / CG);
+        const int32_t n0 = n_blk * bn + (int32_t)cta_rank * (n_size / CG);
+        // The A rows of a tile come from HBM exactly once (the n-tiles of one row block run concurrently on
+        // neighbouring CTAs and share them through L2).  Whoever will open the next row block pulls its A rows into
+        // L2 now, one tile ahead, so those first-touch misses do not stall the operand ring.
+        const int64_t next_tile = tile + tile_stride;
+        const bool prefetch_next = next_tile < total_tiles && (next_tile % n_tiles) == 0;
+        const int32_t next_m0 = (int32_t)((next_tile / n_tiles) * BM * CG + cta_rank * BM);
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (prefetch_next) ptx::tma_prefetch_l2_2d(&tmA, kb * BK, next_m0);
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + C::A_BYTES;
           if constexpr (CG == 1) {
-            ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            ptx::mbar_arrive_expect_tx(full_bar(stage), stage_tx);
             ptx::tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, m0);
             ptx::tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
           } else {
             const uint32_t lbar = leader_full0 + 8u * stage;
             // the peer's bytes may land before this expect_tx: the phase still cannot complete without this arrive
-            if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
             ptx::tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
             ptx::tma_load_2d_pair(b_dst, &tmB, lbar, kb * BK, n0);
           }
@@ -213,7 +214,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t acc_phase = 0;
       for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int n_blk = (int)(tile % n_tiles);
-        const int n_size = min(BN, N - n_blk * BN);
+        const int n_size = min(bn, N - n_blk * bn);
         const uint32_t idesc = make_idesc(KIND, BM * CG, n_size);
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
@@ -241,41 +242,61 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
-    const int q = warp & 3;          // TMEM lane quarter this warp may read (warp id % 4)
-    const int half = (warp - 4) >> 2;  // 0: even 32-column chunks, 1: odd chunks
+    const int q = warp & 3;            // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 4) >> 2;  // 0: even 64-column groups, 1: odd groups
+    constexpr bool OUT_BF16 = (KIND == 0) && (EPI == 0 || EPI == 1);
+    const uint32_t box = staging_base + (uint32_t)(warp - 4) * 4096u;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t leader_tempty0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : 0u;
     for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const int64_t m_blk = tile / n_tiles;
       const int n_blk = (int)(tile % n_tiles);
-      const int n_size = min(BN, N - n_blk * BN);
-      const int64_t row = m_blk * BM * CG + cta_rank * BM + q * 32 + lane;
-      const bool row_ok = row < M;
-      const int ncol0 = n_blk * BN;
+      const int n_size = min(bn, N - n_blk * bn);
+      const int32_t row0 = (int32_t)(m_blk * BM * CG + cta_rank * BM + q * 32);  // first row of this warp's 32-row box
+      const int ncol0 = n_blk * bn;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      int c = half * 32;
-      for (; c + 96 <= n_size; c += 128) {  // two chunks (c, c + 64) per wait
+      for (int c = half * 64; c < n_size; c += 128) {
         uint32_t va[32], vb[32];
         ptx::tmem_ld_32x32(taddr + c, va);
-        ptx::tmem_ld_32x32(taddr + c + 64, vb);
+        ptx::tmem_ld_32x32(taddr + c + 32, vb);
         ptx::tmem_ld_wait();
-        epilogue_store<KIND, EPI, 32>(va, bias, Y, row, N, ncol0 + c, row_ok);
-        epilogue_store<KIND, EPI, 32>(vb, bias, Y, row, N, ncol0 + c + 64, row_ok);
-      }
-      for (; c + 32 <= n_size; c += 64) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + c, v);
-        ptx::tmem_ld_wait();
-        epilogue_store<KIND, EPI, 32>(v, bias, Y, row, N, ncol0 + c, row_ok);
-      }
-      if (c < n_size) {  // n_size % 32 == 16: the trailing half chunk belongs to the warp whose turn it is
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(taddr + c, v);
-        ptx::tmem_ld_wait();
-        epilogue_store<KIND, EPI, 16>(v, bias, Y, row, N, ncol0 + c, row_ok);
+        if constexpr (OUT_BF16) {
+          // one 64-column bf16 box per step
+          float fa[32], fb[32];
+          epilogue_math<KIND, EPI>(va, bias, ncol0 + c, N, fa);
+          epilogue_math<KIND, EPI>(vb, bias, ncol0 + c + 32, N, fb);
+          if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has finished reading the box
+          __syncwarp();
+          stage_row_bf16(box, lane, 0, fa);
+          stage_row_bf16(box, lane, 4, fb);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmY, box, ncol0 + c, row0);
+            ptx::bulk_commit();
+          }
+        } else {
+          // two 32-column fp32 boxes per step, one after the other through the same staging box
+#pragma unroll
+          for (int hbox = 0; hbox < 2; ++hbox) {
+            if (c + 32 * hbox >= n_size) break;
+            float f[32];
+            epilogue_math<KIND, EPI>(hbox ? vb : va, bias, ncol0 + c + 32 * hbox, N, f);
+            if (lane == 0) ptx::bulk_wait_read<0>();
+            __syncwarp();
+            stage_row_f32(box, lane, f);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (EPI == 2) ptx::tma_reduce_add_2d(&tmY, box, ncol0 + c + 32 * hbox, row0);
+              else ptx::tma_store_2d(&tmY, box, ncol0 + c + 32 * hbox, row0);
+              ptx::bulk_commit();
+            }
+          }
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -285,6 +306,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0) ptx::bulk_wait_all();  // every output tile has landed before the CTA retires
+    __syncwarp();
   }
 
   ptx::tc_fence_before();
@@ -314,7 +337,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // [rows, K] row-major matrix, box = 128 bytes of K x box_rows rows, 128B swizzle, out-of-bounds -> zeros
-int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, int box_rows) {
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, int box_rows, int box_cols = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -322,7 +345,7 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, i
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)K * esz};
-  const cuuint32_t box[2] = {(cuuint32_t)(KB_BYTES / esz), (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)(box_cols ? box_cols : KB_BYTES / esz), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -338,8 +361,8 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, i
 int g_gemm_cta_group = 2;  // CTA pairs by default: half the operand traffic per SM (measured faster on every FPT shape)
 
 template <int CG, int KIND, int EPI>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* Y, int64_t M, int N, int K,
-               cudaStream_t s) {
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const float* bias, int64_t M, int N,
+               int K, int bn, cudaStream_t s) {
   using C = Cfg<CG>;
   auto kern = gemm_tcgen05_kernel<CG, KIND, EPI>;
   static bool attr_set = false;  // per instantiation; the attribute is per function, valid on every device of the process
@@ -347,7 +370,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int n_tiles = (N + BN - 1) / BN;
+  const int n_tiles = (N + bn - 1) / bn;
   const int64_t m_tiles = ceil_div(M, (int64_t)BM * CG);
   const int64_t total = m_tiles * n_tiles;
   const int64_t max_groups = kNumSMs / CG;
@@ -364,19 +387,32 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, bias, Y, M, N, K));
+  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmY, bias, M, N, K, bn));
   return MPL_OK;
 }
 
 template <int CG, int KIND>
-int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* Y, int64_t M, int N, int K,
-               cudaStream_t s) {
+int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const float* bias, int64_t M,
+               int N, int K, int bn, cudaStream_t s) {
   switch (epi) {
-    case 0: return launch_one<CG, KIND, 0>(tmA, tmB, bias, Y, M, N, K, s);
-    case 1: return launch_one<CG, KIND, 1>(tmA, tmB, bias, Y, M, N, K, s);
-    case 2: return launch_one<CG, KIND, 2>(tmA, tmB, bias, Y, M, N, K, s);
-    default: return launch_one<CG, KIND, 3>(tmA, tmB, bias, Y, M, N, K, s);
+    case 0: return launch_one<CG, KIND, 0>(tmA, tmB, tmY, bias, M, N, K, bn, s);
+    case 1: return launch_one<CG, KIND, 1>(tmA, tmB, tmY, bias, M, N, K, bn, s);
+    case 2: return launch_one<CG, KIND, 2>(tmA, tmB, tmY, bias, M, N, K, bn, s);
+    default: return launch_one<CG, KIND, 3>(tmA, tmB, tmY, bias, M, N, K, bn, s);
   }
+}
+
+// Output-tile width.  Interior tiles must be multiples of 64 columns (the epilogue stores 64-column groups).  Wide tiles
+// win: measured on B200, N = 1088 as 4 x 256 + 64 beats 5 x 192 + 128 by 8 % (fewer re-reads of A per output column),
+// so 256 is kept unless the tail would be narrower than 64 columns (N = 544 -> 192 + 192 + 160 instead of 256 + 256 + 32).
+int pick_tile_n(int N) {
+  const int rem = N % 256;
+  if (rem == 0 || rem >= 64) return 256;
+  for (int bn : {192, 128}) {
+    const int r = N % bn;
+    if (r == 0 || r >= 64) return bn;
+  }
+  return 256;
 }
 
 }  // namespace
@@ -406,16 +442,20 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
   }
   const int esz = (dtype == MPL_PREC_BF16) ? 2 : 4;
   const int cg = g_gemm_cta_group;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmY;
   MPL_TRY(make_tmap(&tmA, A, M, K, esz, BM));
-  MPL_TRY(make_tmap(&tmB, W, N, K, esz, BN / cg));
+  const int bn = pick_tile_n(N);
+  MPL_TRY(make_tmap(&tmB, W, N, K, esz, bn / cg));
   int epi = epilogue;
   if (epilogue == EPI_BIAS && out_fp32) epi = 3;
   const int kind = (dtype == MPL_PREC_BF16) ? 0 : 1;
+  // output boxes: 32 rows x 128 bytes (64 bf16 or 32 fp32 columns), 128B swizzle like the staging writes
+  const bool out_bf16 = kind == 0 && (epi == 0 || epi == 1);
+  MPL_TRY(make_tmap(&tmY, Y, M, N, out_bf16 ? 2 : 4, 32, out_bf16 ? 64 : 32));
   if (cg == 1) {
-    return kind == 0 ? launch_epi<1, 0>(epi, tmA, tmB, bias, Y, M, N, K, s) : launch_epi<1, 1>(epi, tmA, tmB, bias, Y, M, N, K, s);
+    return kind == 0 ? launch_epi<1, 0>(epi, tmA, tmB, tmY, bias, M, N, K, bn, s) : launch_epi<1, 1>(epi, tmA, tmB, tmY, bias, M, N, K, bn, s);
   }
-  return kind == 0 ? launch_epi<2, 0>(epi, tmA, tmB, bias, Y, M, N, K, s) : launch_epi<2, 1>(epi, tmA, tmB, bias, Y, M, N, K, s);
+  return kind == 0 ? launch_epi<2, 0>(epi, tmA, tmB, tmY, bias, M, N, K, bn, s) : launch_epi<2, 1>(epi, tmA, tmB, tmY, bias, M, N, K, bn, s);
 }
 
 }  // namespace mpl
