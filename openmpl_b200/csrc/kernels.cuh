@@ -111,11 +111,12 @@ bool spt_fused_supports(int J, int d, int H, int hidden);
 size_t spt_fused_layer_bytes();
 int launch_spt_pack_layer(const float* n1w, const float* n1b, const float* qkvw, const float* qkvb, const float* projw,
                           const float* projb, const float* n2w, const float* n2b, const float* fc1w, const float* fc1b,
-                          const float* fc2w, const float* fc2b, void* dst, cudaStream_t s);
-// x_in / x_out [V, B, 17, 32] fp32; wpack_per_view[v] -> [depth] fragment-packed layers; applies every block
-// application of the stack (confidence-weighted pass when conf != null, last block twice) and Spatial_norm
+                          const float* fc2w, const float* fc2b, float scale, void* dst, cudaStream_t s);
+// x_in / x_out [V, B, 17, 32] fp32; wpack_per_view[v] -> [depth] fragment-packed layers (the softmax scale is folded
+// into them by launch_spt_pack_layer); applies every block application of the stack (confidence-weighted pass when
+// conf != null, last block twice) and Spatial_norm
 int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_per_view, int V, int64_t B, int depth,
-                     float scale, const float* sn_w, const float* sn_b, const float* conf, cudaStream_t s);
+                     const float* sn_w, const float* sn_b, const float* conf, cudaStream_t s);
 
 // ---- metric + input builder -----------------------------------------------------------------------------------------
 int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t B, int J, float unit_scale,

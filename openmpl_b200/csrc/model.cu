@@ -470,11 +470,9 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   // ---- SPT blocks (multiview_mpl.py:400-410): conf-weighted pass, last block twice; then Spatial_norm (:412) ----
   const int64_t Rs = (int64_t)V * Bc * J;
   if (m->spt_fused) {
-    const int hd = dim / m->H;
-    const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
     const void* wp[kMaxViews];
     for (int v = 0; v < V; ++v) wp[v] = P.dv("sptpack:" + std::to_string(m->multi ? v : 0));
-    LC(CAT_SPT_FUSED, launch_spt_fused(w.xs, w.xn, wp, V, Bc, m->depth, scale, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"),
+    LC(CAT_SPT_FUSED, launch_spt_fused(w.xs, w.xn, wp, V, Bc, m->depth, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"),
                                        w.conf, s));
   } else {
     if (!d.no_transformer_spt && m->depth > 0) {
@@ -804,6 +802,7 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
   }
   if (m->spt_fused) {
     const int stacks = m->multi ? m->V : 1;
+    const float spt_scale = m->d.qk_scale != 0.f ? m->d.qk_scale : 1.0f / sqrtf((float)(m->dim / m->H));
     for (int st = 0; st < stacks; ++st) {
       const Derived& dd = m->derived[m->dindex.at("sptpack:" + std::to_string(st))];
       for (int l = 0; l < m->depth; ++l) {
@@ -812,7 +811,7 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
                                       m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr, P.f(p + "attn.proj.weight"),
                                       P.f(p + "attn.proj.bias"), P.f(p + "norm2.weight"), P.f(p + "norm2.bias"),
                                       P.f(p + "mlp.fc1.weight"), P.f(p + "mlp.fc1.bias"), P.f(p + "mlp.fc2.weight"),
-                                      P.f(p + "mlp.fc2.bias"), base + dd.offset + (size_t)l * spt_fused_layer_bytes(), s));
+                                      P.f(p + "mlp.fc2.bias"), spt_scale, base + dd.offset + (size_t)l * spt_fused_layer_bytes(), s));
       }
     }
   }

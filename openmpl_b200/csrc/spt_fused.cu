@@ -1,18 +1,25 @@
 // K2: the Spatial Pose Transformer as ONE kernel (multiview_mpl.py:400-412 with Block/Attention/Mlp :21-92).
 //
-// The SPT is latency work, not FLOPs: 17 tokens x 32 channels per (pose, view) set, head_dim 4, depth+1 block
+// The SPT is latency / issue work, not FLOPs: 17 tokens x 32 channels per (pose, view) set, head_dim 4, depth+1 block
 // applications.  Launched layer by layer it is ~14 small kernels per application and re-reads the residual stream
-// from HBM every time; here a CTA keeps 16 sets resident for the whole stack:
-//   * 16 sets x 17 tokens = 272 rows = 17 MMA row tiles of 16 -> 17 warps, zero padding (16*17 == 17*16);
-//   * the residual stream lives in registers as mma.sync C fragments (16 fp32 per lane) across all applications;
-//   * LayerNorm is computed on the fragments (quad shuffles), the four Linears are bf16 mma.sync m16n8k16 with fp32
-//     accumulation, their weights pre-packed in fragment order and double-buffered in shared memory via cp.async;
-//   * q|k|v of the 16 sets are staged once in shared memory (fp32), the 17x17 softmax per head is done by one thread
-//     per (row, half of the heads) in registers — the sets are far too short for flash-style tiling;
-//   * erf-form GELU (A&S 7.1.25, |erf error| < 2.5e-5, result rounded to bf16 for the next mma), residual adds and
-//     the final Spatial_norm stay in fp32 registers.
-// HBM traffic per set: 17*32*4 B in + out, nothing in between.  (tcgen05 needs 128-row operand tiles staged through
-// shared memory for every one of the 52 tiny GEMMs per set; the warp-level mma keeps the operands in registers.)
+// from HBM every time; here a CTA keeps 32 sets resident for the whole stack:
+//   * 32 sets x 17 tokens = 544 rows = 34 MMA row tiles of 16 -> 17 warps x 2 tiles, zero padding, and every weight
+//     fragment read from shared memory feeds two MMAs (the v1 kernel, one tile per warp, was bound by the LSU pipe);
+//   * the residual stream lives in registers as mma.sync C fragments (32 fp32 per lane) across all applications;
+//   * LayerNorm is computed on the fragments (quad shuffles); the four Linears are fp16 mma.sync m16n8k16 with fp32
+//     accumulation (fp16 rather than bf16 operands: 3 more mantissa bits, and every operand here is O(1) after
+//     LayerNorm; conversions saturate), weights pre-packed in fragment order, double-buffered via cp.async;
+//   * q|k|v of the 32 sets are staged once in shared memory as fp16 with the channels of each head PAIR interleaved
+//     (word = (head 2p, head 2p+1) at one head-dim), so that the 17x17 softmax of two heads runs in packed half2
+//     arithmetic straight from 16-byte shared-memory loads: one thread per token row, 4 head pairs, two passes
+//     (max, then exp2 / sum / PV) with the scores kept in registers.  The interleave costs nothing: it is a row
+//     permutation of the QKV weight and a column permutation of the proj weight, applied when the layer is packed;
+//     softmax scale * log2(e) is folded into the q rows the same way;
+//   * the attention output overwrites the (already consumed) q slot of its own row and is the A operand of proj;
+//   * erf-GELU via a tanh-form fit (see gelu_tanh_fit), residual adds and the final Spatial_norm stay in fp32.
+// HBM traffic per set: 17*32*4 B in + out, nothing in between.
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace mpl {
@@ -20,9 +27,10 @@ namespace mpl {
 namespace {
 
 constexpr int J = 17, D = 32, HID = 64, HEADS = 8;
-constexpr int SETS = 16, ROWS = SETS * J, WARPS = 17, THREADS = WARPS * 32;
-constexpr int QS = 100;  // fp32 row pitch of the q|k|v staging buffer (96 + 4: spreads rows over banks, keeps 16B alignment)
-constexpr int AS = 40;   // bf16 row pitch of the attention-output buffer (32 + 8: conflict-free A-fragment loads)
+constexpr int SETS = 32, ROWS = SETS * J, WARPS = 17, THREADS = WARPS * 32;  // 544 rows, one attention thread per row
+constexpr int QP = 104;     // fp16 row pitch of the q|k|v staging buffer (96 + 8): 52 words -> rows g = 0..7 start on banks
+                            // {0,20,8,28,16,4,24,12}: conflict-free half2 C-fragment stores, A-fragment loads and 16 B row loads
+constexpr int QPW = QP / 2;
 
 // fragment-packed layer blob (32-bit words): B fragments of the four weight matrices, then the fp32 vectors
 constexpr int OFF_QKV = 0, OFF_PROJ = 1536, OFF_FC1 = 2048, OFF_FC2 = 3072, FRAG_WORDS = 4096;
@@ -30,17 +38,20 @@ constexpr int F_N1W = 0, F_N1B = 32, F_QKVB = 64, F_PROJB = 160, F_N2W = 192, F_
 constexpr int VEC_WORDS = 352, LAYER_WORDS = FRAG_WORDS + VEC_WORDS;  // 4448 words = 17792 bytes
 
 constexpr int SMEM_W = 2 * LAYER_WORDS * 4;
-constexpr int SMEM_QKV = ROWS * QS * 4;
-constexpr int SMEM_AO = ROWS * AS * 2;
-constexpr int SMEM_TOTAL = SMEM_W + SMEM_QKV + SMEM_AO;
+constexpr int SMEM_QKV = ROWS * QP * 2;
+constexpr int SMEM_TOTAL = SMEM_W + SMEM_QKV;
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&p);
+// staging position (within a 32-wide q, k or v third) of channel c = 8p + 4e + d (head 2p+e, head-dim d): 8p + 2d + e
+__host__ __device__ constexpr int chan_of_pos(int pos) { return (pos & ~7) + 4 * (pos & 1) + ((pos & 7) >> 1); }
+
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -51,7 +62,19 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v;
 }
 
-// LayerNorm (eps 1e-6, biased variance) of the two rows a lane co-owns, straight to bf16 A fragments (2 k-tiles of 16)
+// erf-form GELU (nn.GELU() default, multiview_mpl.py:22,27) for results that are rounded to fp16 / bf16 right after:
+// 0.5 x (1 + tanh(x (c0 + c1 x^2))) with (c0, c1) fitted to the ERF form (max |error| 2.7e-4 over all x, at |x| ~ 2 where
+// the bf16 half-ulp is 4e-3; tanh.approx adds <= 2^-11 relative).  6 FMA-pipe instructions + one MUFU.
+__device__ __forceinline__ float gelu_tanh_fit(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, 0.03470089f, 0.80015708f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
+
+// LayerNorm (eps 1e-6, biased variance) of the two rows a lane co-owns, straight to fp16 A fragments (2 k-tiles of 16)
 __device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float* __restrict__ gw, const float* __restrict__ gb,
                                             int t, uint32_t (&a)[2][4]) {
   float s0 = 0.f, s1 = 0.f;
@@ -72,21 +95,25 @@ __device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float*
     const float2 b = *reinterpret_cast<const float2*>(gb + 8 * nt + 2 * t);
     const float y0 = (x[nt][0] - m0) * r0 * w.x + b.x, y1 = (x[nt][1] - m0) * r0 * w.y + b.y;
     const float y2 = (x[nt][2] - m1) * r1 * w.x + b.x, y3 = (x[nt][3] - m1) * r1 * w.y + b.y;
-    a[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(y0, y1);
-    a[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(y2, y3);
+    a[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(y0, y1);
+    a[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(y2, y3);
   }
 }
 
-// one output tile (16 rows x 8 features): acc = bias, then KT k-steps with B fragments read from the packed blob
+// one output tile column (8 features) for both row tiles of the warp: acc = bias, then KT k-steps; every B fragment
+// read from the packed blob feeds two MMAs
 template <int KT>
-__device__ __forceinline__ void gemm_tile(float (&c)[4], const uint32_t (&a)[KT][4], const uint32_t* __restrict__ wfrag, int nt,
-                                          const float* __restrict__ bias, int lane, int t) {
+__device__ __forceinline__ void gemm_tile2(float (&c0)[4], float (&c1)[4], const uint32_t (&a0)[KT][4], const uint32_t (&a1)[KT][4],
+                                           const uint32_t* __restrict__ wfrag, int nt, const float* __restrict__ bias, int lane,
+                                           int t) {
   const float2 b2 = *reinterpret_cast<const float2*>(bias + 8 * nt + 2 * t);
-  c[0] = b2.x; c[1] = b2.y; c[2] = b2.x; c[3] = b2.y;
+  c0[0] = b2.x; c0[1] = b2.y; c0[2] = b2.x; c0[3] = b2.y;
+  c1[0] = b2.x; c1[1] = b2.y; c1[2] = b2.x; c1[3] = b2.y;
 #pragma unroll
   for (int kt = 0; kt < KT; ++kt) {
     const uint2 b = *reinterpret_cast<const uint2*>(wfrag + ((nt * KT + kt) * 32 + lane) * 2);
-    mma_bf16_16816(c, a[kt], b.x, b.y);
+    mma_f16_16816(c0, a0[kt], b.x, b.y);
+    mma_f16_16816(c1, a1[kt], b.x, b.y);
   }
 }
 
@@ -99,7 +126,6 @@ struct SptArgs {
   const float* conf;                  // [V, B, J] or null: confidence_as_attention_uncertainty_weight
   int64_t B;
   int depth;
-  float scale_log2e;                  // head_dim^-0.5 (or qk_scale) * log2(e)
 };
 
 __device__ __forceinline__ void load_layer_async(uint32_t* dst, const uint32_t* src) {
@@ -112,11 +138,18 @@ __device__ __forceinline__ void load_layer_async(uint32_t* dst, const uint32_t* 
 }
 __device__ __forceinline__ void wait_async_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ __half2 h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 ex2_h2(__half2 x) {
+  uint32_t r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(u32(x)));
+  return h2(r);
+}
+
 __global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel(const SptArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem);
-  float* qkv_s = reinterpret_cast<float*>(smem + SMEM_W);
-  __nv_bfloat16* ao_s = reinterpret_cast<__nv_bfloat16*>(smem + SMEM_W + SMEM_QKV);
+  uint32_t* qkv_w = reinterpret_cast<uint32_t*>(smem + SMEM_W);  // fp16 staging viewed as half2 words, row pitch QPW
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -124,25 +157,31 @@ __global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel(const SptArgs arg
   const int64_t tile = blockIdx.x;
   const int64_t rows_in_view = args.B * J;
   const int64_t view_row0 = (int64_t)view * rows_in_view;
-  const int r0 = warp * 16 + g, r1 = r0 + 8;                    // CTA-local rows of this lane's fragments
-  const int64_t gr0 = tile * ROWS + r0, gr1 = tile * ROWS + r1;  // rows inside the view
-  const bool ok0 = gr0 < rows_in_view, ok1 = gr1 < rows_in_view;
   const uint32_t* wsrc = args.wpack[view];
 
   load_layer_async(wbuf, wsrc);
 
-  // residual stream: C-fragment layout, x[nt][0..1] = row r0 cols 8nt+2t,+1 ; x[nt][2..3] = row r1
-  float x[4][4];
+  // residual stream: C-fragment layout per row tile mt: x[mt][nt][0..1] = row r0 cols 8nt+2t,+1 ; [2..3] = row r0 + 8
+  float x[2][4][4];
+  int lr[2];        // CTA-local first row (r0) of each tile
+  bool ok[2][2];
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
-    if (ok0) v0 = *reinterpret_cast<const float2*>(args.x_in + (view_row0 + gr0) * D + 8 * nt + 2 * t);
-    if (ok1) v1 = *reinterpret_cast<const float2*>(args.x_in + (view_row0 + gr1) * D + 8 * nt + 2 * t);
-    x[nt][0] = v0.x; x[nt][1] = v0.y; x[nt][2] = v1.x; x[nt][3] = v1.y;
+  for (int mt = 0; mt < 2; ++mt) {
+    lr[mt] = warp * 32 + mt * 16 + g;
+    const int64_t gr0 = tile * ROWS + lr[mt], gr1 = gr0 + 8;
+    ok[mt][0] = gr0 < rows_in_view;
+    ok[mt][1] = gr1 < rows_in_view;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+      if (ok[mt][0]) v0 = *reinterpret_cast<const float2*>(args.x_in + (view_row0 + gr0) * D + 8 * nt + 2 * t);
+      if (ok[mt][1]) v1 = *reinterpret_cast<const float2*>(args.x_in + (view_row0 + gr1) * D + 8 * nt + 2 * t);
+      x[mt][nt][0] = v0.x; x[mt][nt][1] = v0.y; x[mt][nt][2] = v1.x; x[mt][nt][3] = v1.y;
+    }
   }
 
-  // attention role of this thread: one row, four heads
-  const int arow = threadIdx.x >> 1, ahh = threadIdx.x & 1;
+  // attention role of this thread: one token row, all 8 heads as 4 head pairs
+  const int arow = threadIdx.x;
   const int aset0 = (arow / J) * J;  // first row of the row's set
   const int64_t agr = tile * ROWS + arow;
   float aconf = 1.0f;
@@ -159,151 +198,186 @@ __global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel(const SptArgs arg
     const int n_apps = (args.conf != nullptr ? 1 : 0) + (layer == args.depth - 1 ? 2 : 1);
     for (int app = 0; app < n_apps; ++app) {
       const bool weighted = (args.conf != nullptr) && app == 0;
-      // ---- LN1 + QKV ----
+      // ---- LN1 + QKV -> fp16 staging (q pre-scaled by scale * log2 e through the packed weights) ----
       {
-        uint32_t a[2][4];
-        ln_to_afrag(x, wv + F_N1W, wv + F_N1B, t, a);
+        uint32_t a0[2][4], a1[2][4];
+        ln_to_afrag(x[0], wv + F_N1W, wv + F_N1B, t, a0);
+        ln_to_afrag(x[1], wv + F_N1W, wv + F_N1B, t, a1);
 #pragma unroll
         for (int nt = 0; nt < 12; ++nt) {
-          float c[4];
-          gemm_tile<2>(c, a, w + OFF_QKV, nt, wv + F_QKVB, lane, t);
-          *reinterpret_cast<float2*>(qkv_s + r0 * QS + 8 * nt + 2 * t) = make_float2(c[0], c[1]);
-          *reinterpret_cast<float2*>(qkv_s + r1 * QS + 8 * nt + 2 * t) = make_float2(c[2], c[3]);
+          float c0[4], c1[4];
+          gemm_tile2<2>(c0, c1, a0, a1, w + OFF_QKV, nt, wv + F_QKVB, lane, t);
+          qkv_w[lr[0] * QPW + 4 * nt + t] = pack_f16(c0[0], c0[1]);
+          qkv_w[(lr[0] + 8) * QPW + 4 * nt + t] = pack_f16(c0[2], c0[3]);
+          qkv_w[lr[1] * QPW + 4 * nt + t] = pack_f16(c1[0], c1[1]);
+          qkv_w[(lr[1] + 8) * QPW + 4 * nt + t] = pack_f16(c1[2], c1[3]);
         }
       }
       __syncthreads();
-      // ---- attention: softmax(q k^T * scale) v over the 17 tokens of the row's set, 4 heads per thread ----
+      // ---- attention: softmax(q k^T * scale) v over the 17 tokens of the row's set; two heads per half2 lane pair ----
       {
         const float rowscale = weighted ? aconf : 1.0f;
-        uint32_t packed[8];
-#pragma unroll
-        for (int hl = 0; hl < 4; ++hl) {
-          const int h = ahh * 4 + hl;
-          float4 q = *reinterpret_cast<const float4*>(qkv_s + arow * QS + 4 * h);
-          q.x *= args.scale_log2e; q.y *= args.scale_log2e; q.z *= args.scale_log2e; q.w *= args.scale_log2e;
-          float sc[J];
-          float mx = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < J; ++j) {
-            const float4 k = *reinterpret_cast<const float4*>(qkv_s + (aset0 + j) * QS + D + 4 * h);
-            sc[j] = q.x * k.x + q.y * k.y + q.z * k.z + q.w * k.w;
-            mx = fmaxf(mx, sc[j]);
-          }
-          float sum = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+        uint4* rowp = reinterpret_cast<uint4*>(qkv_w + arow * QPW);
+        const uint4* setp = reinterpret_cast<const uint4*>(qkv_w + aset0 * QPW);
+        constexpr int RP4 = QPW / 4;  // row pitch in 16-byte units (13)
+#pragma unroll 1
+        for (int p = 0; p < 4; ++p) {
+          const uint4 q = rowp[p];
+          __half2 sc[J];
+          __half2 mx;
 #pragma unroll
           for (int j = 0; j < J; ++j) {
-            const float p = exp2f(sc[j] - mx);
-            const float4 v = *reinterpret_cast<const float4*>(qkv_s + (aset0 + j) * QS + 2 * D + 4 * h);
-            sum += p;
-            o0 = fmaf(p, v.x, o0); o1 = fmaf(p, v.y, o1); o2 = fmaf(p, v.z, o2); o3 = fmaf(p, v.w, o3);
+            const uint4 k = setp[j * RP4 + 4 + p];
+            __half2 s = __hmul2(h2(q.x), h2(k.x));
+            s = __hfma2(h2(q.y), h2(k.y), s);
+            s = __hfma2(h2(q.z), h2(k.z), s);
+            s = __hfma2(h2(q.w), h2(k.w), s);
+            sc[j] = s;
+            mx = (j == 0) ? s : __hmax2(mx, s);
           }
-          const float inv = rowscale / sum;
-          packed[2 * hl] = pack_bf16(o0 * inv, o1 * inv);
-          packed[2 * hl + 1] = pack_bf16(o2 * inv, o3 * inv);
+          __half2 sum = __float2half2_rn(0.f), o0 = sum, o1 = sum, o2 = sum, o3 = sum;
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const uint4 v = setp[j * RP4 + 8 + p];
+            const __half2 e = ex2_h2(__hsub2(sc[j], mx));
+            sum = __hadd2(sum, e);
+            o0 = __hfma2(e, h2(v.x), o0);
+            o1 = __hfma2(e, h2(v.y), o1);
+            o2 = __hfma2(e, h2(v.z), o2);
+            o3 = __hfma2(e, h2(v.w), o3);
+          }
+          const float2 sf = __half22float2(sum);
+          const __half2 inv = __floats2half2_rn(__fdividef(rowscale, sf.x), __fdividef(rowscale, sf.y));
+          uint4 o;
+          o.x = u32(__hmul2(o0, inv)); o.y = u32(__hmul2(o1, inv)); o.z = u32(__hmul2(o2, inv)); o.w = u32(__hmul2(o3, inv));
+          // the q slot of this row / head pair is consumed: it now holds the attention output (A operand of proj)
+          rowp[p] = o;
         }
-        uint4* dst = reinterpret_cast<uint4*>(ao_s + arow * AS + 16 * ahh);
-        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
       __syncthreads();
       // ---- proj + residual ----
       {
-        uint32_t a[2][4];
-        const uint32_t* ao32 = reinterpret_cast<const uint32_t*>(ao_s);
+        uint32_t a0[2][4], a1[2][4];
 #pragma unroll
         for (int kt = 0; kt < 2; ++kt) {
-          a[kt][0] = ao32[r0 * (AS / 2) + 8 * kt + t];
-          a[kt][1] = ao32[r1 * (AS / 2) + 8 * kt + t];
-          a[kt][2] = ao32[r0 * (AS / 2) + 8 * kt + 4 + t];
-          a[kt][3] = ao32[r1 * (AS / 2) + 8 * kt + 4 + t];
+          a0[kt][0] = qkv_w[lr[0] * QPW + 8 * kt + t];
+          a0[kt][1] = qkv_w[(lr[0] + 8) * QPW + 8 * kt + t];
+          a0[kt][2] = qkv_w[lr[0] * QPW + 8 * kt + 4 + t];
+          a0[kt][3] = qkv_w[(lr[0] + 8) * QPW + 8 * kt + 4 + t];
+          a1[kt][0] = qkv_w[lr[1] * QPW + 8 * kt + t];
+          a1[kt][1] = qkv_w[(lr[1] + 8) * QPW + 8 * kt + t];
+          a1[kt][2] = qkv_w[lr[1] * QPW + 8 * kt + 4 + t];
+          a1[kt][3] = qkv_w[(lr[1] + 8) * QPW + 8 * kt + 4 + t];
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          float c[4];
-          gemm_tile<2>(c, a, w + OFF_PROJ, nt, wv + F_PROJB, lane, t);
+          float c0[4], c1[4];
+          gemm_tile2<2>(c0, c1, a0, a1, w + OFF_PROJ, nt, wv + F_PROJB, lane, t);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[nt][i] += c[i];
+          for (int i = 0; i < 4; ++i) { x[0][nt][i] += c0[i]; x[1][nt][i] += c1[i]; }
         }
       }
       // ---- LN2 + fc1 + GELU + fc2 + residual ----
       {
-        uint32_t a[2][4];
-        ln_to_afrag(x, wv + F_N2W, wv + F_N2B, t, a);
-        uint32_t a2[4][4];
+        uint32_t a0[2][4], a1[2][4];
+        ln_to_afrag(x[0], wv + F_N2W, wv + F_N2B, t, a0);
+        ln_to_afrag(x[1], wv + F_N2W, wv + F_N2B, t, a1);
+        uint32_t h0[4][4], h1[4][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-          float c[4];
-          gemm_tile<2>(c, a, w + OFF_FC1, nt, wv + F_FC1B, lane, t);
-          a2[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(gelu_erf_fast(c[0]), gelu_erf_fast(c[1]));
-          a2[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(gelu_erf_fast(c[2]), gelu_erf_fast(c[3]));
+          float c0[4], c1[4];
+          gemm_tile2<2>(c0, c1, a0, a1, w + OFF_FC1, nt, wv + F_FC1B, lane, t);
+          h0[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(gelu_tanh_fit(c0[0]), gelu_tanh_fit(c0[1]));
+          h0[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(gelu_tanh_fit(c0[2]), gelu_tanh_fit(c0[3]));
+          h1[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(gelu_tanh_fit(c1[0]), gelu_tanh_fit(c1[1]));
+          h1[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(gelu_tanh_fit(c1[2]), gelu_tanh_fit(c1[3]));
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-          float c[4];
-          gemm_tile<4>(c, a2, w + OFF_FC2, nt, wv + F_FC2B, lane, t);
+          float c0[4], c1[4];
+          gemm_tile2<4>(c0, c1, h0, h1, w + OFF_FC2, nt, wv + F_FC2B, lane, t);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) x[nt][i] += c[i];
+          for (int i = 0; i < 4; ++i) { x[0][nt][i] += c0[i]; x[1][nt][i] += c1[i]; }
         }
       }
     }
   }
 
   // ---- Spatial_norm (multiview_mpl.py:412), fp32 out ----
-  {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) { s0 += x[nt][0] + x[nt][1]; s1 += x[nt][2] + x[nt][3]; }
+    for (int nt = 0; nt < 4; ++nt) { s0 += x[mt][nt][0] + x[mt][nt][1]; s1 += x[mt][nt][2] + x[mt][nt][3]; }
     const float m0 = quad_sum(s0) * (1.0f / D), m1 = quad_sum(s1) * (1.0f / D);
     float q0 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      const float d0 = x[nt][0] - m0, d1 = x[nt][1] - m0, d2 = x[nt][2] - m1, d3 = x[nt][3] - m1;
+      const float d0 = x[mt][nt][0] - m0, d1 = x[mt][nt][1] - m0, d2 = x[mt][nt][2] - m1, d3 = x[mt][nt][3] - m1;
       q0 += d0 * d0 + d1 * d1;
       q1 += d2 * d2 + d3 * d3;
     }
     const float rs0 = rsqrtf(quad_sum(q0) * (1.0f / D) + 1e-6f), rs1 = rsqrtf(quad_sum(q1) * (1.0f / D) + 1e-6f);
+    const int64_t gr0 = tile * ROWS + lr[mt], gr1 = gr0 + 8;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const float2 wg = __ldg(reinterpret_cast<const float2*>(args.sn_w + 8 * nt + 2 * t));
       const float2 bg = __ldg(reinterpret_cast<const float2*>(args.sn_b + 8 * nt + 2 * t));
-      if (ok0)
+      if (ok[mt][0])
         *reinterpret_cast<float2*>(args.x_out + (view_row0 + gr0) * D + 8 * nt + 2 * t) =
-            make_float2((x[nt][0] - m0) * rs0 * wg.x + bg.x, (x[nt][1] - m0) * rs0 * wg.y + bg.y);
-      if (ok1)
+            make_float2((x[mt][nt][0] - m0) * rs0 * wg.x + bg.x, (x[mt][nt][1] - m0) * rs0 * wg.y + bg.y);
+      if (ok[mt][1])
         *reinterpret_cast<float2*>(args.x_out + (view_row0 + gr1) * D + 8 * nt + 2 * t) =
-            make_float2((x[nt][2] - m1) * rs1 * wg.x + bg.x, (x[nt][3] - m1) * rs1 * wg.y + bg.y);
+            make_float2((x[mt][nt][2] - m1) * rs1 * wg.x + bg.x, (x[mt][nt][3] - m1) * rs1 * wg.y + bg.y);
     }
   }
 }
 
-// fp32 parameters of one Block -> the fragment-packed layer blob
+// fp32 parameters of one Block -> the fragment-packed layer blob (fp16 operands, head-pair interleave, q scale folded)
 struct SptPackArgs {
   const float *n1w, *n1b, *qkvw, *qkvb, *projw, *projb, *n2w, *n2b, *fc1w, *fc1b, *fc2w, *fc2b;
   uint32_t* dst;
+  float q_scale;  // softmax scale * log2(e), folded into the q rows of the QKV weight and bias
 };
+
+__device__ __forceinline__ uint32_t pack_f16_rn(float lo, float hi) {
+  __half2 p = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
 
 __global__ void spt_pack_kernel(const SptPackArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= LAYER_WORDS) return;
   if (i < FRAG_WORDS) {
     const float* W;
-    int K, KT, base;
-    if (i < OFF_PROJ) { W = a.qkvw; K = 32; KT = 2; base = OFF_QKV; }
-    else if (i < OFF_FC1) { W = a.projw; K = 32; KT = 2; base = OFF_PROJ; }
-    else if (i < OFF_FC2) { W = a.fc1w; K = 32; KT = 2; base = OFF_FC1; }
-    else { W = a.fc2w; K = 64; KT = 4; base = OFF_FC2; }
+    int K, KT, base, kind;  // kind 0 qkv (output rows permuted), 1 proj (input columns permuted), 2 plain
+    if (i < OFF_PROJ) { W = a.qkvw; K = 32; KT = 2; base = OFF_QKV; kind = 0; }
+    else if (i < OFF_FC1) { W = a.projw; K = 32; KT = 2; base = OFF_PROJ; kind = 1; }
+    else if (i < OFF_FC2) { W = a.fc1w; K = 32; KT = 2; base = OFF_FC1; kind = 2; }
+    else { W = a.fc2w; K = 64; KT = 4; base = OFF_FC2; kind = 2; }
     const int j = i - base;
     const int reg = j & 1, lane = (j >> 1) & 31, tl = j >> 6;
     const int nt = tl / KT, kt = tl % KT;
     const int g = lane >> 2, t = lane & 3;
-    const int n = 8 * nt + g, k = 16 * kt + 2 * t + 8 * reg;
-    a.dst[i] = pack_bf16(W[n * K + k], W[n * K + k + 1]);
+    int n = 8 * nt + g;
+    const int k = 16 * kt + 2 * t + 8 * reg;
+    float sc = 1.0f;
+    if (kind == 0) {
+      const int third = n / 32;
+      n = third * 32 + chan_of_pos(n % 32);
+      if (third == 0) sc = a.q_scale;
+    }
+    const int k0 = (kind == 1) ? chan_of_pos(k) : k, k1 = (kind == 1) ? chan_of_pos(k + 1) : k + 1;
+    a.dst[i] = pack_f16_rn(W[n * K + k0] * sc, W[n * K + k1] * sc);
   } else {
     const int f = i - FRAG_WORDS;
     float v;
     if (f < F_N1B) v = a.n1w[f - F_N1W];
     else if (f < F_QKVB) v = a.n1b[f - F_N1B];
-    else if (f < F_PROJB) v = a.qkvb ? a.qkvb[f - F_QKVB] : 0.f;
+    else if (f < F_PROJB) {
+      const int pos = f - F_QKVB, third = pos / 32;
+      v = a.qkvb ? a.qkvb[third * 32 + chan_of_pos(pos % 32)] * (third == 0 ? a.q_scale : 1.0f) : 0.f;
+    }
     else if (f < F_N2W) v = a.projb[f - F_PROJB];
     else if (f < F_N2B) v = a.n2w[f - F_N2W];
     else if (f < F_FC1B) v = a.n2b[f - F_N2B];
@@ -320,15 +394,16 @@ size_t spt_fused_layer_bytes() { return (size_t)LAYER_WORDS * 4; }
 
 int launch_spt_pack_layer(const float* n1w, const float* n1b, const float* qkvw, const float* qkvb, const float* projw,
                           const float* projb, const float* n2w, const float* n2b, const float* fc1w, const float* fc1b,
-                          const float* fc2w, const float* fc2b, void* dst, cudaStream_t s) {
-  SptPackArgs a{n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, reinterpret_cast<uint32_t*>(dst)};
+                          const float* fc2w, const float* fc2b, float scale, void* dst, cudaStream_t s) {
+  SptPackArgs a{n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, reinterpret_cast<uint32_t*>(dst),
+                scale * 1.4426950408889634f};
   spt_pack_kernel<<<(LAYER_WORDS + 255) / 256, 256, 0, s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
 
 int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_per_view, int V, int64_t B, int depth,
-                     float scale, const float* sn_w, const float* sn_b, const float* conf, cudaStream_t s) {
+                     const float* sn_w, const float* sn_b, const float* conf, cudaStream_t s) {
   if (B == 0 || V == 0) return MPL_OK;
   SptArgs a{};
   a.x_in = x_in;
@@ -339,7 +414,6 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
   a.conf = conf;
   a.B = B;
   a.depth = depth;
-  a.scale_log2e = scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
     MPL_CUDA(cudaFuncSetAttribute(spt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));

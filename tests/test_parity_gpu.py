@@ -126,6 +126,32 @@ def test_large_batch_pose_independence_against_oracle(precision, name, B):
     np.testing.assert_array_equal(alone, out[idx])
 
 
+_FUSED_SPT_KW = dict(num_joints=17, embed_dim_ratio=32, num_heads=8, depth=3, num_views=3, drop_path_rate=0.1)
+
+
+@pytest.mark.parametrize("flags", [
+    dict(confidence_as_attention_uncertainty_weight=True, multiple_spatial_blocks=True, confidence_input_as_third=True),
+    dict(confidence_as_attention_uncertainty_weight=True, pose_3d_emb_learnable=True),
+    dict(qkv_bias=False, qk_scale=0.3, pose_3d_emb_learnable=True),
+    dict(add_confidence_input=True, mult_confidence_emb=True, no_transformer_fpt=True),
+    dict(depth=1, input_rays_as_token=True),
+], ids=["confattn_multi", "confattn_single", "noqkvbias_scale", "spt_only", "depth1_raytok"])
+@pytest.mark.parametrize("B", [5, 77])
+def test_fused_spt_kernel_variants_against_oracle(flags, B):
+    """The single-kernel SPT (bf16 mode, d = 32, H = 8, J = 17) under the constructor flags that change what it does:
+    the confidence-weighted extra pass per block (multiview_mpl.py:406-407), shared vs per-view stacks, no qkv bias,
+    explicit qk_scale, depth 1 (the only block runs twice) and batches that do not fill a 32-set CTA tile."""
+    kw = dict(_FUSED_SPT_KW, **flags)
+    cfg = spec.make_config(**kw)
+    weights = synth.named_weights(spec.param_spec(cfg), seed=5)
+    batch = synth.make_batch(B, synth.make_rig(cfg.V), seed=9)
+    m = build_module(kw, weights, "bf16")
+    out = run_module(m, batch)[0]
+    ref = oracle_outputs(cfg, weights, batch)[0]
+    e = rel_err(out, ref)
+    assert e <= TOL["bf16"], f"{flags}: {e:.3e} of scale"
+
+
 def test_native_library_is_what_ran():
     maps = open("/proc/self/maps").read()
     assert "libmpl_b200.so" in maps
