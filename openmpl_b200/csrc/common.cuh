@@ -69,6 +69,18 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(-fabsf(hx), e, hx + fabsf(hx));
 }
 
+// erf-form GELU (nn.GELU() default, multiview_mpl.py:22,27) for results that are rounded to fp16 / bf16 right after:
+// 0.5 x (1 + tanh(x (c0 + c1 x^2))) with (c0, c1) fitted to the ERF form (max |error| 2.7e-4 over all x, at |x| ~ 2 where
+// the bf16 half-ulp is 4e-3; tanh.approx adds <= 2^-11 relative).  6 FMA-pipe instructions + one MUFU.
+__device__ __forceinline__ float gelu_tanh_fit(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, 0.03470089f, 0.80015708f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == ACT_GELU) return gelu_erf(x);
   if (act == ACT_RELU) return fmaxf(x, 0.0f);

@@ -81,7 +81,7 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], const flo
   }
   if constexpr (EPI == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = (KIND == 0) ? gelu_erf_fast(f[i]) : round_tf32_dev(gelu_erf(f[i]));
+    for (int i = 0; i < 32; ++i) f[i] = (KIND == 0) ? gelu_tanh_fit(f[i]) : round_tf32_dev(gelu_erf(f[i]));
   }
 }
 

@@ -1,0 +1,292 @@
+// The HBM-bound edge kernels of the forward for the shipped widths (d % 4 == 0): K1 joint embedding, FPT token build and
+// the K5 fused head, written so that every global access is a 16-byte (or a coalesced 128-byte-per-warp) transaction
+// and the per-element index arithmetic of the generic kernels (kernels_generic.cu) disappears.  The generic kernels stay
+// as the path for odd widths / unaligned pointers; launch_* in kernels_generic.cu dispatch here first.
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace mpl {
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 joint embedding (multiview_mpl.py:349-398).  grid.y = view; a thread owns 4 consecutive channels for the whole
+// launch (its rows of W_e / b_e / W_c live in registers) and walks over token rows; a warp writes 512 contiguous bytes.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_vec_kernel(const EmbedArgs a) {
+  const int v = blockIdx.y;
+  const int d4 = a.d >> 2;                 // float4 chunks per token row
+  const int c = (threadIdx.x % d4) * 4;    // first channel of this thread
+  const int rows_per_pass = 256 / d4;
+  const float* We = a.We[v] + c * a.in_ch;
+  float w[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    w[i][0] = __ldg(We + i * a.in_ch);
+    w[i][1] = __ldg(We + i * a.in_ch + 1);
+    w[i][2] = (a.in_ch == 3) ? __ldg(We + i * a.in_ch + 2) : 0.f;
+  }
+  const float4 be = ld4(a.be[v] + c);
+  const bool conf_emb = a.add_conf || a.mult_conf;
+  float4 wc = make_float4(0.f, 0.f, 0.f, 0.f), bc = wc;
+  if (conf_emb) { wc = ld4(a.Wc[v] + c); bc = ld4(a.bc[v] + c); }
+  float wl[4][3];
+  float4 bl = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.spatial_pos_mode == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { wl[i][0] = __ldg(a.Wl + (c + i) * 3); wl[i][1] = __ldg(a.Wl + (c + i) * 3 + 1); wl[i][2] = __ldg(a.Wl + (c + i) * 3 + 2); }
+    bl = ld4(a.bl + c);
+  }
+  const int64_t rows = a.B * a.J;
+  const float* poses = a.poses[v];
+  float* xv = a.x + (int64_t)v * rows * a.d;
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_pass + threadIdx.x / d4; row < rows; row += (int64_t)gridDim.x * rows_per_pass) {
+    const int64_t b = row / a.J;
+    const int j = (int)(row - b * a.J);
+    const float* p = poses + b * a.pose_stride + j * 3;
+    const float px = __ldg(p), py = __ldg(p + 1), pc = __ldg(p + 2);
+    float o[4];
+    const float bev[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = fmaf(w[i][2], pc, fmaf(w[i][1], py, fmaf(w[i][0], px, bev[i])));  // w[i][2] = 0 when in_ch == 2
+    if (conf_emb) {
+      const float ce[4] = {fmaf(wc.x, pc, bc.x), fmaf(wc.y, pc, bc.y), fmaf(wc.z, pc, bc.z), fmaf(wc.w, pc, bc.w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (a.add_conf) o[i] += ce[i];
+        if (a.mult_conf) o[i] *= ce[i];
+      }
+    }
+    const float4 ps = ld4(a.Ps[v] + j * a.d + c);
+    o[0] += ps.x; o[1] += ps.y; o[2] += ps.z; o[3] += ps.w;
+    if (a.spatial_pos_mode == 1) {
+      const float4 t = ld4(a.pos3d + j * a.pos3d_ld + c);
+      o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+    } else if (a.spatial_pos_mode == 2) {
+      const float* r = a.rays[v] + b * a.pose_stride + j * 3;
+      const float* ce = a.centers[v] + b * a.center_stride;
+      const float dx = __ldg(r) - __ldg(ce), dy = __ldg(r + 1) - __ldg(ce + 1), dz = __ldg(r + 2) - __ldg(ce + 2);
+      const float inv = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);  // F.normalize eps
+      const float blv[4] = {bl.x, bl.y, bl.z, bl.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] += fmaf(wl[i][2], dz * inv, fmaf(wl[i][1], dy * inv, fmaf(wl[i][0], dx * inv, blv[i])));
+    }
+    *reinterpret_cast<float4*>(xv + row * a.d + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.conf != nullptr && c == 0) a.conf[(int64_t)v * rows + row] = pc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FPT token build (multiview_mpl.py:463-499): one thread per 4 consecutive channels of tok [B, V, tok_w]; the three
+// layouts (no ray token / [x | ray] per joint / J pose tokens then J ray tokens) differ only in how a 4-channel chunk
+// maps to (joint, segment), and d % 4 == 0 keeps every chunk inside one segment.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) token_build_vec_kernel(const TokenArgs a) {
+  const int w4 = a.tok_w >> 2;
+  const int64_t total = a.B * a.V * (int64_t)w4;
+  const int d = a.d, J = a.J;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % w4) * 4;
+    const int64_t bv = idx / w4;
+    const int v = (int)(bv % a.V);
+    const int64_t b = bv / a.V;
+    int j, c, pos_c;
+    bool is_ray = false, add_pos = true;
+    if (a.ray_layout == 1) {
+      j = e / (2 * d);
+      c = e - j * 2 * d;
+      pos_c = c;
+      if (c >= d) { is_ray = true; c -= d; }
+    } else if (a.ray_layout == 2) {
+      const int t = e / d;
+      c = e - t * d;
+      pos_c = c;
+      if (t >= J) { is_ray = true; j = t - J; add_pos = false; } else { j = t; }
+    } else {
+      j = e / d;
+      c = e - j * d;
+      pos_c = c;
+    }
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (is_ray || (add_pos && a.pos_table == nullptr)) {
+      const float* r = a.rays[v] + b * a.pose_stride + j * 3;
+      const float* ce = a.centers[v] + b * a.center_stride;
+      dx = __ldg(r) - __ldg(ce);
+      dy = __ldg(r + 1) - __ldg(ce + 1);
+      dz = __ldg(r + 2) - __ldg(ce + 2);
+    }
+    float o[4];
+    if (is_ray) {
+      const float4 br = ld4(a.br + c);
+      const float brv[4] = {br.x, br.y, br.z, br.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* wr = a.Wr + (c + i) * 3;
+        o[i] = fmaf(__ldg(wr + 2), dz, fmaf(__ldg(wr + 1), dy, fmaf(__ldg(wr), dx, brv[i])));
+      }
+    } else {
+      const float4 xv = *reinterpret_cast<const float4*>(a.xn + (((int64_t)v * a.B + b) * J + j) * d + c);
+      o[0] = xv.x; o[1] = xv.y; o[2] = xv.z; o[3] = xv.w;
+      if (a.Wcf != nullptr) {
+        const float pc = __ldg(a.poses[v] + b * a.pose_stride + j * 3 + 2);
+        const float4 wc = ld4(a.Wcf + c), bc = ld4(a.bcf + c);
+        o[0] += fmaf(wc.x, pc, bc.x); o[1] += fmaf(wc.y, pc, bc.y); o[2] += fmaf(wc.z, pc, bc.z); o[3] += fmaf(wc.w, pc, bc.w);
+      }
+    }
+    if (add_pos) {
+      if (a.pos_table != nullptr) {
+        const float4 t = ld4(a.pos_table + j * a.pos_w + pos_c);
+        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+      } else {
+        const float inv = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+        const float4 bl = ld4(a.bl + pos_c);
+        const float blv[4] = {bl.x, bl.y, bl.z, bl.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* wl = a.Wl + (pos_c + i) * 3;
+          o[i] += fmaf(__ldg(wl + 2), dz * inv, fmaf(__ldg(wl + 1), dy * inv, fmaf(__ldg(wl), dx * inv, blv[i])));
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(a.tok + idx * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K5 fused head (multiview_mpl.py:425-446, 517-523): one WARP per pose.  Channel e of the stripped row lives in lane
+// e % 32, register e / 32 (segments are multiples of 32 wide for the shipped d = 32, so every load is a coalesced
+// 128-byte line); View_norm and the head LayerNorm reduce with shuffles only — no shared memory, no block barriers.
+// The E -> 3J Linear reads each weight row once per warp (L1-resident, 3J*E*4 = 111 KB) and reduces across lanes.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256, 3) head_warp_kernel(const HeadArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int E = a.E;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int col[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = 32 * i + lane;
+    col[i] = (e / a.seg_len) * a.seg_stride + (e % a.seg_len);
+  }
+  const float invE = 1.0f / (float)E;
+  for (int64_t b = warp_global; b < a.B; b += warps_total) {
+    float pooled[NV];
+    const float wmb = __ldg(a.wm_b);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) pooled[i] = wmb;
+    for (int v = 0; v < a.V; ++v) {
+      const float* row = a.tok + (b * a.V + v) * (int64_t)a.tok_w;
+      float x[NV];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        x[i] = (32 * i + lane < E) ? row[col[i]] : 0.f;
+        s += x[i];
+      }
+      const float mean = warp_sum(s) * invE;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float t = (32 * i + lane < E) ? x[i] - mean : 0.f;
+        q = fmaf(t, t, q);
+      }
+      const float rstd = rsqrtf(warp_sum(q) * invE + 1e-6f);
+      const float wv = __ldg(a.wm_w + v);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int e = 32 * i + lane;
+        if (e < E) pooled[i] = fmaf(wv, fmaf((x[i] - mean) * rstd, __ldg(a.vn_w + e), __ldg(a.vn_b + e)), pooled[i]);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (32 * i + lane < E) ? pooled[i] : 0.f;
+    const float mean = warp_sum(s) * invE;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float t = (32 * i + lane < E) ? pooled[i] - mean : 0.f;
+      q = fmaf(t, t, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invE + 1e-5f);  // head LayerNorm: default eps (multiview_mpl.py:284)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = 32 * i + lane;
+      pooled[i] = (e < E) ? fmaf((pooled[i] - mean) * rstd, __ldg(a.hn_w + e), __ldg(a.hn_b + e)) : 0.f;
+    }
+    // Linear E -> out_dim: lane-partial dot products, butterfly reduction; lane o % 32 keeps output o
+    float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f;
+    for (int o = 0; o < a.out_dim; ++o) {
+      const float* wr = a.hw + (int64_t)o * E;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int e = 32 * i + lane;
+        if (e < E) acc = fmaf(pooled[i], __ldg(wr + e), acc);
+      }
+      acc = warp_sum(acc);
+      if ((o & 31) == lane) {
+        if (o < 32) keep0 = acc; else if (o < 64) keep1 = acc; else keep2 = acc;
+      }
+    }
+    float* out = a.out + b * a.out_dim;
+    if (lane < a.out_dim) out[lane] = keep0 + __ldg(a.hb + lane);
+    if (32 + lane < a.out_dim) out[32 + lane] = keep1 + __ldg(a.hb + 32 + lane);
+    if (64 + lane < a.out_dim) out[64 + lane] = keep2 + __ldg(a.hb + 64 + lane);
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// returns MPL_OK if it launched, 1 if the shapes / alignment need the generic kernel
+int try_launch_embed_vec(const EmbedArgs& a, cudaStream_t s) {
+  if (a.d % 4 != 0 || a.d > 1024 || 256 % (a.d / 4) != 0 || !aligned16(a.x)) return 1;
+  for (int v = 0; v < a.V; ++v) {
+    if (!aligned16(a.be[v]) || !aligned16(a.Ps[v])) return 1;
+    if ((a.add_conf || a.mult_conf) && (!aligned16(a.Wc[v]) || !aligned16(a.bc[v]))) return 1;
+  }
+  if (a.spatial_pos_mode == 1 && (!aligned16(a.pos3d) || a.pos3d_ld % 4 != 0)) return 1;
+  if (a.spatial_pos_mode == 2 && !aligned16(a.bl)) return 1;
+  const int64_t rows = a.B * a.J;
+  if (rows == 0) return MPL_OK;
+  const int rows_per_pass = 256 / (a.d / 4);
+  const int64_t blocks = ceil_div(rows, rows_per_pass);
+  const int64_t per_view = std::max<int64_t>(1, (int64_t)kNumSMs * 16 / a.V);
+  dim3 grid((unsigned)std::min<int64_t>(blocks, per_view), (unsigned)a.V);
+  embed_vec_kernel<<<grid, 256, 0, s>>>(a);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s) {
+  if (a.d % 4 != 0 || a.tok_w % 4 != 0 || !aligned16(a.tok) || !aligned16(a.xn)) return 1;
+  if (a.Wcf != nullptr && (!aligned16(a.Wcf) || !aligned16(a.bcf))) return 1;
+  if (a.br != nullptr && !aligned16(a.br)) return 1;
+  if (a.pos_table != nullptr && (!aligned16(a.pos_table) || a.pos_w % 4 != 0)) return 1;
+  if (a.pos_table == nullptr && !aligned16(a.bl)) return 1;
+  const int64_t total = a.B * a.V * (int64_t)(a.tok_w / 4);
+  if (total == 0) return MPL_OK;
+  const int64_t blocks = std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 32);
+  token_build_vec_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+int try_launch_head_warp(const HeadArgs& a, cudaStream_t s) {
+  if (a.E > 32 * 17 || a.out_dim > 96) return 1;
+  if (a.B == 0) return MPL_OK;
+  const int64_t blocks = std::min<int64_t>(ceil_div(a.B, 8), (int64_t)kNumSMs * 16);
+  if (a.E > 32 * 9) head_warp_kernel<17><<<(unsigned)blocks, 256, 0, s>>>(a);
+  else head_warp_kernel<9><<<(unsigned)blocks, 256, 0, s>>>(a);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+}  // namespace mpl

@@ -27,6 +27,7 @@ struct EmbedArgs {
   float* conf;  // [V, B, J] or null (confidence_as_attention_uncertainty_weight)
 };
 int launch_embed(const EmbedArgs& a, cudaStream_t s);
+int try_launch_embed_vec(const EmbedArgs& a, cudaStream_t s);  // io_kernels.cu: MPL_OK if launched, 1 if the generic kernel is needed
 
 // ---- FPT token build (multiview_mpl.py:463-499) ------------------------------------------------------------------
 struct TokenArgs {
@@ -48,6 +49,7 @@ struct TokenArgs {
   float* tok;           // [B, V, tok_w] fp32
 };
 int launch_token_build(const TokenArgs& a, cudaStream_t s);
+int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s);
 
 // ---- LayerNorm over the last dim; column e of the output reads input column (e / seg_len) * seg_stride + e % seg_len
 int launch_layernorm(const float* x, int64_t ldx, int seg_len, int seg_stride, const float* w, const float* b, float eps,
@@ -89,6 +91,7 @@ struct HeadArgs {
   float* out;                            // [B, out_dim]
 };
 int launch_head_fused(const HeadArgs& a, cudaStream_t s);
+int try_launch_head_warp(const HeadArgs& a, cudaStream_t s);
 
 // ---- pack helpers ---------------------------------------------------------------------------------------------------
 // Linear followed by eval-mode BatchNorm1d folded into one Linear: W' = W * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(var+eps) + beta

@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
 int launch_embed(const EmbedArgs& a, cudaStream_t s) {
   const int64_t total = (int64_t)a.V * a.B * a.J * a.d;
   if (total == 0) return MPL_OK;
+  const int vec = try_launch_embed_vec(a, s);
+  if (vec != 1) return vec;
   embed_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(256) token_build_kernel(const TokenArgs a) {
 int launch_token_build(const TokenArgs& a, cudaStream_t s) {
   const int64_t total = a.B * a.V * (int64_t)a.tok_w;
   if (total == 0) return MPL_OK;
+  const int vec = try_launch_token_build_vec(a, s);
+  if (vec != 1) return vec;
   token_build_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
@@ -766,6 +770,8 @@ __global__ void __launch_bounds__(128) head_fused_kernel(const HeadArgs a) {
 
 int launch_head_fused(const HeadArgs& a, cudaStream_t s) {
   if (a.B == 0) return MPL_OK;
+  const int vec = try_launch_head_warp(a, s);
+  if (vec != 1) return vec;
   head_fused_kernel<<<(unsigned)a.B, 128, (size_t)a.E * sizeof(float), s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;

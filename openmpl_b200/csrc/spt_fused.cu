@@ -2,9 +2,11 @@
 //
 // The SPT is latency / issue work, not FLOPs: 17 tokens x 32 channels per (pose, view) set, head_dim 4, depth+1 block
 // applications.  Launched layer by layer it is ~14 small kernels per application and re-reads the residual stream
-// from HBM every time; here a CTA keeps 32 sets resident for the whole stack:
-//   * 32 sets x 17 tokens = 544 rows = 34 MMA row tiles of 16 -> 17 warps x 2 tiles, zero padding, and every weight
-//     fragment read from shared memory feeds two MMAs (the v1 kernel, one tile per warp, was bound by the LSU pipe);
+// from HBM every time; here a CTA keeps 16 sets resident for the whole stack, two CTAs per SM:
+//   * 16 sets x 17 tokens = 272 rows = 17 MMA row tiles of 16 -> 9 warps x 2 tiles (the last warp's second tile is a
+//     phantom), so every weight fragment read from shared memory feeds two MMAs (the v1 kernel, one tile per warp,
+//     was bound by the LSU pipe); the two resident CTAs run out of phase, so the attention phase of one (LSU + MUFU)
+//     overlaps the MMA / GELU phases of the other (one 544-thread CTA per SM issued only 48 % of the cycles);
 //   * the residual stream lives in registers as mma.sync C fragments (32 fp32 per lane) across all applications;
 //   * LayerNorm is computed on the fragments (quad shuffles); the four Linears are fp16 mma.sync m16n8k16 with fp32
 //     accumulation (fp16 rather than bf16 operands: 3 more mantissa bits, and every operand here is O(1) after
@@ -27,7 +29,8 @@ namespace mpl {
 namespace {
 
 constexpr int J = 17, D = 32, HID = 64, HEADS = 8;
-constexpr int SETS = 32, ROWS = SETS * J, WARPS = 17, THREADS = WARPS * 32;  // 544 rows, one attention thread per row
+constexpr int SETS = 16, ROWS = SETS * J, WARPS = 9, THREADS = WARPS * 32;  // 272 rows, one attention thread per row
+constexpr int SROWS = WARPS * 32;  // staging rows incl. the phantom tile of the last warp (rows 272..287)
 constexpr int QP = 104;     // fp16 row pitch of the q|k|v staging buffer (96 + 8): 52 words -> rows g = 0..7 start on banks
                             // {0,20,8,28,16,4,24,12}: conflict-free half2 C-fragment stores, A-fragment loads and 16 B row loads
 constexpr int QPW = QP / 2;
@@ -38,7 +41,7 @@ constexpr int F_N1W = 0, F_N1B = 32, F_QKVB = 64, F_PROJB = 160, F_N2W = 192, F_
 constexpr int VEC_WORDS = 352, LAYER_WORDS = FRAG_WORDS + VEC_WORDS;  // 4448 words = 17792 bytes
 
 constexpr int SMEM_W = 2 * LAYER_WORDS * 4;
-constexpr int SMEM_QKV = ROWS * QP * 2;
+constexpr int SMEM_QKV = SROWS * QP * 2;
 constexpr int SMEM_TOTAL = SMEM_W + SMEM_QKV;
 
 // staging position (within a 32-wide q, k or v third) of channel c = 8p + 4e + d (head 2p+e, head-dim d): 8p + 2d + e
@@ -56,22 +59,17 @@ __device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// first k-step of a tile: D = A.B + (bx, by, bx, by) -- the bias enters as the C operand, no accumulator initialisation
+__device__ __forceinline__ void mma_f16_16816_bias(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float bx, float by) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(bx), "f"(by));
+}
+
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
   return v;
-}
-
-// erf-form GELU (nn.GELU() default, multiview_mpl.py:22,27) for results that are rounded to fp16 / bf16 right after:
-// 0.5 x (1 + tanh(x (c0 + c1 x^2))) with (c0, c1) fitted to the ERF form (max |error| 2.7e-4 over all x, at |x| ~ 2 where
-// the bf16 half-ulp is 4e-3; tanh.approx adds <= 2^-11 relative).  6 FMA-pipe instructions + one MUFU.
-__device__ __forceinline__ float gelu_tanh_fit(float x) {
-  const float x2 = x * x;
-  const float u = x * fmaf(x2, 0.03470089f, 0.80015708f);
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
-  const float hx = 0.5f * x;
-  return fmaf(hx, th, hx);
 }
 
 // LayerNorm (eps 1e-6, biased variance) of the two rows a lane co-owns, straight to fp16 A fragments (2 k-tiles of 16)
@@ -107,10 +105,13 @@ __device__ __forceinline__ void gemm_tile2(float (&c0)[4], float (&c1)[4], const
                                            const uint32_t* __restrict__ wfrag, int nt, const float* __restrict__ bias, int lane,
                                            int t) {
   const float2 b2 = *reinterpret_cast<const float2*>(bias + 8 * nt + 2 * t);
-  c0[0] = b2.x; c0[1] = b2.y; c0[2] = b2.x; c0[3] = b2.y;
-  c1[0] = b2.x; c1[1] = b2.y; c1[2] = b2.x; c1[3] = b2.y;
+  {
+    const uint2 b = *reinterpret_cast<const uint2*>(wfrag + ((nt * KT) * 32 + lane) * 2);
+    mma_f16_16816_bias(c0, a0[0], b.x, b.y, b2.x, b2.y);
+    mma_f16_16816_bias(c1, a1[0], b.x, b.y, b2.x, b2.y);
+  }
 #pragma unroll
-  for (int kt = 0; kt < KT; ++kt) {
+  for (int kt = 1; kt < KT; ++kt) {
     const uint2 b = *reinterpret_cast<const uint2*>(wfrag + ((nt * KT + kt) * 32 + lane) * 2);
     mma_f16_16816(c0, a0[kt], b.x, b.y);
     mma_f16_16816(c1, a1[kt], b.x, b.y);
@@ -146,7 +147,7 @@ __device__ __forceinline__ __half2 ex2_h2(__half2 x) {
   return h2(r);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel(const SptArgs args) {
+__global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem);
   uint32_t* qkv_w = reinterpret_cast<uint32_t*>(smem + SMEM_W);  // fp16 staging viewed as half2 words, row pitch QPW
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel(const SptArgs arg
   for (int mt = 0; mt < 2; ++mt) {
     lr[mt] = warp * 32 + mt * 16 + g;
     const int64_t gr0 = tile * ROWS + lr[mt], gr1 = gr0 + 8;
-    ok[mt][0] = gr0 < rows_in_view;
-    ok[mt][1] = gr1 < rows_in_view;
+    ok[mt][0] = lr[mt] < ROWS && gr0 < rows_in_view;
+    ok[mt][1] = lr[mt] + 8 < ROWS && gr1 < rows_in_view;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel(const SptArgs arg
   const int aset0 = (arow / J) * J;  // first row of the row's set
   const int64_t agr = tile * ROWS + arow;
   float aconf = 1.0f;
-  if (args.conf != nullptr && agr < rows_in_view) aconf = __ldg(args.conf + view_row0 + agr);
+  if (args.conf != nullptr && arow < ROWS && agr < rows_in_view) aconf = __ldg(args.conf + view_row0 + agr);
 
   for (int layer = 0; layer < args.depth; ++layer) {
     wait_async_all();
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel(const SptArgs arg
       }
       __syncthreads();
       // ---- attention: softmax(q k^T * scale) v over the 17 tokens of the row's set; two heads per half2 lane pair ----
-      {
+      if (arow < ROWS) {
         const float rowscale = weighted ? aconf : 1.0f;
         uint4* rowp = reinterpret_cast<uint4*>(qkv_w + arow * QPW);
         const uint4* setp = reinterpret_cast<const uint4*>(qkv_w + aset0 * QPW);
