@@ -317,6 +317,10 @@ def main():
         if cg:
             from openmpl_b200 import _lib
             _lib.check(_lib.lib().mpl_set_gemm_cta_group(int(cg)))
+        lnf = os.environ.get("MPL_LN_FUSION")
+        if lnf:
+            from openmpl_b200 import _lib
+            _lib.check(_lib.lib().mpl_set_ln_fusion(int(lnf)))
         run_ours(args)
 
 

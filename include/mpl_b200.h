@@ -168,6 +168,11 @@ int mpl_test_gemm(const void* A, const void* W, const float* bias, void* Y, int6
 /* 1: one CTA per 128x256 tile (cta_group::1); 2: CTA pair per 256x256 tile (cta_group::2, cluster 2x1x1). Process-wide. */
 int mpl_set_gemm_cta_group(int cta_group);
 int mpl_get_gemm_cta_group(void);
+/* bf16 mode only: fold the FPT LayerNorms into the projection GEMMs (default 1): the GEMM that updates the residual
+ * stream also emits its bf16 copy and per-row (sum, sum^2); the next GEMM multiplies the raw rows by W diag(gamma) and
+ * applies (mean, rstd) in its epilogue.  0 = separate LayerNorm kernels.  Process-wide; read by mpl_create. */
+int mpl_set_ln_fusion(int enabled);
+int mpl_get_ln_fusion(void);
 
 #ifdef __cplusplus
 }

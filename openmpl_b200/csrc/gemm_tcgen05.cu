@@ -14,6 +14,7 @@
 // the K tail is zero-filled by TMA, so no padding copies are needed.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "kernels.cuh"
@@ -66,20 +67,48 @@ __device__ __forceinline__ float round_tf32_dev(float x) {
   return __uint_as_float(r);
 }
 
-// EPI: 0 bias -> operand dtype, 1 bias + GELU -> operand dtype, 2 Y(fp32) += acc + bias, 3 bias -> fp32
-// accumulator chunk (32 columns of this lane's row) -> + bias (-> GELU) as fp32
+// EPI: 0 bias -> operand dtype, 1 bias + GELU -> operand dtype, 2 Y(fp32) += acc + bias, 3 bias -> fp32,
+//      4 / 5 = 0 / 1 with LayerNorm folded in (see GemmLn), 6 residual update that also emits the next LayerNorm's inputs.
+//
+// LayerNorm fused around the projections (bf16 mode).  LN(x) W^T + b = rstd * (x W'^T - mu * colsum(W')) + b' with
+// W' = W diag(gamma), b' = b + W beta: the consumer GEMM (QKV, fc1; EPI 4 / 5) multiplies the RAW residual rows (a bf16
+// copy) by W' and applies the per-row (mu, rstd) in its epilogue; the producer GEMM of that residual (proj, fc2; EPI 6)
+// computes x_new = x_old + acc + bias in its epilogue, stores it (fp32) together with the bf16 copy and per-row partial
+// (sum, sum of squares) of its column slice into a fixed slot -> no LayerNorm kernel, no atomics, bitwise reproducible.
+struct GemmLn {
+  const float* colsum;      // [N]  sum_k bf16(W'[n,k])                       (EPI 4 / 5)
+  const float2* stats_in;   // [M, slots_in] partial (sum x, sum x^2) per row   (EPI 4 / 5)
+  float2* stats_out;        // [M, slots_out]                                   (EPI 6)
+  __nv_bfloat16* xb;        // [M, N] bf16 copy of the updated residual         (EPI 6)
+  float* y_raw;             // [M, N] the fp32 residual (read in the epilogue)  (EPI 6)
+  int slots_in, slots_out;
+  float inv_k, eps;         // 1 / LayerNorm width (= K of the consumer), LayerNorm eps
+  int flags;                // bit 0: L2-prefetch the residual tile from the producer warp
+};
+
+// accumulator chunk (32 columns of this lane's row) -> + bias (-> GELU) as fp32; LNF: LayerNorm row statistics applied
 template <int KIND, int EPI>
-__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], const float* __restrict__ bias, int n, int N, float (&f)[32]) {
+__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], const float* __restrict__ bias, int n, int N, float (&f)[32],
+                                              const float* __restrict__ colsum = nullptr, float mu = 0.f, float rstd = 1.f) {
   // columns >= N (ragged last tile) are clipped by the TMA store; their bias reads are clamped into the array
+  constexpr bool LNF = (EPI == 4 || EPI == 5);
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + min(n + i, N - 4)));
-    f[i] = __uint_as_float(v[i]) + b4.x;
-    f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-    f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
-    f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+    if constexpr (LNF) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(colsum + min(n + i, N - 4)));
+      f[i] = fmaf(rstd, fmaf(-mu, c4.x, __uint_as_float(v[i])), b4.x);
+      f[i + 1] = fmaf(rstd, fmaf(-mu, c4.y, __uint_as_float(v[i + 1])), b4.y);
+      f[i + 2] = fmaf(rstd, fmaf(-mu, c4.z, __uint_as_float(v[i + 2])), b4.z);
+      f[i + 3] = fmaf(rstd, fmaf(-mu, c4.w, __uint_as_float(v[i + 3])), b4.w);
+    } else {
+      f[i] = __uint_as_float(v[i]) + b4.x;
+      f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+      f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
+      f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+    }
   }
-  if constexpr (EPI == 1) {
+  if constexpr (EPI == 1 || EPI == 5) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = (KIND == 0) ? gelu_tanh_fit(f[i]) : round_tf32_dev(gelu_erf(f[i]));
   }
@@ -111,7 +140,7 @@ template <int CG, int KIND, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int64_t M, int N, int K,
-                    int bn) {  // bn: output-tile width (256 / 192 / 128), chosen so that no interior tile is narrow
+                    int bn, const GemmLn ln) {  // bn: output-tile width (256 / 192 / 128), chosen so that no interior tile is narrow
   using C = Cfg<CG>;
   constexpr int ESZ = (KIND == 0) ? 2 : 4;
   constexpr int BK = KB_BYTES / ESZ;  // K elements per stage
@@ -244,7 +273,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================================== epilogue ==========================================
     const int q = warp & 3;            // TMEM lane quarter this warp may read (warp id % 4)
     const int half = (warp - 4) >> 2;  // 0: even 64-column groups, 1: odd groups
-    constexpr bool OUT_BF16 = (KIND == 0) && (EPI == 0 || EPI == 1);
+    constexpr bool OUT_BF16 = (KIND == 0) && (EPI == 0 || EPI == 1 || EPI == 4 || EPI == 5);
+    constexpr bool LNF = (EPI == 4 || EPI == 5);
     const uint32_t box = staging_base + (uint32_t)(warp - 4) * 4096u;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -255,6 +285,104 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n_size = min(bn, N - n_blk * bn);
       const int32_t row0 = (int32_t)(m_blk * BM * CG + cta_rank * BM + q * 32);  // first row of this warp's 32-row box
       const int ncol0 = n_blk * bn;
+      const int64_t my_row = (int64_t)row0 + lane;
+      const bool row_ok = my_row < M;
+      float mu = 0.f, rstd = 1.f;
+      if constexpr (LNF) {
+        // LayerNorm statistics of this lane's row from the producer's per-slice partial sums (fixed order: reproducible)
+        float s1 = 0.f, s2 = 0.f;
+        if (row_ok) {
+          const float2* sp = ln.stats_in + my_row * ln.slots_in;
+          for (int i0 = 0; i0 < ln.slots_in; i0 += 16) {  // 16 independent loads in flight, summed in slot order
+            float2 t[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = (i0 + i < ln.slots_in) ? sp[i0 + i] : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { s1 += t[i].x; s2 += t[i].y; }
+          }
+        }
+        mu = s1 * ln.inv_k;
+        rstd = rsqrtf(fmaxf(fmaf(-mu, mu, s2 * ln.inv_k), 0.f) + ln.eps);
+      }
+      if constexpr (EPI == 6) {
+        // Residual update x_new = x_old + acc + bias, 32-column chunks.  The accumulator arrives one row per lane; the
+        // residual is read and written in a COALESCED layout instead (lane = (row & 3, 16-byte column group): 4 rows x
+        // 128 B per instruction), the staging box doing the transpose.  x_old of the next chunk is prefetched into
+        // registers while the current one is processed (the first one before the accumulator is even complete).
+        const int rs = lane >> 3, c4 = lane & 7;
+        auto chunk_col = [&](int ci) { return half * 64 + (ci >> 1) * 128 + (ci & 1) * 32; };
+        // No predicates: N % 32 == 0 makes a chunk valid for all lanes or none, and the caller pads the residual, its
+        // bf16 copy and the statistics to a multiple of BM * CG rows, so rows past M are scratch (read, updated, ignored).
+        float* const lp = ln.y_raw + ((int64_t)row0 + rs) * N + ncol0 + 4 * c4;
+        __nv_bfloat16* const lb = ln.xb + ((int64_t)row0 + rs) * N + ncol0 + 4 * c4;
+        const int64_t rowstep = 4 * (int64_t)N;
+        auto load_xold = [&](int ci, float4 (&xo)[8]) {
+          const float* p = lp + chunk_col(ci);
+#pragma unroll
+          for (int it = 0; it < 8; ++it, p += rowstep) xo[it] = *reinterpret_cast<const float4*>(p);
+        };
+        float s1[8], s2[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) { s1[it] = 0.f; s2[it] = 0.f; }
+        float4 xo[2][8];  // ping-pong prefetch buffers (the chunk loop is fully unrolled: compile-time indices, no copies)
+        load_xold(0, xo[0]);
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        const uint32_t rd_base = box + rs * 128;  // this lane reads rows 4*it + rs of the box: (4*it + rs) & 7 = ((it & 1) * 4 + rs)
+        const uint32_t rd_sw0 = (uint32_t)((c4 ^ rs) << 4), rd_sw1 = (uint32_t)((c4 ^ (4 + rs)) << 4);
+#pragma unroll
+        for (int ci = 0; ci < BN / 64; ++ci) {  // at most 4 chunks of 32 columns per warp and tile
+          const int cc = chunk_col(ci);
+          if (cc >= n_size) break;
+          uint32_t va[32];
+          ptx::tmem_ld_32x32(taddr + cc, va);
+          if (ci + 1 < BN / 64 && chunk_col(ci + 1) < n_size) load_xold(ci + 1, xo[(ci + 1) & 1]);
+          ptx::tmem_ld_wait();
+          float f[32];
+          epilogue_math<KIND, 0>(va, bias, ncol0 + cc, N, f);
+          stage_row_f32(box, lane, f);
+          __syncwarp();
+          float* sp = lp + cc;
+          __nv_bfloat16* sb = lb + cc;
+#pragma unroll
+          for (int it = 0; it < 8; ++it, sp += rowstep, sb += rowstep) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(rd_base + it * 512 + ((it & 1) ? rd_sw1 : rd_sw0)));
+            const float4 o = xo[ci & 1][it];
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            s1[it] += (v.x + v.y) + (v.z + v.w);
+            s2[it] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[it]))));
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<float4*>(sp) = v;
+            *reinterpret_cast<uint2*>(sb) = pk;
+          }
+          __syncwarp();  // every lane is done reading the box before the next chunk is staged
+        }
+        // per-row partial statistics: sum over the 8 lanes that share a row, fixed order
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            s1[it] += __shfl_xor_sync(0xffffffffu, s1[it], o);
+            s2[it] += __shfl_xor_sync(0xffffffffu, s2[it], o);
+          }
+          if (c4 == 0) ln.stats_out[((int64_t)row0 + 4 * it + rs) * ln.slots_out + 2 * n_blk + half] = make_float2(s1[it], s2[it]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
+          else ptx::mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -266,8 +394,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (OUT_BF16) {
           // one 64-column bf16 box per step
           float fa[32], fb[32];
-          epilogue_math<KIND, EPI>(va, bias, ncol0 + c, N, fa);
-          epilogue_math<KIND, EPI>(vb, bias, ncol0 + c + 32, N, fb);
+          epilogue_math<KIND, EPI>(va, bias, ncol0 + c, N, fa, ln.colsum, mu, rstd);
+          epilogue_math<KIND, EPI>(vb, bias, ncol0 + c + 32, N, fb, ln.colsum, mu, rstd);
           if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has finished reading the box
           __syncwarp();
           stage_row_bf16(box, lane, 0, fa);
@@ -362,13 +490,15 @@ int g_gemm_cta_group = 2;  // CTA pairs by default: half the operand traffic per
 
 template <int CG, int KIND, int EPI>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const float* bias, int64_t M, int N,
-               int K, int bn, cudaStream_t s) {
+               int K, int bn, const GemmLn& ln, cudaStream_t s) {
   using C = Cfg<CG>;
   auto kern = gemm_tcgen05_kernel<CG, KIND, EPI>;
-  static bool attr_set = false;  // per instantiation; the attribute is per function, valid on every device of the process
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per instantiation and device (function attributes live in the device's context)
+  int dev = 0;
+  MPL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int n_tiles = (N + bn - 1) / bn;
   const int64_t m_tiles = ceil_div(M, (int64_t)BM * CG);
@@ -387,19 +517,30 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmY, bias, M, N, K, bn));
+  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmY, bias, M, N, K, bn, ln));
   return MPL_OK;
 }
 
 template <int CG, int KIND>
 int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const float* bias, int64_t M,
-               int N, int K, int bn, cudaStream_t s) {
+               int N, int K, int bn, const GemmLn& ln, cudaStream_t s) {
   switch (epi) {
-    case 0: return launch_one<CG, KIND, 0>(tmA, tmB, tmY, bias, M, N, K, bn, s);
-    case 1: return launch_one<CG, KIND, 1>(tmA, tmB, tmY, bias, M, N, K, bn, s);
-    case 2: return launch_one<CG, KIND, 2>(tmA, tmB, tmY, bias, M, N, K, bn, s);
-    default: return launch_one<CG, KIND, 3>(tmA, tmB, tmY, bias, M, N, K, bn, s);
+    case 0: return launch_one<CG, KIND, 0>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+    case 1: return launch_one<CG, KIND, 1>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+    case 2: return launch_one<CG, KIND, 2>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+    case 3: return launch_one<CG, KIND, 3>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+    default: break;
   }
+  if constexpr (KIND == 0) {  // the LayerNorm-fused epilogues exist for bf16 operands only
+    switch (epi) {
+      case 4: return launch_one<CG, KIND, 4>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+      case 5: return launch_one<CG, KIND, 5>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+      case 6: return launch_one<CG, KIND, 6>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+      default: break;
+    }
+  }
+  set_error("launch_gemm_tcgen05: epilogue %d is not available for this operand type", epi);
+  return MPL_ERR_UNSUPPORTED;
 }
 
 // Output-tile width.  Interior tiles must be multiples of 64 columns (the epilogue stores 64-column groups).  Wide tiles
@@ -425,9 +566,37 @@ bool gemm_tcgen05_supports(int N, int K, int dtype) {
   return N >= 16 && N % 16 == 0 && K >= 1 && ((int64_t)K * esz) % 16 == 0;
 }
 
+int gemm_ln_slots(int N) { return 2 * ((N + pick_tile_n(N) - 1) / pick_tile_n(N)); }
+
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
-                        int epilogue, int out_fp32, cudaStream_t s) {
+                        int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* lnargs) {
   if (M == 0) return MPL_OK;
+  GemmLn ln{};
+  if (epilogue >= EPI_LN_BIAS) {
+    if (lnargs == nullptr || dtype != MPL_PREC_BF16) {
+      set_error("launch_gemm_tcgen05: LayerNorm-fused epilogues need bf16 operands and GemmLnArgs");
+      return MPL_ERR_INVALID_ARGUMENT;
+    }
+    ln.colsum = lnargs->colsum;
+    ln.stats_in = reinterpret_cast<const float2*>(lnargs->stats_in);
+    ln.stats_out = reinterpret_cast<float2*>(lnargs->stats_out);
+    ln.xb = reinterpret_cast<__nv_bfloat16*>(lnargs->xb);
+    ln.y_raw = reinterpret_cast<float*>(Y);
+    ln.slots_in = lnargs->slots_in;
+    ln.slots_out = gemm_ln_slots(N);
+    ln.inv_k = 1.0f / (float)K;
+    ln.eps = lnargs->eps;
+    static const int dbg_flags = getenv("MPL_GEMM_LN_FLAGS") ? atoi(getenv("MPL_GEMM_LN_FLAGS")) : 0;
+    ln.flags = dbg_flags;
+    if (epilogue == EPI_RESIDUAL_EMIT && (N % 32 != 0 || ln.stats_out == nullptr || ln.xb == nullptr)) {
+      set_error("launch_gemm_tcgen05: residual-emit epilogue needs N %% 32 == 0, a statistics buffer and a bf16 copy buffer");
+      return MPL_ERR_INVALID_ARGUMENT;
+    }
+    if (epilogue != EPI_RESIDUAL_EMIT && (ln.colsum == nullptr || ln.stats_in == nullptr || ln.slots_in < 1)) {
+      set_error("launch_gemm_tcgen05: LayerNorm-apply epilogue needs column sums and row statistics");
+      return MPL_ERR_INVALID_ARGUMENT;
+    }
+  }
   if (dtype != MPL_PREC_BF16 && dtype != MPL_PREC_TF32) {
     set_error("launch_gemm_tcgen05: dtype must be MPL_PREC_BF16 or MPL_PREC_TF32");
     return MPL_ERR_INVALID_ARGUMENT;
@@ -450,12 +619,12 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
   if (epilogue == EPI_BIAS && out_fp32) epi = 3;
   const int kind = (dtype == MPL_PREC_BF16) ? 0 : 1;
   // output boxes: 32 rows x 128 bytes (64 bf16 or 32 fp32 columns), 128B swizzle like the staging writes
-  const bool out_bf16 = kind == 0 && (epi == 0 || epi == 1);
+  const bool out_bf16 = kind == 0 && (epi == 0 || epi == 1 || epi == 4 || epi == 5);
   MPL_TRY(make_tmap(&tmY, Y, M, N, out_bf16 ? 2 : 4, 32, out_bf16 ? 64 : 32));
   if (cg == 1) {
-    return kind == 0 ? launch_epi<1, 0>(epi, tmA, tmB, tmY, bias, M, N, K, bn, s) : launch_epi<1, 1>(epi, tmA, tmB, tmY, bias, M, N, K, bn, s);
+    return kind == 0 ? launch_epi<1, 0>(epi, tmA, tmB, tmY, bias, M, N, K, bn, ln, s) : launch_epi<1, 1>(epi, tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
   }
-  return kind == 0 ? launch_epi<2, 0>(epi, tmA, tmB, tmY, bias, M, N, K, bn, s) : launch_epi<2, 1>(epi, tmA, tmB, tmY, bias, M, N, K, bn, s);
+  return kind == 0 ? launch_epi<2, 0>(epi, tmA, tmB, tmY, bias, M, N, K, bn, ln, s) : launch_epi<2, 1>(epi, tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
 }
 
 }  // namespace mpl

@@ -156,88 +156,104 @@ __global__ void __launch_bounds__(256) token_build_vec_kernel(const TokenArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K5 fused head (multiview_mpl.py:425-446, 517-523): one WARP per pose.  Channel e of the stripped row lives in lane
-// e % 32, register e / 32 (segments are multiples of 32 wide for the shipped d = 32, so every load is a coalesced
+// K5 fused head (multiview_mpl.py:425-446, 517-523): one WARP per PAIR of poses.  Channel e of the stripped row lives in
+// lane e % 32, register e / 32 (segments are multiples of 32 wide for the shipped d = 32, so every load is a coalesced
 // 128-byte line); View_norm and the head LayerNorm reduce with shuffles only — no shared memory, no block barriers.
-// The E -> 3J Linear reads each weight row once per warp (L1-resident, 3J*E*4 = 111 KB) and reduces across lanes.
+// The E -> 3J Linear reads each weight row once per pose pair (L1-resident, 3J*E*4 = 111 KB) and reduces across lanes.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(256, 3) head_warp_kernel(const HeadArgs a) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void head_pool_one(const HeadArgs& a, int64_t b, int lane, float (&pooled)[NV]) {
   const int E = a.E;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  int col[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int e = 32 * i + lane;
-    col[i] = (e / a.seg_len) * a.seg_stride + (e % a.seg_len);
-  }
   const float invE = 1.0f / (float)E;
-  for (int64_t b = warp_global; b < a.B; b += warps_total) {
-    float pooled[NV];
-    const float wmb = __ldg(a.wm_b);
+  const float wmb = __ldg(a.wm_b);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) pooled[i] = wmb;
-    for (int v = 0; v < a.V; ++v) {
-      const float* row = a.tok + (b * a.V + v) * (int64_t)a.tok_w;
-      float x[NV];
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        x[i] = (32 * i + lane < E) ? row[col[i]] : 0.f;
-        s += x[i];
-      }
-      const float mean = warp_sum(s) * invE;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float t = (32 * i + lane < E) ? x[i] - mean : 0.f;
-        q = fmaf(t, t, q);
-      }
-      const float rstd = rsqrtf(warp_sum(q) * invE + 1e-6f);
-      const float wv = __ldg(a.wm_w + v);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int e = 32 * i + lane;
-        if (e < E) pooled[i] = fmaf(wv, fmaf((x[i] - mean) * rstd, __ldg(a.vn_w + e), __ldg(a.vn_b + e)), pooled[i]);
-      }
-    }
+  for (int i = 0; i < NV; ++i) pooled[i] = wmb;
+  for (int v = 0; v < a.V; ++v) {
+    const float* row = a.tok + (b * a.V + v) * (int64_t)a.tok_w + lane;
+    float x[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) s += (32 * i + lane < E) ? pooled[i] : 0.f;
+    for (int i = 0; i < NV; ++i) {
+      const int e0 = 32 * i;  // warp-uniform: the whole 32-channel group sits in one segment (seg_len % 32 == 0)
+      x[i] = (e0 + lane < E) ? row[(e0 / a.seg_len) * a.seg_stride + (e0 % a.seg_len)] : 0.f;
+      s += x[i];
+    }
     const float mean = warp_sum(s) * invE;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float t = (32 * i + lane < E) ? pooled[i] - mean : 0.f;
+      const float t = (32 * i + lane < E) ? x[i] - mean : 0.f;
       q = fmaf(t, t, q);
     }
-    const float rstd = rsqrtf(warp_sum(q) * invE + 1e-5f);  // head LayerNorm: default eps (multiview_mpl.py:284)
+    const float rstd = rsqrtf(warp_sum(q) * invE + 1e-6f);
+    const float wv = __ldg(a.wm_w + v);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int e = 32 * i + lane;
-      pooled[i] = (e < E) ? fmaf((pooled[i] - mean) * rstd, __ldg(a.hn_w + e), __ldg(a.hn_b + e)) : 0.f;
+      if (e < E) pooled[i] = fmaf(wv, fmaf((x[i] - mean) * rstd, __ldg(a.vn_w + e), __ldg(a.vn_b + e)), pooled[i]);
     }
-    // Linear E -> out_dim: lane-partial dot products, butterfly reduction; lane o % 32 keeps output o
-    float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (32 * i + lane < E) ? pooled[i] : 0.f;
+  const float mean = warp_sum(s) * invE;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float t = (32 * i + lane < E) ? pooled[i] - mean : 0.f;
+    q = fmaf(t, t, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * invE + 1e-5f);  // head LayerNorm: default eps (multiview_mpl.py:284)
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = 32 * i + lane;
+    pooled[i] = (e < E) ? fmaf((pooled[i] - mean) * rstd, __ldg(a.hn_w + e), __ldg(a.hn_b + e)) : 0.f;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256, 2) head_warp_kernel(const HeadArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int E = a.E;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t pairs = (a.B + 1) >> 1;
+  for (int64_t pr = warp_global; pr < pairs; pr += warps_total) {
+    const int64_t b0 = 2 * pr;
+    const bool two = b0 + 1 < a.B;
+    float p0[NV], p1[NV];
+    head_pool_one<NV>(a, b0, lane, p0);
+    head_pool_one<NV>(a, two ? b0 + 1 : b0, lane, p1);
+    // Linear E -> out_dim: lane-partial dot products, butterfly reduction; lane o % 32 keeps output o of both poses
+    float k0[3] = {0.f, 0.f, 0.f}, k1[3] = {0.f, 0.f, 0.f};
     for (int o = 0; o < a.out_dim; ++o) {
-      const float* wr = a.hw + (int64_t)o * E;
-      float acc = 0.f;
+      const float* wr = a.hw + (int64_t)o * E + lane;
+      float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const int e = 32 * i + lane;
-        if (e < E) acc = fmaf(pooled[i], __ldg(wr + e), acc);
+        if (32 * i + lane < E) {
+          const float w = __ldg(wr + 32 * i);
+          acc0 = fmaf(p0[i], w, acc0);
+          acc1 = fmaf(p1[i], w, acc1);
+        }
       }
-      acc = warp_sum(acc);
+      acc0 = warp_sum(acc0);
+      acc1 = warp_sum(acc1);
       if ((o & 31) == lane) {
-        if (o < 32) keep0 = acc; else if (o < 64) keep1 = acc; else keep2 = acc;
+        k0[0] = (o < 32) ? acc0 : k0[0]; k0[1] = (o >= 32 && o < 64) ? acc0 : k0[1]; k0[2] = (o >= 64) ? acc0 : k0[2];
+        k1[0] = (o < 32) ? acc1 : k1[0]; k1[1] = (o >= 32 && o < 64) ? acc1 : k1[1]; k1[2] = (o >= 64) ? acc1 : k1[2];
       }
     }
-    float* out = a.out + b * a.out_dim;
-    if (lane < a.out_dim) out[lane] = keep0 + __ldg(a.hb + lane);
-    if (32 + lane < a.out_dim) out[32 + lane] = keep1 + __ldg(a.hb + 32 + lane);
-    if (64 + lane < a.out_dim) out[64 + lane] = keep2 + __ldg(a.hb + 64 + lane);
+    float* out0 = a.out + b0 * a.out_dim;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int o = 32 * r + lane;
+      if (o < a.out_dim) {
+        const float hb = __ldg(a.hb + o);
+        out0[o] = k0[r] + hb;
+        if (two) out0[a.out_dim + o] = k1[r] + hb;
+      }
+    }
   }
 }
 
@@ -280,9 +296,9 @@ int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s) {
 }
 
 int try_launch_head_warp(const HeadArgs& a, cudaStream_t s) {
-  if (a.E > 32 * 17 || a.out_dim > 96) return 1;
+  if (a.E > 32 * 17 || a.out_dim > 96 || a.seg_len % 32 != 0) return 1;
   if (a.B == 0) return MPL_OK;
-  const int64_t blocks = std::min<int64_t>(ceil_div(a.B, 8), (int64_t)kNumSMs * 16);
+  const int64_t blocks = std::min<int64_t>(ceil_div(a.B, 16), (int64_t)kNumSMs * 16);
   if (a.E > 32 * 9) head_warp_kernel<17><<<(unsigned)blocks, 256, 0, s>>>(a);
   else head_warp_kernel<9><<<(unsigned)blocks, 256, 0, s>>>(a);
   MPL_LAUNCH_CHECK();

@@ -61,6 +61,13 @@ int launch_layernorm_bf16(const float* x, int64_t ldx, const float* w, const flo
 int launch_layernorm_tf32(const float* x, int64_t ldx, const float* w, const float* b, float eps, float* y, int64_t ldy,
                           int64_t rows, int C, cudaStream_t s);
 
+// entry of the LayerNorm-fused FPT: raw bf16 copy of the rows + (sum, sum^2) in statistics slot 0 of `slots`
+int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, int64_t ldb, void* stats, int slots, int64_t rows, int C,
+                   cudaStream_t s);
+// pack time: W' = bf16(W diag(gamma)), colsum = row sums of W', bias' = b + W beta
+int launch_ln_fold(const float* W, const float* b, const float* gamma, const float* beta, __nv_bfloat16* Wf, float* colsum,
+                   float* bias_f, int N, int K, cudaStream_t s);
+
 // ---- fp32 CUDA-core Linear: Y = act(X W^T + bias) (+ R) ------------------------------------------------------------
 int launch_linear_f32(const float* X, int64_t lda, const float* W, const float* bias, const float* R, int64_t ldr,
                       float* Y, int64_t ldc, int64_t M, int N, int K, int act, cudaStream_t s);
@@ -101,12 +108,27 @@ int launch_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t
 int launch_to_tf32(const float* src, float* dst, int64_t n, cudaStream_t s);
 
 // ---- tcgen05 projection GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
-enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESIDUAL = 2 };
+enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_LN_BIAS = 4, EPI_LN_BIAS_GELU = 5, EPI_RESIDUAL_EMIT = 6 };
+// LayerNorm fused around the bf16 projections (see gemm_tcgen05.cu):
+//   EPI_RESIDUAL_EMIT  Y(fp32) = Y + A W^T + bias, plus xb = bf16(Y) and per-row partial (sum, sum^2) into stats_out
+//                      [M, gemm_ln_slots(N)] float2.  Y, xb and stats_out must be ALLOCATED for M rounded up to a
+//                      multiple of 256 rows (the epilogue reads and writes whole row tiles unpredicated), N % 32 == 0;
+//   EPI_LN_BIAS(_GELU) Y = act(rstd * (A W'^T - mu * colsum) + bias) with A = xb (raw residual rows), W' = W diag(gamma),
+//                      bias = b + W beta, (mu, rstd) from stats_in [M, slots_in].
+struct GemmLnArgs {
+  const float* colsum;
+  const void* stats_in;
+  void* stats_out;
+  void* xb;
+  int slots_in;
+  float eps;
+};
+int gemm_ln_slots(int N);
 // A [M,K] row-major (lda = K), W [N,K] row-major, both bf16 (dtype MPL_PREC_BF16) or tf32-rounded fp32 (MPL_PREC_TF32).
 // EPI_BIAS / EPI_BIAS_GELU write Y [M,N] in the operand dtype (or fp32 if out_fp32); EPI_BIAS_RESIDUAL does
 // Y(fp32) += A W^T + bias in place.
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
-                        int epilogue, int out_fp32, cudaStream_t s);
+                        int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* ln = nullptr);
 bool gemm_tcgen05_supports(int N, int K, int dtype);
 
 // ---- K2: fused Spatial Pose Transformer stack (spt_fused.cu) ---------------------------------------------------------

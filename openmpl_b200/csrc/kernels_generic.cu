@@ -279,6 +279,87 @@ int launch_layernorm_tf32(const float* x, int64_t ldx, const float* w, const flo
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Entry of the LayerNorm-fused FPT (bf16 mode): the residual rows as a raw bf16 copy + their (sum, sum of squares) in
+// statistics slot 0 (the other slots zeroed) -- what the residual-emit GEMM epilogue produces for every later block.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MAXV4>
+__global__ void __launch_bounds__(256) ln_prep_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ xb,
+                                                      int64_t ldb, float2* __restrict__ stats, int slots, int64_t rows, int C) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const int n4 = C >> 2;
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    const int e4 = lane + i * 32;
+    if (e4 < n4) {
+      const float4 v = xr[e4];
+      s += (v.x + v.y) + (v.z + v.w);
+      q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(xb + row * ldb)[e4] = pk;
+    }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  for (int i = lane; i < slots; i += 32) stats[row * slots + i] = (i == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
+int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, int64_t ldb, void* stats, int slots, int64_t rows, int C,
+                   cudaStream_t s) {
+  if (rows == 0) return MPL_OK;
+  if (C % 4 != 0 || ldx % 4 != 0 || ldb % 4 != 0 || C > 32 * 4 * 17) {
+    set_error("launch_ln_prep: width %d is not supported", C);
+    return MPL_ERR_UNSUPPORTED;
+  }
+  const unsigned grid = (unsigned)ceil_div(rows, 8);
+  float2* st = reinterpret_cast<float2*>(stats);
+  if (C <= 32 * 4 * 5) ln_prep_kernel<5><<<grid, 256, 0, s>>>(x, ldx, xb, ldb, st, slots, rows, C);
+  else if (C <= 32 * 4 * 9) ln_prep_kernel<9><<<grid, 256, 0, s>>>(x, ldx, xb, ldb, st, slots, rows, C);
+  else ln_prep_kernel<17><<<grid, 256, 0, s>>>(x, ldx, xb, ldb, st, slots, rows, C);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// Pack-time fold of a LayerNorm into the Linear that consumes it: W' = bf16(W diag(gamma)), colsum[n] = sum_k W'[n,k]
+// (of the ROUNDED values: it must cancel exactly what the tensor core multiplies), bias'[n] = b[n] + sum_k W[n,k] beta[k].
+__global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      __nv_bfloat16* __restrict__ Wf, float* __restrict__ colsum,
+                                                      float* __restrict__ bias_f, int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(int64_t)n * K + k];
+    const __nv_bfloat16 r = __float2bfloat16_rn(w * gamma[k]);
+    Wf[(int64_t)n * K + k] = r;
+    cs += __bfloat162float(r);
+    bb = fmaf(w, beta[k], bb);
+  }
+  cs = warp_sum(cs);
+  bb = warp_sum(bb);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_f[n] = (b != nullptr ? b[n] : 0.f) + bb;
+  }
+}
+
+int launch_ln_fold(const float* W, const float* b, const float* gamma, const float* beta, __nv_bfloat16* Wf, float* colsum,
+                   float* bias_f, int N, int K, cudaStream_t s) {
+  if (N == 0) return MPL_OK;
+  ln_fold_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, s>>>(W, b, gamma, beta, Wf, colsum, bias_f, N, K);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // fp32 Linear on CUDA cores: 64x64 output tile, K step 16, 256 threads x (4x4) accumulators.  Any M, N, K, strides.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int LBM = 64, LBN = 64, LBK = 16;

@@ -25,6 +25,7 @@ void set_error(const char* fmt, ...) {
 
 void set_gemm_cta_group(int cg);
 int get_gemm_cta_group();
+static int g_ln_fusion = 1;  // bf16 mode: LayerNorm fused into the FPT projection epilogues (handles created afterwards)
 
 struct ParamInfo {
   std::string name;
@@ -58,6 +59,8 @@ struct MplModel {
   int n_out;
   bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
   bool spt_fused;  // the SPT stack runs as the single fused bf16-mma kernel (bf16 mode, d=32, H=8, J=17)
+  bool ln_fused;   // bf16 mode: the FPT LayerNorms are folded into the projection GEMMs (no LayerNorm kernel)
+  int ln_slots;    // statistics slots per row written by the residual-emit GEMMs
   std::vector<ParamInfo> params;
   std::unordered_map<std::string, int> index;
   std::vector<Derived> derived;
@@ -236,9 +239,18 @@ static void build_tables(MplModel* m) {
     for (int l = 0; l < m->depth; ++l) {
       const std::string p = "blocks." + std::to_string(l) + ".";
       const int64_t D = m->fpt_dim, Hf = m->fpt_hidden;
-      add_derived(m, tag + p + "attn.qkv.weight", 3 * D * D, esz);
+      if (m->ln_fused) {
+        add_derived(m, "lnw:" + p + "attn.qkv", 3 * D * D, 2);
+        add_derived(m, "lncs:" + p + "attn.qkv", 3 * D, 4);
+        add_derived(m, "lnb:" + p + "attn.qkv", 3 * D, 4);
+        add_derived(m, "lnw:" + p + "mlp.fc1", Hf * D, 2);
+        add_derived(m, "lncs:" + p + "mlp.fc1", Hf, 4);
+        add_derived(m, "lnb:" + p + "mlp.fc1", Hf, 4);
+      } else {
+        add_derived(m, tag + p + "attn.qkv.weight", 3 * D * D, esz);
+        add_derived(m, tag + p + "mlp.fc1.weight", Hf * D, esz);
+      }
       add_derived(m, tag + p + "attn.proj.weight", D * D, esz);
-      add_derived(m, tag + p + "mlp.fc1.weight", Hf * D, esz);
       add_derived(m, tag + p + "mlp.fc2.weight", D * Hf, esz);
     }
   }
@@ -275,6 +287,7 @@ struct Workspace {
   float *xs, *xn, *qkv, *att, *hid, *conf;       // SPT, [V*Bc*J, .]
   float* tok;                                    // [Bc, V*tok_w] fp32 residual stream of the FPT
   void *fxn, *fqkv, *fatt, *fhid;                // FPT activations (fp32 / bf16 per precision)
+  void* fstats;                                  // [Bc*N, ln_slots] float2 row statistics (LayerNorm-fused bf16 mode)
   float *vn, *pooled, *hn, *h1, *h2, *cat;       // head
   size_t bytes;
 };
@@ -297,15 +310,18 @@ static Workspace layout_workspace(const MplModel* m, int64_t Bc, uint8_t* base) 
     w.hid = (float*)take(Rs * m->spt_hidden * 4);
   }
   if (m->d.confidence_as_attention_uncertainty_weight) w.conf = (float*)take(Rs * 4);
-  w.tok = (float*)take(Bc * (int64_t)m->V * m->tok_w * 4);
+  // LayerNorm-fused mode: the residual-emit epilogue touches whole 256-row tiles -> rows padded (pad rows are scratch)
+  const int64_t tok_rows_pad = m->ln_fused ? (int64_t)align_up((size_t)(Bc * m->fpt_tokens), 256) * m->fpt_dim : 0;
+  w.tok = (float*)take(std::max<int64_t>(Bc * (int64_t)m->V * m->tok_w, tok_rows_pad) * 4);
   if (!m->d.no_transformer_fpt) {
-    const int64_t Rf = Bc * m->fpt_tokens;
+    const int64_t Rf = m->ln_fused ? (int64_t)align_up((size_t)(Bc * m->fpt_tokens), 256) : Bc * m->fpt_tokens;
     const int64_t D = m->fpt_dim, Hf = m->fpt_hidden;
     const int esz = (m->fpt_tc && m->d.precision == MPL_PREC_BF16) ? 2 : 4;
     w.fxn = take(Rf * D * esz);
     w.fqkv = take(Rf * 3 * D * esz);
     w.fatt = take(Rf * D * esz);
     w.fhid = take(Rf * Hf * esz);
+    if (m->ln_fused) w.fstats = take(Rf * (size_t)m->ln_slots * 8);
   }
   const int E = m->E, Hd = m->d.hidden_dim, out_dim = 3 * m->J;
   const bool fused_head = !m->d.linear_weighted_mean && !m->d.deep_head && !m->d.head_kadkhod;
@@ -358,6 +374,7 @@ static cudaEvent_t prof_event(MplModel* m) {
 struct BlockW {
   const float *n1w, *n1b, *qkvw, *qkvb, *projw, *projb, *n2w, *n2b, *fc1w, *fc1b, *fc2w, *fc2b;
   const void *qkvw_tc, *projw_tc, *fc1w_tc, *fc2w_tc;  // tensor-core operand copies (FPT, bf16 / tf32 modes)
+  const float *qkv_cs, *qkv_bf, *fc1_cs, *fc1_bf;      // LayerNorm-fused mode: column sums of W' and folded biases
 };
 
 static BlockW block_weights(const MplModel* m, const Packed& P, const std::string& p, bool tc) {
@@ -376,9 +393,18 @@ static BlockW block_weights(const MplModel* m, const Packed& P, const std::strin
   b.fc2b = P.f(p + "mlp.fc2.bias");
   if (tc) {
     const std::string tag = (m->d.precision == MPL_PREC_BF16) ? "bf16:" : "tf32:";
-    b.qkvw_tc = P.dv(tag + p + "attn.qkv.weight");
+    if (m->ln_fused) {
+      b.qkvw_tc = P.dv("lnw:" + p + "attn.qkv");
+      b.qkv_cs = P.df("lncs:" + p + "attn.qkv");
+      b.qkv_bf = P.df("lnb:" + p + "attn.qkv");
+      b.fc1w_tc = P.dv("lnw:" + p + "mlp.fc1");
+      b.fc1_cs = P.df("lncs:" + p + "mlp.fc1");
+      b.fc1_bf = P.df("lnb:" + p + "mlp.fc1");
+    } else {
+      b.qkvw_tc = P.dv(tag + p + "attn.qkv.weight");
+      b.fc1w_tc = P.dv(tag + p + "mlp.fc1.weight");
+    }
     b.projw_tc = P.dv(tag + p + "attn.proj.weight");
-    b.fc1w_tc = P.dv(tag + p + "mlp.fc1.weight");
     b.fc2w_tc = P.dv(tag + p + "mlp.fc2.weight");
   }
   return b;
@@ -402,9 +428,28 @@ static int block_f32(MplModel* m, bool fpt, const BlockW& w, float* x, int64_t r
 
 // Same block with the four projections on tcgen05 (bf16 or tf32 operands); LayerNorm / softmax / residual stay fp32.
 static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_t sets, int N, int C, int hidden, float scale,
-                    void* xn, void* qkv, void* att, void* hid, cudaStream_t s) {
+                    void* xn, void* qkv, void* att, void* hid, void* stats, cudaStream_t s) {
   const int prec = m->d.precision;
   const int hd = C / m->H;
+  if (m->ln_fused) {
+    // xn holds the raw bf16 copy of x and `stats` its per-row (sum, sum^2) partials, both written by the previous
+    // residual-emit epilogue (or by launch_ln_prep before the first block): 5 launches per block, no LayerNorm kernel
+    GemmLnArgs app{};  // LayerNorm-apply side (QKV, fc1)
+    app.stats_in = stats;
+    app.slots_in = m->ln_slots;
+    app.eps = 1e-6f;
+    GemmLnArgs emit{};  // residual-emit side (proj, fc2)
+    emit.stats_out = stats;
+    emit.xb = xn;
+    app.colsum = w.qkv_cs;
+    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkv_bf, qkv, rows, 3 * C, C, prec, EPI_LN_BIAS, 0, s, &app));
+    LC(CAT_FPT_ATTN, launch_attention_bf16((const __nv_bfloat16*)qkv, (__nv_bfloat16*)att, sets, N, m->H, hd, scale, s));
+    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_RESIDUAL_EMIT, 1, s, &emit));
+    app.colsum = w.fc1_cs;
+    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1_bf, hid, rows, hidden, C, prec, EPI_LN_BIAS_GELU, 0, s, &app));
+    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_RESIDUAL_EMIT, 1, s, &emit));
+    return MPL_OK;
+  }
   if (prec == MPL_PREC_BF16) {
     LC(CAT_FPT_LN, launch_layernorm_bf16(x, C, w.n1w, w.n1b, 1e-6f, (__nv_bfloat16*)xn, C, rows, C, s));
     LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkvb, qkv, rows, 3 * C, C, prec, EPI_BIAS, 0, s));
@@ -538,12 +583,14 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
     const int hd = D / m->H;
     const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
     const int64_t rows = Bc * N;
+    if (m->ln_fused)
+      LC(CAT_FPT_LN, launch_ln_prep(w.tok, D, (__nv_bfloat16*)w.fxn, D, w.fstats, m->ln_slots, rows, D, s));
     for (int ix = 0; ix < m->depth; ++ix) {
       const BlockW bw = block_weights(m, P, "blocks." + std::to_string(ix) + ".", m->fpt_tc);
       const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
       for (int r = 0; r < reps; ++r) {
         if (m->fpt_tc)
-          MPL_TRY(block_tc(m, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, w.fxn, w.fqkv, w.fatt, w.fhid, s));
+          MPL_TRY(block_tc(m, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, w.fxn, w.fqkv, w.fatt, w.fhid, w.fstats, s));
         else
           MPL_TRY(block_f32(m, true, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, nullptr, (float*)w.fxn, (float*)w.fqkv, (float*)w.fatt, (float*)w.fhid, s));
       }
@@ -684,6 +731,9 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
     }
     m->fpt_tc = true;
   }
+  // LayerNorm fusion: the residual-emit epilogue works on whole 32-column chunks, launch_ln_prep on float4 rows
+  m->ln_fused = m->fpt_tc && d.precision == MPL_PREC_BF16 && g_ln_fusion != 0 && m->fpt_dim % 32 == 0 && m->fpt_dim <= 32 * 4 * 17;
+  m->ln_slots = m->ln_fused ? gemm_ln_slots(m->fpt_dim) : 0;
   build_tables(m);
   *out = m;
   return MPL_OK;
@@ -820,7 +870,20 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
     const std::string tag = bf ? "bf16:" : "tf32:";
     for (int l = 0; l < m->depth; ++l) {
       const std::string p = "blocks." + std::to_string(l) + ".";
+      if (m->ln_fused) {
+        const int D = m->fpt_dim, Hf = m->fpt_hidden;
+        auto mut = [&](const std::string& name) { return base + m->derived[m->dindex.at(name)].offset; };
+        MPL_TRY(launch_ln_fold(P.f(p + "attn.qkv.weight"), m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr, P.f(p + "norm1.weight"),
+                               P.f(p + "norm1.bias"), reinterpret_cast<__nv_bfloat16*>(mut("lnw:" + p + "attn.qkv")),
+                               reinterpret_cast<float*>(mut("lncs:" + p + "attn.qkv")),
+                               reinterpret_cast<float*>(mut("lnb:" + p + "attn.qkv")), 3 * D, D, s));
+        MPL_TRY(launch_ln_fold(P.f(p + "mlp.fc1.weight"), P.f(p + "mlp.fc1.bias"), P.f(p + "norm2.weight"), P.f(p + "norm2.bias"),
+                               reinterpret_cast<__nv_bfloat16*>(mut("lnw:" + p + "mlp.fc1")),
+                               reinterpret_cast<float*>(mut("lncs:" + p + "mlp.fc1")),
+                               reinterpret_cast<float*>(mut("lnb:" + p + "mlp.fc1")), Hf, D, s));
+      }
       for (const char* wn : {"attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"}) {
+        if (m->ln_fused && (std::string(wn) == "attn.qkv.weight" || std::string(wn) == "mlp.fc1.weight")) continue;
         const float* src = P.f(p + wn);
         const Derived& dd = m->derived[m->dindex.at(tag + p + wn)];
         if (bf) MPL_TRY(launch_to_bf16(src, reinterpret_cast<__nv_bfloat16*>(base + dd.offset), dd.numel, s));
@@ -947,5 +1010,11 @@ int mpl_set_gemm_cta_group(int cta_group) {
   return MPL_OK;
 }
 int mpl_get_gemm_cta_group(void) { return get_gemm_cta_group(); }
+
+int mpl_set_ln_fusion(int enabled) {
+  g_ln_fusion = enabled != 0;
+  return MPL_OK;
+}
+int mpl_get_ln_fusion(void) { return g_ln_fusion; }
 
 }  // extern "C"

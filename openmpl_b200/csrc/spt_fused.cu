@@ -13,8 +13,8 @@
 //     LayerNorm; conversions saturate), weights pre-packed in fragment order, double-buffered via cp.async;
 //   * q|k|v of the 32 sets are staged once in shared memory as fp16 with the channels of each head PAIR interleaved
 //     (word = (head 2p, head 2p+1) at one head-dim), so that the 17x17 softmax of two heads runs in packed half2
-//     arithmetic straight from 16-byte shared-memory loads: one thread per token row, 4 head pairs, two passes
-//     (max, then exp2 / sum / PV) with the scores kept in registers.  The interleave costs nothing: it is a row
+//     arithmetic straight from 16-byte shared-memory loads: one thread per two token rows x two head pairs (every
+//     k / v vector read serves both rows), two passes (max, then exp2 / sum / PV) with the scores kept in registers.  The interleave costs nothing: it is a row
 //     permutation of the QKV weight and a column permutation of the proj weight, applied when the layer is packed;
 //     softmax scale * log2(e) is folded into the q rows the same way;
 //   * the attention output overwrites the (already consumed) q slot of its own row and is the A operand of proj;
@@ -181,12 +181,18 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
     }
   }
 
-  // attention role of this thread: one token row, all 8 heads as 4 head pairs
-  const int arow = threadIdx.x;
-  const int aset0 = (arow / J) * J;  // first row of the row's set
-  const int64_t agr = tile * ROWS + arow;
-  float aconf = 1.0f;
-  if (args.conf != nullptr && arow < ROWS && agr < rows_in_view) aconf = __ldg(args.conf + view_row0 + agr);
+  // attention role of this thread: TWO token rows of one set (rows 2rs, 2rs+1; the 9th slot of a set holds row 16 alone)
+  // x two head pairs (hh, hh + 2): every k / v vector read from shared memory serves both rows.  18 threads per set.
+  const int aset = threadIdx.x / 18, arem = threadIdx.x % 18, ars = arem >> 1, ahh = arem & 1;
+  const int ra = aset * J + 2 * ars;
+  const bool two = ars < 8;
+  const int rb = two ? ra + 1 : ra;
+  const int aset0 = aset * J;  // first row of the set
+  float aconf_a = 1.0f, aconf_b = 1.0f;
+  if (args.conf != nullptr) {
+    if (tile * ROWS + ra < rows_in_view) aconf_a = __ldg(args.conf + view_row0 + tile * ROWS + ra);
+    if (tile * ROWS + rb < rows_in_view) aconf_b = __ldg(args.conf + view_row0 + tile * ROWS + rb);
+  }
 
   for (int layer = 0; layer < args.depth; ++layer) {
     wait_async_all();
@@ -216,43 +222,56 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
       }
       __syncthreads();
       // ---- attention: softmax(q k^T * scale) v over the 17 tokens of the row's set; two heads per half2 lane pair ----
-      if (arow < ROWS) {
-        const float rowscale = weighted ? aconf : 1.0f;
-        uint4* rowp = reinterpret_cast<uint4*>(qkv_w + arow * QPW);
+      {
+        const float sa = weighted ? aconf_a : 1.0f, sb = weighted ? aconf_b : 1.0f;
+        uint4* rowpa = reinterpret_cast<uint4*>(qkv_w + ra * QPW);
+        uint4* rowpb = reinterpret_cast<uint4*>(qkv_w + rb * QPW);
         const uint4* setp = reinterpret_cast<const uint4*>(qkv_w + aset0 * QPW);
         constexpr int RP4 = QPW / 4;  // row pitch in 16-byte units (13)
 #pragma unroll 1
-        for (int p = 0; p < 4; ++p) {
-          const uint4 q = rowp[p];
-          __half2 sc[J];
-          __half2 mx;
+        for (int pp = 0; pp < 2; ++pp) {
+          const int p = ahh + 2 * pp;
+          const uint4 qa = rowpa[p], qb = rowpb[p];
+          __half2 sca[J], scb[J];
+          __half2 mxa, mxb;
 #pragma unroll
           for (int j = 0; j < J; ++j) {
             const uint4 k = setp[j * RP4 + 4 + p];
-            __half2 s = __hmul2(h2(q.x), h2(k.x));
-            s = __hfma2(h2(q.y), h2(k.y), s);
-            s = __hfma2(h2(q.z), h2(k.z), s);
-            s = __hfma2(h2(q.w), h2(k.w), s);
-            sc[j] = s;
-            mx = (j == 0) ? s : __hmax2(mx, s);
+            __half2 s0 = __hmul2(h2(qa.x), h2(k.x)), s1 = __hmul2(h2(qb.x), h2(k.x));
+            s0 = __hfma2(h2(qa.y), h2(k.y), s0); s1 = __hfma2(h2(qb.y), h2(k.y), s1);
+            s0 = __hfma2(h2(qa.z), h2(k.z), s0); s1 = __hfma2(h2(qb.z), h2(k.z), s1);
+            s0 = __hfma2(h2(qa.w), h2(k.w), s0); s1 = __hfma2(h2(qb.w), h2(k.w), s1);
+            sca[j] = s0; scb[j] = s1;
+            mxa = (j == 0) ? s0 : __hmax2(mxa, s0);
+            mxb = (j == 0) ? s1 : __hmax2(mxb, s1);
           }
-          __half2 sum = __float2half2_rn(0.f), o0 = sum, o1 = sum, o2 = sum, o3 = sum;
+          const __half2 z = __float2half2_rn(0.f);
+          __half2 suma = z, a0 = z, a1 = z, a2 = z, a3 = z, sumb = z, b0 = z, b1 = z, b2 = z, b3 = z;
 #pragma unroll
           for (int j = 0; j < J; ++j) {
             const uint4 v = setp[j * RP4 + 8 + p];
-            const __half2 e = ex2_h2(__hsub2(sc[j], mx));
-            sum = __hadd2(sum, e);
-            o0 = __hfma2(e, h2(v.x), o0);
-            o1 = __hfma2(e, h2(v.y), o1);
-            o2 = __hfma2(e, h2(v.z), o2);
-            o3 = __hfma2(e, h2(v.w), o3);
+            const __half2 ea = ex2_h2(__hsub2(sca[j], mxa)), eb = ex2_h2(__hsub2(scb[j], mxb));
+            suma = __hadd2(suma, ea); sumb = __hadd2(sumb, eb);
+            a0 = __hfma2(ea, h2(v.x), a0); b0 = __hfma2(eb, h2(v.x), b0);
+            a1 = __hfma2(ea, h2(v.y), a1); b1 = __hfma2(eb, h2(v.y), b1);
+            a2 = __hfma2(ea, h2(v.z), a2); b2 = __hfma2(eb, h2(v.z), b2);
+            a3 = __hfma2(ea, h2(v.w), a3); b3 = __hfma2(eb, h2(v.w), b3);
           }
-          const float2 sf = __half22float2(sum);
-          const __half2 inv = __floats2half2_rn(__fdividef(rowscale, sf.x), __fdividef(rowscale, sf.y));
-          uint4 o;
-          o.x = u32(__hmul2(o0, inv)); o.y = u32(__hmul2(o1, inv)); o.z = u32(__hmul2(o2, inv)); o.w = u32(__hmul2(o3, inv));
-          // the q slot of this row / head pair is consumed: it now holds the attention output (A operand of proj)
-          rowp[p] = o;
+          // the q slot of a row / head pair is consumed: it now holds the attention output (A operand of proj)
+          {
+            const float2 sf = __half22float2(suma);
+            const __half2 inv = __floats2half2_rn(__fdividef(sa, sf.x), __fdividef(sa, sf.y));
+            uint4 o;
+            o.x = u32(__hmul2(a0, inv)); o.y = u32(__hmul2(a1, inv)); o.z = u32(__hmul2(a2, inv)); o.w = u32(__hmul2(a3, inv));
+            rowpa[p] = o;
+          }
+          if (two) {
+            const float2 sf = __half22float2(sumb);
+            const __half2 inv = __floats2half2_rn(__fdividef(sb, sf.x), __fdividef(sb, sf.y));
+            uint4 o;
+            o.x = u32(__hmul2(b0, inv)); o.y = u32(__hmul2(b1, inv)); o.z = u32(__hmul2(b2, inv)); o.w = u32(__hmul2(b3, inv));
+            rowpb[p] = o;
+          }
         }
       }
       __syncthreads();
