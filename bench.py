@@ -30,7 +30,7 @@ ARCH = dict(num_joints=17, embed_dim_ratio=32, num_heads=8, depth=12, num_views=
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--precision", default=os.environ.get("MPL_BENCH_PRECISION", "bf16"), choices=["bf16", "tf32", "fp32"])
@@ -111,7 +111,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -174,8 +174,8 @@ def run_ours(args):
     batch = synth.make_batch(B, rig, seed=1, start=start)
     host = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("poses", "rays", "centers", "target")}
     devin = {k: v.to(dev) for k, v in host.items()}
-    h2d = sum(host[k].numel() * 4 for k in ("poses", "rays", "centers"))
-    d2h = B * cfg.J * 3 * 4
+    h2d = world * sum(host[k].numel() * 4 for k in ("poses", "rays", "centers"))     # whole job, all ranks
+    d2h = world * B * cfg.J * 3 * 4
 
     def step_device():
         with torch.no_grad():
@@ -250,6 +250,10 @@ def run_ours(args):
                         "fpt_gemm_fc1": 2.0 * M * Hf * D, "fpt_gemm_fc2": 2.0 * M * D * Hf}
     chunks = -(-B // 32768)
     roofline, breakdown = None, {}
+    try:      # per-launch DRAM traffic of the GEMM launches from the committed `ncu --set full` capture (profiles/)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        traffic = {}
     tot_ms = sum(a[0] for a in agg.values())
     for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         breakdown[k] = {"ms_per_step": t / prof_steps, "launches_per_step": n // prof_steps, "share": t / tot_ms if tot_ms else 0}
@@ -261,13 +265,35 @@ def run_ours(args):
         achieved = g_flops / (g_ms / 1000.0) / 1e12
         peak = pk.get("bf16_tflops_sustained", 1400.0) * (0.5 if args.precision == "tf32" else 1.0)
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV/proj/fc1/fc2 of the FPT)", "achieved": achieved,
-                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": traffic.get("gemm_tcgen05_kernel", {}).get("bytes_per_launch"),
+                    "traffic_note": traffic.get("gemm_tcgen05_kernel", {}).get("note"),
+                    "algorithmic_flops_per_launch": g_flops / g_n,
                     "peak_source": f"{pk_src} bf16_tflops_sustained" + (" / 2 (tf32)" if args.precision == "tf32" else ""),
                     "avg_launch_ms": g_ms / g_n, "launches_timed": g_n, "share_of_step": g_ms / tot_ms}
     elif agg:
         k = max(agg, key=lambda c: agg[c][0])
         roofline = {"bound": "tensor", "kernel": k, "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "note": "fp32 CUDA-core path: no tensor-core kernel in this mode"}
+
+    # ---- HBM-bound kernels: algorithmic bytes per launch / measured launch time vs the measured copy bandwidth ----
+    Bc = min(B, 32768)
+    rows_f = Bc * cfg.fpt_tokens
+    esz = 2 if args.precision == "bf16" else 4
+    alg_bytes = {
+        "embed": Bc * cfg.V * (cfg.J * 12 + cfg.J * cfg.d * 4),
+        "token_build": Bc * cfg.V * (cfg.J * cfg.d * 4 + 2 * cfg.J * 12 + 12 + cfg.tok_w * 4),
+        "fpt_attention": rows_f * (3 * D + D) * esz,
+        "fpt_layernorm": rows_f * (D * 4 + D * esz),
+        "head": Bc * (cfg.V * cfg.E * 4 + cfg.J * 12),
+    }
+    memory_kernels = {}
+    for k, nbytes in alg_bytes.items():
+        if k in agg and agg[k][1]:
+            ms_l = agg[k][0] / agg[k][1]
+            gbs = nbytes / (ms_l * 1e-3) / 1e9
+            memory_kernels[k] = {"avg_launch_ms": ms_l, "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": gbs,
+                                 "frac_of_hbm_peak": gbs / pk.get("hbm_gbs", 6650.0)}
 
     # ---- one collective: MPJPE accumulators all-reduced over ranks (NCCL) ----
     acc = metric.MpjpeAccumulator(cfg.J, output_in_meter=True, device=dev)
@@ -298,7 +324,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "whole_path_tflops": value / world * flops / 1e12,
-            "breakdown": breakdown, "cpu_baseline": cpu, "parity": parity,
+            "breakdown": breakdown, "memory_bound_kernels": memory_kernels, "hbm_peak_gbs": pk.get("hbm_gbs"),
+            "cpu_baseline": cpu, "parity": parity,
             "mpjpe_cm": {"absolute": res["mpjpe_abs"], "root_relative": res["mpjpe_rel"], "poses": res["n"],
                          "note": "random-init weights: the value only exercises the accumulator + all-reduce"},
         }

@@ -159,6 +159,14 @@ int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d
 int mpl_build_inputs(const float* pix, const double* calib, int64_t batch, int num_views, int num_joints, float* poses,
                      float* rays, float* centers, mpl_stream_t stream);
 
+/* MHP-style synthetic data on the device (what MHP/utils.py:261-318 + MPL/lib/utils/calib.py:42-77 do to AMASS poses:
+ * place a 3D pose in the room, project it through every calibration).  Pose i of `seed` depends only on (seed, start + i)
+ * (numpy Philox4x64-10 stream, identical to openmpl_b200/synth.py), so any sharding of the global index range gives the
+ * same data.  room [4] fp64 = (min_x, max_x, min_y, max_y); calib as in mpl_build_inputs.
+ *   pix    [B, V, J, 3] fp32 raw pixels (u, v, conf) -- feed to mpl_build_inputs;  target [B, J, 3] fp32, metres. */
+int mpl_synth_project(uint64_t seed, int64_t start, int64_t batch, int num_views, int num_joints, const double* calib,
+                      const double* room, int conf_ones, float* pix, float* target, mpl_stream_t stream);
+
 /* ---- unit-test hooks for the building blocks (used by tests/ only) ------------------------------------------- */
 /* Y[M,N] = epilogue(A[M,K] . W[N,K]^T): the tcgen05 projection kernel in isolation.
  *   dtype: MPL_PREC_BF16 (A, W bf16) or MPL_PREC_TF32 (A, W fp32 pre-rounded to tf32)

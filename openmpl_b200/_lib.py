@@ -27,7 +27,7 @@ EXPORTS = [
     "mpl_packed_bytes", "mpl_pack_weights", "mpl_workspace_bytes", "mpl_chunk_poses", "mpl_set_chunk_poses",
     "mpl_forward", "mpl_last_launch_count", "mpl_mpjpe_accumulate", "mpl_build_inputs", "mpl_test_gemm",
     "mpl_set_gemm_cta_group", "mpl_get_gemm_cta_group", "mpl_set_profile", "mpl_profile_categories",
-    "mpl_profile_category_name", "mpl_profile_collect", "mpl_set_ln_fusion", "mpl_get_ln_fusion",
+    "mpl_profile_category_name", "mpl_profile_collect", "mpl_set_ln_fusion", "mpl_get_ln_fusion", "mpl_synth_project",
 ]
 
 _DESC_FLAGS = [
@@ -111,6 +111,8 @@ def lib():
         L.mpl_profile_collect.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]
         L.mpl_set_gemm_cta_group.argtypes = [c_int]
         L.mpl_get_gemm_cta_group.restype = c_int
+        L.mpl_synth_project.argtypes = [ctypes.c_uint64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                        c_void_p, c_void_p]
         L.mpl_set_ln_fusion.argtypes = [c_int]
         L.mpl_get_ln_fusion.restype = c_int
         if L.mpl_abi_version() != 1:

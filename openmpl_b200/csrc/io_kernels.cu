@@ -211,50 +211,66 @@ __device__ __forceinline__ void head_pool_one(const HeadArgs& a, int64_t b, int 
   }
 }
 
+// One warp per group of PG poses.  Phase 1 (per pose): View_norm -> view-weighted sum -> head LayerNorm in registers
+// (lane = channel % 32), result parked in shared memory as [channel][pose].  Phase 2: lane l owns outputs l and l + 32
+// for all PG poses: it walks the E channels reading the transposed, 64-padded head weight (coalesced, L1-resident,
+// each element read once per PG poses) and the PG pooled values of that channel (one broadcast 16-byte load) -- no
+// cross-lane reduction at all.
+constexpr int HEAD_PG = 4;
+
 template <int NV>
 __global__ void __launch_bounds__(256, 2) head_warp_kernel(const HeadArgs a) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) float hsm[];  // [warps][E][HEAD_PG]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int E = a.E;
+  float* pool = hsm + (size_t)warp * E * HEAD_PG;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t pairs = (a.B + 1) >> 1;
-  for (int64_t pr = warp_global; pr < pairs; pr += warps_total) {
-    const int64_t b0 = 2 * pr;
-    const bool two = b0 + 1 < a.B;
-    float p0[NV], p1[NV];
-    head_pool_one<NV>(a, b0, lane, p0);
-    head_pool_one<NV>(a, two ? b0 + 1 : b0, lane, p1);
-    // Linear E -> out_dim: lane-partial dot products, butterfly reduction; lane o % 32 keeps output o of both poses
-    float k0[3] = {0.f, 0.f, 0.f}, k1[3] = {0.f, 0.f, 0.f};
-    for (int o = 0; o < a.out_dim; ++o) {
-      const float* wr = a.hw + (int64_t)o * E + lane;
-      float acc0 = 0.f, acc1 = 0.f;
+  const int64_t groups = (a.B + HEAD_PG - 1) / HEAD_PG;
+  const float hb0 = (lane < a.out_dim) ? __ldg(a.hb + lane) : 0.f;
+  const float hb1 = (32 + lane < a.out_dim) ? __ldg(a.hb + 32 + lane) : 0.f;
+  for (int64_t gi = warp_global; gi < groups; gi += warps_total) {
+    const int64_t b0 = gi * HEAD_PG;
+#pragma unroll 1
+    for (int pi = 0; pi < HEAD_PG; ++pi) {
+      float p[NV];
+      head_pool_one<NV>(a, min(b0 + pi, a.B - 1), lane, p);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        if (32 * i + lane < E) {
-          const float w = __ldg(wr + 32 * i);
-          acc0 = fmaf(p0[i], w, acc0);
-          acc1 = fmaf(p1[i], w, acc1);
-        }
-      }
-      acc0 = warp_sum(acc0);
-      acc1 = warp_sum(acc1);
-      if ((o & 31) == lane) {
-        k0[0] = (o < 32) ? acc0 : k0[0]; k0[1] = (o >= 32 && o < 64) ? acc0 : k0[1]; k0[2] = (o >= 64) ? acc0 : k0[2];
-        k1[0] = (o < 32) ? acc1 : k1[0]; k1[1] = (o >= 32 && o < 64) ? acc1 : k1[1]; k1[2] = (o >= 64) ? acc1 : k1[2];
+      for (int i = 0; i < NV; ++i)
+        if (32 * i + lane < E) pool[(32 * i + lane) * HEAD_PG + pi] = p[i];
+    }
+    __syncwarp();
+    float acc0[HEAD_PG], acc1[HEAD_PG];
+#pragma unroll
+    for (int pi = 0; pi < HEAD_PG; ++pi) { acc0[pi] = hb0; acc1[pi] = hb1; }
+    const float* wt = a.hwT + lane;
+#pragma unroll 4
+    for (int e = 0; e < E; ++e) {
+      const float w0 = __ldg(wt + e * 64), w1 = __ldg(wt + e * 64 + 32);
+      const float4 pv = *reinterpret_cast<const float4*>(pool + e * HEAD_PG);
+      acc0[0] = fmaf(pv.x, w0, acc0[0]); acc1[0] = fmaf(pv.x, w1, acc1[0]);
+      acc0[1] = fmaf(pv.y, w0, acc0[1]); acc1[1] = fmaf(pv.y, w1, acc1[1]);
+      acc0[2] = fmaf(pv.z, w0, acc0[2]); acc1[2] = fmaf(pv.z, w1, acc1[2]);
+      acc0[3] = fmaf(pv.w, w0, acc0[3]); acc1[3] = fmaf(pv.w, w1, acc1[3]);
+    }
+#pragma unroll
+    for (int pi = 0; pi < HEAD_PG; ++pi) {
+      if (b0 + pi < a.B) {
+        float* out = a.out + (b0 + pi) * a.out_dim;
+        if (lane < a.out_dim) out[lane] = acc0[pi];
+        if (32 + lane < a.out_dim) out[32 + lane] = acc1[pi];
       }
     }
-    float* out0 = a.out + b0 * a.out_dim;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int o = 32 * r + lane;
-      if (o < a.out_dim) {
-        const float hb = __ldg(a.hb + o);
-        out0[o] = k0[r] + hb;
-        if (two) out0[a.out_dim + o] = k1[r] + hb;
-      }
-    }
+    __syncwarp();  // the pooled values are reused by the next group
   }
+}
+
+// head.1.weight [out_dim, E] -> transposed and padded [E, 64] (pack time)
+__global__ void head_transpose_kernel(const float* __restrict__ W, float* __restrict__ WT, int out_dim, int E) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E * 64) return;
+  const int e = idx >> 6, o = idx & 63;
+  WT[idx] = (o < out_dim) ? W[(int64_t)o * E + e] : 0.f;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -296,11 +312,27 @@ int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s) {
 }
 
 int try_launch_head_warp(const HeadArgs& a, cudaStream_t s) {
-  if (a.E > 32 * 17 || a.out_dim > 96 || a.seg_len % 32 != 0) return 1;
+  if (a.E > 32 * 17 || a.out_dim > 64 || a.seg_len % 32 != 0 || a.hwT == nullptr) return 1;
   if (a.B == 0) return MPL_OK;
-  const int64_t blocks = std::min<int64_t>(ceil_div(a.B, 16), (int64_t)kNumSMs * 16);
-  if (a.E > 32 * 9) head_warp_kernel<17><<<(unsigned)blocks, 256, 0, s>>>(a);
-  else head_warp_kernel<9><<<(unsigned)blocks, 256, 0, s>>>(a);
+  const int64_t blocks = std::min<int64_t>(ceil_div(a.B, 8 * HEAD_PG), (int64_t)kNumSMs * 2);
+  const size_t smem = (size_t)8 * a.E * HEAD_PG * sizeof(float);
+  static bool attr_set[64][2] = {};
+  int dev = 0;
+  MPL_CUDA(cudaGetDevice(&dev));
+  const int which = a.E > 32 * 9 ? 1 : 0;
+  if (dev < 0 || dev >= 64 || !attr_set[dev][which]) {
+    if (which) MPL_CUDA(cudaFuncSetAttribute(head_warp_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else MPL_CUDA(cudaFuncSetAttribute(head_warp_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) attr_set[dev][which] = true;
+  }
+  if (which) head_warp_kernel<17><<<(unsigned)blocks, 256, smem, s>>>(a);
+  else head_warp_kernel<9><<<(unsigned)blocks, 256, smem, s>>>(a);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+int launch_head_transpose(const float* W, float* WT, int out_dim, int E, cudaStream_t s) {
+  head_transpose_kernel<<<(unsigned)ceil_div((int64_t)E * 64, 256), 256, 0, s>>>(W, WT, out_dim, E);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

@@ -95,10 +95,12 @@ struct HeadArgs {
   const float* wm_w; const float* wm_b;  // weighted_mean (Conv1d) [V], [1]
   const float* hn_w; const float* hn_b;  // head.0 LayerNorm
   const float* hw;   const float* hb;    // head.1 Linear [out_dim, E]
+  const float* hwT;                      // the same weight transposed and padded to [E, 64] (or null: generic kernel)
   float* out;                            // [B, out_dim]
 };
 int launch_head_fused(const HeadArgs& a, cudaStream_t s);
 int try_launch_head_warp(const HeadArgs& a, cudaStream_t s);
+int launch_head_transpose(const float* W, float* WT, int out_dim, int E, cudaStream_t s);
 
 // ---- pack helpers ---------------------------------------------------------------------------------------------------
 // Linear followed by eval-mode BatchNorm1d folded into one Linear: W' = W * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(var+eps) + beta
@@ -148,5 +150,7 @@ int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* con
                             double* acc, cudaStream_t s);
 int launch_build_inputs(const float* pix, const double* calib, int64_t B, int V, int J, float* poses, float* rays,
                         float* centers, cudaStream_t s);
+int launch_synth_project(uint64_t seed, int64_t start, int64_t B, int V, int J, const double* calib, const double* room,
+                         int conf_ones, float* pix, float* target, cudaStream_t s);
 
 }  // namespace mpl

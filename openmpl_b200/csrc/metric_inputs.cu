@@ -120,6 +120,92 @@ __global__ void __launch_bounds__(256) build_inputs_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// N3: MHP-style synthetic projector.  3D poses from a counter-based generator keyed by (seed, GLOBAL pose index) --
+// any sharding of the index range over ranks / micro-batches yields the same data -- pushed through V calibrations:
+// x_cam = R (X - t), u = f x_cam / z + c (MPL/lib/utils/calib.py:42-77).  Emits raw detector-style pixels (u, v, conf)
+// for mpl_build_inputs and the 3D target.  The generator is numpy's Philox4x64-10 stream, bit for bit (openmpl_b200/
+// synth.py draws the same uniforms on the host), so the device data can be checked against the host generator.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x64_10(uint64_t n, uint64_t key0, uint64_t (&out)[4]) {
+  uint64_t c0 = n, c1 = 0, c2 = 0, c3 = 0, k0 = key0, k1 = 0;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) { k0 += 0x9E3779B97F4A7C15ull; k1 += 0xBB67AE8584CAA73Bull; }
+    const uint64_t hi0 = __umul64hi(0xD2E7470EE14C6C93ull, c0), lo0 = 0xD2E7470EE14C6C93ull * c0;
+    const uint64_t hi1 = __umul64hi(0xCA5A826395121157ull, c2), lo1 = 0xCA5A826395121157ull * c2;
+    const uint64_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct UniformCursor {  // sequential reader of one pose's uniform stream with a one-block cache
+  uint64_t v[4];
+  int64_t blk;
+  uint64_t base, key;
+  __device__ UniformCursor(uint64_t base_, uint64_t key_) : blk(-1), base(base_), key(key_) {}
+  __device__ double get(int i) {
+    const int64_t b = i >> 2;
+    if (b != blk) { philox4x64_10(base + (uint64_t)b + 1ull, key, v); blk = b; }  // numpy increments the counter before generating
+    const int k = i & 3;
+    const uint64_t raw = k == 0 ? v[0] : (k == 1 ? v[1] : (k == 2 ? v[2] : v[3]));
+    return (double)(raw >> 11) * (1.0 / 9007199254740992.0);
+  }
+};
+
+__global__ void __launch_bounds__(128) synth_project_kernel(uint64_t seed, int64_t start, int64_t B, int V, int J,
+                                                            const double* __restrict__ calib, const double* __restrict__ room,
+                                                            int conf_ones, float* __restrict__ pix, float* __restrict__ target) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int n = 3 * (J - 1);
+  const int per_pose = 3 + 2 * n + V * J;
+  const uint64_t blocks = (uint64_t)((per_pose + 3) / 4);
+  const uint64_t base = (uint64_t)(start + b) * blocks;
+  UniformCursor ca(base, seed), cb(base, seed);
+  double root[3];
+  root[0] = room[0] + ca.get(0) * (room[1] - room[0]);
+  root[1] = room[2] + ca.get(1) * (room[3] - room[2]);
+  root[2] = 0.8 + 0.2 * ca.get(2);
+  float* tg = target + b * J * 3;
+  float* px = pix + b * V * J * 3;
+  UniformCursor cc(base, seed);
+  for (int j = 0; j < J; ++j) {
+    double X[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      X[k] = root[k];
+      if (j > 0) {
+        const int i = (j - 1) * 3 + k;
+        const double u1 = fmax(ca.get(3 + i), 1e-12), u2 = cb.get(3 + n + i);
+        X[k] += 0.25 * (sqrt(-2.0 * log(u1)) * cos(2.0 * 3.14159265358979323846 * u2));  // Box-Muller, fixed draw count
+      }
+      tg[j * 3 + k] = (float)X[k];
+    }
+    for (int v = 0; v < V; ++v) {
+      const double* c = calib + v * 18;
+      double xc[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        xc[r] = c[3 * r] * (X[0] - c[9]) + c[3 * r + 1] * (X[1] - c[10]) + c[3 * r + 2] * (X[2] - c[11]);
+      const double u = xc[0] / xc[2] * c[12] + c[14], w = xc[1] / xc[2] * c[13] + c[15];
+      double conf = conf_ones ? 1.0 : 0.3 + 0.7 * cc.get(3 + 2 * n + v * J + j);
+      if (!(xc[2] > 0.0)) conf = 0.0;  // behind the camera: never a detection
+      float* o = px + (v * J + j) * 3;
+      o[0] = (float)u; o[1] = (float)w; o[2] = (float)conf;
+    }
+  }
+}
+
+int launch_synth_project(uint64_t seed, int64_t start, int64_t B, int V, int J, const double* calib, const double* room,
+                         int conf_ones, float* pix, float* target, cudaStream_t s) {
+  if (B == 0) return MPL_OK;
+  synth_project_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(seed, start, B, V, J, calib, room, conf_ones, pix, target);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
 int launch_build_inputs(const float* pix, const double* calib, int64_t B, int V, int J, float* poses, float* rays,
                         float* centers, cudaStream_t s) {
   const int64_t total = B * V * J;

@@ -229,6 +229,7 @@ static void build_tables(MplModel* m) {
   }
   const int maxdim = std::max(m->dim, m->fpt_dim);
   add_derived(m, "zeros", 3 * (int64_t)maxdim, 4);
+  if (!d.linear_weighted_mean && !d.deep_head && !d.head_kadkhod && out_dim <= 64) add_derived(m, "headT", (int64_t)E * 64, 4);
   if (m->spt_fused) {
     const int stacks = m->multi ? V : 1;
     for (int st = 0; st < stacks; ++st) add_derived(m, "sptpack:" + std::to_string(st), (int64_t)m->depth * spt_fused_layer_bytes(), 1);
@@ -609,6 +610,7 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
     ha.wm_w = P.f("weighted_mean.weight"); ha.wm_b = P.f("weighted_mean.bias");
     ha.hn_w = P.f("head.0.weight"); ha.hn_b = P.f("head.0.bias");
     ha.hw = P.f("head.1.weight"); ha.hb = P.f("head.1.bias");
+    ha.hwT = m->dindex.count("headT") ? P.df("headT") : nullptr;
     ha.out = out;
     LC(CAT_HEAD, launch_head_fused(ha, s));
     return MPL_OK;
@@ -850,6 +852,10 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
     const Derived& z = m->derived[m->dindex.at("zeros")];
     MPL_CUDA(cudaMemsetAsync(base + z.offset, 0, (size_t)z.numel * 4, s));
   }
+  if (m->dindex.count("headT")) {
+    const Derived& ht = m->derived[m->dindex.at("headT")];
+    MPL_TRY(launch_head_transpose(P.f("head.1.weight"), reinterpret_cast<float*>(base + ht.offset), 3 * m->J, m->E, s));
+  }
   if (m->spt_fused) {
     const int stacks = m->multi ? m->V : 1;
     const float spt_scale = m->d.qk_scale != 0.f ? m->d.qk_scale : 1.0f / sqrtf((float)(m->dim / m->H));
@@ -994,6 +1000,18 @@ int mpl_build_inputs(const float* pix, const double* calib, int64_t batch, int n
     return MPL_ERR_INVALID_ARGUMENT;
   }
   return launch_build_inputs(pix, calib, batch, num_views, num_joints, poses, rays, centers, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mpl_synth_project(uint64_t seed, int64_t start, int64_t batch, int num_views, int num_joints, const double* calib,
+                      const double* room, int conf_ones, float* pix, float* target, mpl_stream_t stream) {
+  if (batch == 0) return MPL_OK;
+  if (calib == nullptr || room == nullptr || pix == nullptr || target == nullptr || batch < 0 || start < 0 || num_views < 1 ||
+      num_joints < 1) {
+    set_error("mpl_synth_project: bad argument");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  return launch_synth_project(seed, start, batch, num_views, num_joints, calib, room, conf_ones, pix, target,
+                              reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mpl_test_gemm(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype, int epilogue,

@@ -33,3 +33,26 @@ def build_inputs(pix: torch.Tensor, calib) -> tuple:
         _lib.check(_lib.lib().mpl_build_inputs(pix.data_ptr(), calib.data_ptr(), B, V, J, poses.data_ptr(), rays.data_ptr(),
                                                centers.data_ptr(), stream))
     return poses, rays, centers
+
+
+def synth_project(batch: int, rig, seed: int = 0, start: int = 0, conf_mode: str = "uniform", device=None) -> tuple:
+    """N3: MHP-style synthetic poses generated and projected ON THE DEVICE (`mpl_synth_project`).
+
+    Pose i depends only on (seed, start + i) — the same Philox stream as `synth.make_batch` — so ranks / micro-batches
+    can shard the global index range freely.  Returns (pix [B,V,17,3] raw pixels (u, v, conf), target [B,17,3] metres,
+    calib [V,18] fp64 on the device); `build_inputs(pix, calib)` turns the pixels into the model's inputs.
+    """
+    from .synth import NUM_JOINTS
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    V, J = rig.num_views, NUM_JOINTS
+    calib = torch.as_tensor(pack_calibration(rig.R, rig.t, rig.f, rig.c, rig.image_size)).to(device)
+    room = torch.as_tensor(np.asarray(rig.room, dtype=np.float64)).to(device)
+    pix = torch.empty((batch, V, J, 3), dtype=torch.float32, device=device)
+    target = torch.empty((batch, J, 3), dtype=torch.float32, device=device)
+    if conf_mode not in ("uniform", "ones"):
+        raise ValueError(conf_mode)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(_lib.lib().mpl_synth_project(int(seed), int(start), int(batch), V, J, calib.data_ptr(), room.data_ptr(),
+                                                int(conf_mode == "ones"), pix.data_ptr(), target.data_ptr(), stream))
+    return pix, target, calib
