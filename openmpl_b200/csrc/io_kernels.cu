@@ -161,53 +161,69 @@ __global__ void __launch_bounds__(256) token_build_vec_kernel(const TokenArgs a)
 // 128-byte line); View_norm and the head LayerNorm reduce with shuffles only — no shared memory, no block barriers.
 // The E -> 3J Linear reads each weight row once per pose pair (L1-resident, 3J*E*4 = 111 KB) and reduces across lanes.
 // ---------------------------------------------------------------------------------------------------------------------
+// View_norm -> view-weighted sum -> head LayerNorm for TWO poses at once (independent load / reduction chains interleave)
 template <int NV>
-__device__ __forceinline__ void head_pool_one(const HeadArgs& a, int64_t b, int lane, float (&pooled)[NV]) {
+__device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int64_t bb, int lane, float (&pa)[NV], float (&pb)[NV]) {
   const int E = a.E;
   const float invE = 1.0f / (float)E;
   const float wmb = __ldg(a.wm_b);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) pooled[i] = wmb;
+  for (int i = 0; i < NV; ++i) { pa[i] = wmb; pb[i] = wmb; }
   for (int v = 0; v < a.V; ++v) {
-    const float* row = a.tok + (b * a.V + v) * (int64_t)a.tok_w + lane;
-    float x[NV];
-    float s = 0.f;
+    const float* ra = a.tok + (ba * a.V + v) * (int64_t)a.tok_w + lane;
+    const float* rb = a.tok + (bb * a.V + v) * (int64_t)a.tok_w + lane;
+    float xa[NV], xb[NV];
+    float sa = 0.f, sb = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int e0 = 32 * i;  // warp-uniform: the whole 32-channel group sits in one segment (seg_len % 32 == 0)
-      x[i] = (e0 + lane < E) ? row[(e0 / a.seg_len) * a.seg_stride + (e0 % a.seg_len)] : 0.f;
-      s += x[i];
+      const int col = (e0 / a.seg_len) * a.seg_stride + (e0 % a.seg_len);
+      const bool ok = e0 + lane < E;
+      xa[i] = ok ? ra[col] : 0.f;
+      xb[i] = ok ? rb[col] : 0.f;
+      sa += xa[i];
+      sb += xb[i];
     }
-    const float mean = warp_sum(s) * invE;
-    float q = 0.f;
+    const float ma = warp_sum(sa) * invE, mb = warp_sum(sb) * invE;
+    float qa = 0.f, qb = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float t = (32 * i + lane < E) ? x[i] - mean : 0.f;
-      q = fmaf(t, t, q);
+      const bool ok = 32 * i + lane < E;
+      const float ta = ok ? xa[i] - ma : 0.f, tb = ok ? xb[i] - mb : 0.f;
+      qa = fmaf(ta, ta, qa);
+      qb = fmaf(tb, tb, qb);
     }
-    const float rstd = rsqrtf(warp_sum(q) * invE + 1e-6f);
+    const float rsa = rsqrtf(warp_sum(qa) * invE + 1e-6f), rsb = rsqrtf(warp_sum(qb) * invE + 1e-6f);
     const float wv = __ldg(a.wm_w + v);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int e = 32 * i + lane;
-      if (e < E) pooled[i] = fmaf(wv, fmaf((x[i] - mean) * rstd, __ldg(a.vn_w + e), __ldg(a.vn_b + e)), pooled[i]);
+      if (e < E) {
+        const float g = __ldg(a.vn_w + e), bt = __ldg(a.vn_b + e);
+        pa[i] = fmaf(wv, fmaf((xa[i] - ma) * rsa, g, bt), pa[i]);
+        pb[i] = fmaf(wv, fmaf((xb[i] - mb) * rsb, g, bt), pb[i]);
+      }
     }
   }
-  float s = 0.f;
+  float sa = 0.f, sb = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) s += (32 * i + lane < E) ? pooled[i] : 0.f;
-  const float mean = warp_sum(s) * invE;
-  float q = 0.f;
+  for (int i = 0; i < NV; ++i) { const bool ok = 32 * i + lane < E; sa += ok ? pa[i] : 0.f; sb += ok ? pb[i] : 0.f; }
+  const float ma = warp_sum(sa) * invE, mb = warp_sum(sb) * invE;
+  float qa = 0.f, qb = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const float t = (32 * i + lane < E) ? pooled[i] - mean : 0.f;
-    q = fmaf(t, t, q);
+    const bool ok = 32 * i + lane < E;
+    const float ta = ok ? pa[i] - ma : 0.f, tb = ok ? pb[i] - mb : 0.f;
+    qa = fmaf(ta, ta, qa);
+    qb = fmaf(tb, tb, qb);
   }
-  const float rstd = rsqrtf(warp_sum(q) * invE + 1e-5f);  // head LayerNorm: default eps (multiview_mpl.py:284)
+  const float rsa = rsqrtf(warp_sum(qa) * invE + 1e-5f), rsb = rsqrtf(warp_sum(qb) * invE + 1e-5f);  // head LN: eps 1e-5 (multiview_mpl.py:284)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int e = 32 * i + lane;
-    pooled[i] = (e < E) ? fmaf((pooled[i] - mean) * rstd, __ldg(a.hn_w + e), __ldg(a.hn_b + e)) : 0.f;
+    const float g = (e < E) ? __ldg(a.hn_w + e) : 0.f, bt = (e < E) ? __ldg(a.hn_b + e) : 0.f;
+    pa[i] = fmaf((pa[i] - ma) * rsa, g, bt);
+    pb[i] = fmaf((pb[i] - mb) * rsb, g, bt);
   }
 }
 
@@ -232,19 +248,19 @@ __global__ void __launch_bounds__(256, 2) head_warp_kernel(const HeadArgs a) {
   for (int64_t gi = warp_global; gi < groups; gi += warps_total) {
     const int64_t b0 = gi * HEAD_PG;
 #pragma unroll 1
-    for (int pi = 0; pi < HEAD_PG; ++pi) {
-      float p[NV];
-      head_pool_one<NV>(a, min(b0 + pi, a.B - 1), lane, p);
+    for (int pi = 0; pi < HEAD_PG; pi += 2) {
+      float pa[NV], pb[NV];
+      head_pool_two<NV>(a, min(b0 + pi, a.B - 1), min(b0 + pi + 1, a.B - 1), lane, pa, pb);
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (32 * i + lane < E) pool[(32 * i + lane) * HEAD_PG + pi] = p[i];
+        if (32 * i + lane < E) *reinterpret_cast<float2*>(pool + (32 * i + lane) * HEAD_PG + pi) = make_float2(pa[i], pb[i]);
     }
     __syncwarp();
     float acc0[HEAD_PG], acc1[HEAD_PG];
 #pragma unroll
     for (int pi = 0; pi < HEAD_PG; ++pi) { acc0[pi] = hb0; acc1[pi] = hb1; }
     const float* wt = a.hwT + lane;
-#pragma unroll 4
+#pragma unroll 8
     for (int e = 0; e < E; ++e) {
       const float w0 = __ldg(wt + e * 64), w1 = __ldg(wt + e * 64 + 32);
       const float4 pv = *reinterpret_cast<const float4*>(pool + e * HEAD_PG);

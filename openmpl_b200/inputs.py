@@ -24,7 +24,10 @@ def build_inputs(pix: torch.Tensor, calib) -> tuple:
     B, V, J, _ = pix.shape
     device = pix.device
     pix = pix.to(torch.float32).contiguous()
-    calib = torch.as_tensor(np.asarray(calib, dtype=np.float64)).to(device).contiguous()
+    if isinstance(calib, torch.Tensor):
+        calib = calib.to(device=device, dtype=torch.float64).contiguous()
+    else:
+        calib = torch.as_tensor(np.asarray(calib, dtype=np.float64)).to(device).contiguous()
     poses = torch.empty((B, V, J, 3), dtype=torch.float32, device=device)
     rays = torch.empty_like(poses)
     centers = torch.empty((B, V, 1, 3), dtype=torch.float32, device=device)
