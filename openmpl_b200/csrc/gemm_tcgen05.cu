@@ -56,8 +56,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 
 // kind::f16 / kind::tf32 instruction descriptor: fp32 accumulate, K-major A and B
-__device__ __forceinline__ uint32_t make_idesc(int kind, int m, int n) {
-  const uint32_t fmt = (kind == 0) ? 1u : 2u;  // BF16 : TF32
+__device__ __forceinline__ uint32_t make_idesc(int kind, int m, int n, bool fp16 = false) {
+  const uint32_t fmt = (kind == 0) ? (fp16 ? 0u : 1u) : 2u;  // kind::f16: F16 = 0, BF16 = 1; kind::tf32: TF32 = 2
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
@@ -83,7 +83,7 @@ struct GemmLn {
   float* y_raw;             // [M, N] the fp32 residual (read in the epilogue)  (EPI 6)
   int slots_in, slots_out;
   float inv_k, eps;         // 1 / LayerNorm width (= K of the consumer), LayerNorm eps
-  int flags;                // bit 0: L2-prefetch the residual tile from the producer warp
+  int flags;                // bit 1: A and W are fp16 (not bf16); bit 2: the 16-bit output is fp16 and GELU runs in packed half2
 };
 
 // accumulator chunk (32 columns of this lane's row) -> + bias (-> GELU) as fp32; LNF: LayerNorm row statistics applied
@@ -133,6 +133,35 @@ __device__ __forceinline__ void stage_row_bf16(uint32_t box, int lane, int j0, c
     __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
     ptx::st_shared_v4(rowaddr + (((j0 + j) ^ (lane & 7)) << 4), *reinterpret_cast<uint32_t*>(&p0),
                       *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+  }
+}
+
+// fp16 output path (fc1 -> fc2 hidden activations kept in fp16: 3 more mantissa bits than bf16, and the GELU runs as packed
+// half2 arithmetic): 32 fp32 values -> half2 pairs (saturating) -> optional tanh-fit erf-GELU -> chunks j0 .. j0+3 of the row
+__device__ __forceinline__ uint32_t gelu_tanh_fit_h2(uint32_t xu) {
+  const __half2 x = *reinterpret_cast<const __half2*>(&xu);
+  const __half2 x2 = __hmul2(x, x);
+  const __half2 t = __hfma2(x2, __float2half2_rn(0.03470089f), __float2half2_rn(0.80015708f));
+  const __half2 u = __hmul2(x, t);
+  uint32_t thu, uu = *reinterpret_cast<const uint32_t*>(&u);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(thu) : "r"(uu));
+  const __half2 th = *reinterpret_cast<const __half2*>(&thu);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 r = __hfma2(hx, th, hx);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <bool GELU>
+__device__ __forceinline__ void stage_row_f16(uint32_t box, int lane, int j0, const float (&f)[32]) {
+  const uint32_t rowaddr = box + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(p[i]) : "f"(f[8 * j + 2 * i + 1]), "f"(f[8 * j + 2 * i]));
+      if (GELU) p[i] = gelu_tanh_fit_h2(p[i]);
+    }
+    ptx::st_shared_v4(rowaddr + (((j0 + j) ^ (lane & 7)) << 4), p[0], p[1], p[2], p[3]);
   }
 }
 
@@ -244,7 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int n_blk = (int)(tile % n_tiles);
         const int n_size = min(bn, N - n_blk * bn);
-        const uint32_t idesc = make_idesc(KIND, BM * CG, n_size);
+        const uint32_t idesc = make_idesc(KIND, BM * CG, n_size, (ln.flags & 2) != 0);
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -394,12 +423,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (OUT_BF16) {
           // one 64-column bf16 box per step
           float fa[32], fb[32];
-          epilogue_math<KIND, EPI>(va, bias, ncol0 + c, N, fa, ln.colsum, mu, rstd);
-          epilogue_math<KIND, EPI>(vb, bias, ncol0 + c + 32, N, fb, ln.colsum, mu, rstd);
+          constexpr bool GELU = (EPI == 1 || EPI == 5);
+          const bool f16_out = KIND == 0 && (ln.flags & 4);
+          if (GELU && f16_out) {  // activation deferred to the packed-half2 stage
+            epilogue_math<KIND, EPI == 5 ? 4 : 0>(va, bias, ncol0 + c, N, fa, ln.colsum, mu, rstd);
+            epilogue_math<KIND, EPI == 5 ? 4 : 0>(vb, bias, ncol0 + c + 32, N, fb, ln.colsum, mu, rstd);
+          } else {
+            epilogue_math<KIND, EPI>(va, bias, ncol0 + c, N, fa, ln.colsum, mu, rstd);
+            epilogue_math<KIND, EPI>(vb, bias, ncol0 + c + 32, N, fb, ln.colsum, mu, rstd);
+          }
           if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has finished reading the box
           __syncwarp();
-          stage_row_bf16(box, lane, 0, fa);
-          stage_row_bf16(box, lane, 4, fb);
+          if (f16_out) {
+            stage_row_f16<GELU>(box, lane, 0, fa);
+            stage_row_f16<GELU>(box, lane, 4, fb);
+          } else {
+            stage_row_bf16(box, lane, 0, fa);
+            stage_row_bf16(box, lane, 4, fb);
+          }
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -586,8 +627,7 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
     ln.slots_out = gemm_ln_slots(N);
     ln.inv_k = 1.0f / (float)K;
     ln.eps = lnargs->eps;
-    static const int dbg_flags = getenv("MPL_GEMM_LN_FLAGS") ? atoi(getenv("MPL_GEMM_LN_FLAGS")) : 0;
-    ln.flags = dbg_flags;
+    ln.flags = (lnargs->ab_fp16 ? 2 : 0) | (lnargs->out_fp16 ? 4 : 0);
     if (epilogue == EPI_RESIDUAL_EMIT && (N % 32 != 0 || ln.stats_out == nullptr || ln.xb == nullptr)) {
       set_error("launch_gemm_tcgen05: residual-emit epilogue needs N %% 32 == 0, a statistics buffer and a bf16 copy buffer");
       return MPL_ERR_INVALID_ARGUMENT;

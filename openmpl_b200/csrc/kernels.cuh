@@ -107,6 +107,7 @@ int launch_head_transpose(const float* W, float* WT, int out_dim, int E, cudaStr
 int launch_fold_bn(const float* W, const float* b, const float* g, const float* beta, const float* mean, const float* var,
                    float eps, float* Wf, float* bf, int N, int K, cudaStream_t s);
 int launch_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);
+int launch_to_f16(const float* src, void* dst, int64_t n, cudaStream_t s);
 int launch_to_tf32(const float* src, float* dst, int64_t n, cudaStream_t s);
 
 // ---- tcgen05 projection GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
@@ -124,6 +125,8 @@ struct GemmLnArgs {
   void* xb;
   int slots_in;
   float eps;
+  int ab_fp16;   // A and W hold fp16 (not bf16) values
+  int out_fp16;  // EPI_LN_BIAS(_GELU): write fp16 (not bf16); the GELU then runs in packed half2 arithmetic
 };
 int gemm_ln_slots(int N);
 // A [M,K] row-major (lda = K), W [N,K] row-major, both bf16 (dtype MPL_PREC_BF16) or tf32-rounded fp32 (MPL_PREC_TF32).

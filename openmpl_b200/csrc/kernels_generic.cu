@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <type_traits>
 
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace mpl {
@@ -884,6 +886,16 @@ __global__ void to_bf16_kernel(const float* src, __nv_bfloat16* dst, int64_t n) 
 int launch_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s) {
   if (n == 0) return MPL_OK;
   to_bf16_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, dst, n);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+__global__ void to_f16_kernel(const float* src, __half* dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+int launch_to_f16(const float* src, void* dst, int64_t n, cudaStream_t s) {
+  if (n == 0) return MPL_OK;
+  to_f16_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

@@ -447,7 +447,9 @@ static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_
     LC(CAT_FPT_ATTN, launch_attention_bf16((const __nv_bfloat16*)qkv, (__nv_bfloat16*)att, sets, N, m->H, hd, scale, s));
     LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_RESIDUAL_EMIT, 1, s, &emit));
     app.colsum = w.fc1_cs;
+    app.out_fp16 = 1;   // hidden activations in fp16 (GELU in packed half2), fc2 runs kind::f16 on fp16 operands
     LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1_bf, hid, rows, hidden, C, prec, EPI_LN_BIAS_GELU, 0, s, &app));
+    emit.ab_fp16 = 1;
     LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_RESIDUAL_EMIT, 1, s, &emit));
     return MPL_OK;
   }
@@ -892,7 +894,8 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
         if (m->ln_fused && (std::string(wn) == "attn.qkv.weight" || std::string(wn) == "mlp.fc1.weight")) continue;
         const float* src = P.f(p + wn);
         const Derived& dd = m->derived[m->dindex.at(tag + p + wn)];
-        if (bf) MPL_TRY(launch_to_bf16(src, reinterpret_cast<__nv_bfloat16*>(base + dd.offset), dd.numel, s));
+        if (bf && m->ln_fused && std::string(wn) == "mlp.fc2.weight") MPL_TRY(launch_to_f16(src, base + dd.offset, dd.numel, s));
+        else if (bf) MPL_TRY(launch_to_bf16(src, reinterpret_cast<__nv_bfloat16*>(base + dd.offset), dd.numel, s));
         else MPL_TRY(launch_to_tf32(src, reinterpret_cast<float*>(base + dd.offset), dd.numel, s));
       }
     }
