@@ -434,10 +434,12 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
   a.conf = conf;
   a.B = B;
   a.depth = depth;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: function attributes live in the device's context (DataParallel replicas)
+  int dev = 0;
+  MPL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     MPL_CUDA(cudaFuncSetAttribute(spt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   dim3 grid((unsigned)ceil_div(B, SETS), (unsigned)V);
   spt_fused_kernel<<<grid, THREADS, SMEM_TOTAL, s>>>(a);

@@ -34,18 +34,19 @@ class _Node(nn.Module):
 
 
 class _Handle:
-    """Owns one `MplModel*`; shared by reference between DataParallel replicas, never copied."""
+    """Owns the `MplModel*` handles of a module, one per device (a handle is used by one thread at a time, and
+    DataParallel runs one replica thread per GPU); shared by reference between replicas, never copied."""
 
     def __init__(self):
-        self.ptr = None
+        self.ptrs = {}
 
     def __deepcopy__(self, memo):
-        return _Handle()          # a deep-copied module lazily creates its own handle
+        return _Handle()          # a deep-copied module lazily creates its own handles
 
     def __del__(self):
         try:
-            if self.ptr is not None:
-                _lib.lib().mpl_destroy(self.ptr)
+            for p in self.ptrs.values():
+                _lib.lib().mpl_destroy(p)
         except Exception:
             pass
 
@@ -111,14 +112,18 @@ class MultiView_MPL(nn.Module):
         for name, (shape, kind, fan_in) in self._spec.items():
             _register(self, name, _default_init(shape, kind, fan_in), kind in BUFFER_KINDS)
         self._names = list(self._spec.keys())
-        self._h = _Handle()          # MplModel*, created at the first forward (the reference also fails there, Q6)
+        self._h = _Handle()          # MplModel* per device, created at the first forward (the reference also fails there, Q6)
         self._dev = {}               # device index -> dict(packed, stamp, workspace)
         self._lock = threading.Lock()
+        self._origin = [self]        # survives DataParallel's shallow replica copies: the module that owns the parameters
+        self._chunk = None
         self.last_launches = 0
 
     # ---- handle / packing ------------------------------------------------------------------------------------------
-    def _get_handle(self):
-        if self._h.ptr is None:
+    def _get_handle(self, index=None):
+        if index is None:
+            index = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        if index not in self._h.ptrs:
             L = _lib.lib()
             desc = _lib.make_desc(self.cfg.kw, self.precision)
             h = ctypes.c_void_p()
@@ -133,23 +138,28 @@ class MultiView_MPL(nn.Module):
                     raise RuntimeError(f"parameter table mismatch for {lib_names[-1]}")
             if lib_names != self._names:
                 raise RuntimeError("parameter table of libmpl_b200.so differs from the module's state_dict")
-            self._h.ptr = h
-        return self._h.ptr
+            if self._chunk is not None:
+                _lib.check(L.mpl_set_chunk_poses(h, int(self._chunk)))
+            self._h.ptrs[index] = h
+        return self._h.ptrs[index]
 
     def _tensor(self, name):
         mod = self
         parts = name.split(".")
         for p in parts[:-1]:
             mod = mod._modules[p]
-        t = mod._parameters.get(parts[-1])
-        return t if t is not None else mod._buffers[parts[-1]]
+        # getattr, not _parameters: in a DataParallel replica the parameters are plain tensor attributes
+        return getattr(mod, parts[-1])
 
     def _state(self, device):
         """Per-device packed weights, repacked whenever a parameter's storage or version changes."""
         L = _lib.lib()
-        h = self._get_handle()
+        h = self._get_handle(device.index)
         tensors = [self._tensor(n) for n in self._names]
-        stamp = tuple((t.data_ptr(), t._version) for t in tensors)
+        # The stamp is taken on the parameters of the ORIGINAL module: DataParallel re-broadcasts fresh copies to the
+        # replicas on every call, which must not trigger a repack while the master's weights are unchanged.
+        origin = self._origin[0]
+        stamp = tuple((t.data_ptr(), t._version) for t in (origin._tensor(n) for n in self._names))
         with self._lock:
             st = self._dev.get(device.index)
             if st is None or st["stamp"] != stamp:
@@ -168,7 +178,9 @@ class MultiView_MPL(nn.Module):
             return st
 
     def set_chunk_poses(self, chunk: int):
-        _lib.check(_lib.lib().mpl_set_chunk_poses(self._get_handle(), int(chunk)))
+        self._chunk = int(chunk)
+        for h in self._h.ptrs.values():
+            _lib.check(_lib.lib().mpl_set_chunk_poses(h, int(chunk)))
 
     def set_profile(self, enabled: bool):
         """Bracket every kernel launch of the next forwards with CUDA events (see `profile()`)."""
@@ -196,6 +208,8 @@ class MultiView_MPL(nn.Module):
         for k, v in self.__dict__.items():
             if k == "_dev":
                 new.__dict__[k] = {}
+            elif k == "_origin":
+                new.__dict__[k] = [new]
             elif k == "_lock":
                 new.__dict__[k] = threading.Lock()
             else:
@@ -245,7 +259,7 @@ class MultiView_MPL(nn.Module):
         L = _lib.lib()
         with torch.cuda.device(device):
             st = self._state(device)
-            h = self._h.ptr
+            h = self._get_handle(device.index)
             out = torch.empty((B, J, 3), dtype=torch.float32, device=device)
             aux = [torch.empty_like(out), torch.empty_like(out)] if self.cfg.kw["head_kadkhod"] else [None, None]
             need = L.mpl_workspace_bytes(h, B)

@@ -176,3 +176,24 @@ def test_layernorm_fusion_on_and_off_agree_with_the_reference(name):
 def test_native_library_is_what_ran():
     maps = open("/proc/self/maps").read()
     assert "libmpl_b200.so" in maps
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_data_parallel_replicas_like_the_reference_runner(precision):
+    """The reference's only multi-GPU mechanism: `torch.nn.DataParallel(model, device_ids=gpus).cuda()` fed lists of
+    CPU tensors (MPL/run/valid_mpl.py:177-178, core/function_mpl.py:344-350).  Replicas share the C handle and keep
+    per-device packed weights; the gathered output must equal the single-GPU output."""
+    case = CASES["cmu0_v2_d2"]
+    cfg, weights, _ = make_inputs(case)
+    batch = synth.make_batch(64, synth.make_rig(cfg.V, "cmu"), seed=3)
+    m = build_module(case["kw"], weights, precision)
+    single = run_module(m, batch)[0]
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1]).cuda()
+    V = cfg.V
+    args = [[torch.from_numpy(np.ascontiguousarray(batch[k][:, v])) for v in range(V)] for k in ("poses", "rays", "centers")]
+    with torch.no_grad():
+        out = dp(args[0], rays=args[1], centers=args[2])
+    torch.cuda.synchronize()
+    assert out.shape == (64, 17, 3) and out.device.index == 0
+    np.testing.assert_array_equal(out.cpu().numpy(), single)
