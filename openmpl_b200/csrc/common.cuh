@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 
@@ -81,6 +82,19 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
   return fmaf(hx, th, hx);
 }
 
+// the same fit on a packed pair of fp16 values (5 packed FMA-pipe instructions + the MUFU pair)
+__device__ __forceinline__ uint32_t gelu_tanh_fit_h2(uint32_t xu) {
+  const __half2 x = *reinterpret_cast<const __half2*>(&xu);
+  const __half2 x2 = __hmul2(x, x);
+  const __half2 t = __hfma2(x2, __float2half2_rn(0.03470089f), __float2half2_rn(0.80015708f));
+  const __half2 u = __hmul2(x, t);
+  uint32_t thu, uu = *reinterpret_cast<const uint32_t*>(&u);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(thu) : "r"(uu));
+  const __half2 th = *reinterpret_cast<const __half2*>(&thu);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 r = __hfma2(hx, th, hx);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == ACT_GELU) return gelu_erf(x);
   if (act == ACT_RELU) return fmaxf(x, 0.0f);

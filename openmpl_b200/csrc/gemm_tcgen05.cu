@@ -138,18 +138,6 @@ __device__ __forceinline__ void stage_row_bf16(uint32_t box, int lane, int j0, c
 
 // fp16 output path (fc1 -> fc2 hidden activations kept in fp16: 3 more mantissa bits than bf16, and the GELU runs as packed
 // half2 arithmetic): 32 fp32 values -> half2 pairs (saturating) -> optional tanh-fit erf-GELU -> chunks j0 .. j0+3 of the row
-__device__ __forceinline__ uint32_t gelu_tanh_fit_h2(uint32_t xu) {
-  const __half2 x = *reinterpret_cast<const __half2*>(&xu);
-  const __half2 x2 = __hmul2(x, x);
-  const __half2 t = __hfma2(x2, __float2half2_rn(0.03470089f), __float2half2_rn(0.80015708f));
-  const __half2 u = __hmul2(x, t);
-  uint32_t thu, uu = *reinterpret_cast<const uint32_t*>(&u);
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(thu) : "r"(uu));
-  const __half2 th = *reinterpret_cast<const __half2*>(&thu);
-  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
-  const __half2 r = __hfma2(hx, th, hx);
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
 template <bool GELU>
 __device__ __forceinline__ void stage_row_f16(uint32_t box, int lane, int j0, const float (&f)[32]) {
   const uint32_t rowaddr = box + lane * 128;

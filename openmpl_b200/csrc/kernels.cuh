@@ -144,9 +144,16 @@ int launch_spt_pack_layer(const float* n1w, const float* n1b, const float* qkvw,
                           const float* fc2w, const float* fc2b, float scale, void* dst, cudaStream_t s);
 // x_in / x_out [V, B, 17, 32] fp32; wpack_per_view[v] -> [depth] fragment-packed layers (the softmax scale is folded
 // into them by launch_spt_pack_layer); applies every block application of the stack (confidence-weighted pass when
-// conf != null, last block twice) and Spatial_norm
+// conf_weighted, last block twice) and Spatial_norm.  x_in == null: the K1 joint embedding is computed in the kernel's
+// prologue from io->embed (spatial_pos_mode 0 / 1 only); x_out == null: the FPT tokens are written by its epilogue from
+// io->token (tok, layouts, ray / confidence / position embeddings) -- no embed / token-build launch, no xs / xn round trip.
+struct SptIo {
+  EmbedArgs embed;
+  TokenArgs token;
+};
 int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_per_view, int V, int64_t B, int depth,
-                     const float* sn_w, const float* sn_b, const float* conf, cudaStream_t s);
+                     const float* sn_w, const float* sn_b, const float* conf, int conf_weighted, const SptIo* io,
+                     cudaStream_t s);
 
 // ---- metric + input builder -----------------------------------------------------------------------------------------
 int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t B, int J, float unit_scale,

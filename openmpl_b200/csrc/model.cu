@@ -514,37 +514,7 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   ea.V = V; ea.J = J; ea.d = dim;
   ea.x = w.xs;
   ea.conf = w.conf;
-  LC(CAT_EMBED, launch_embed(ea, s));
-  // ---- SPT blocks (multiview_mpl.py:400-410): conf-weighted pass, last block twice; then Spatial_norm (:412) ----
-  const int64_t Rs = (int64_t)V * Bc * J;
-  if (m->spt_fused) {
-    const void* wp[kMaxViews];
-    for (int v = 0; v < V; ++v) wp[v] = P.dv("sptpack:" + std::to_string(m->multi ? v : 0));
-    LC(CAT_SPT_FUSED, launch_spt_fused(w.xs, w.xn, wp, V, Bc, m->depth, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"),
-                                       w.conf, s));
-  } else {
-    if (!d.no_transformer_spt && m->depth > 0) {
-      const int hd = dim / m->H;
-      const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
-      const int stacks = m->multi ? V : 1;
-      const int64_t rows_per_stack = (m->multi ? 1 : V) * Bc * J;
-      for (int st = 0; st < stacks; ++st) {
-        float* x = w.xs + (int64_t)st * rows_per_stack * dim;
-        const float* cf = w.conf ? w.conf + (int64_t)st * rows_per_stack : nullptr;
-        const std::string vp = m->multi ? std::to_string(st) + "." : std::string("");
-        for (int ix = 0; ix < m->depth; ++ix) {
-          const BlockW bw = block_weights(m, P, "Spatial_blocks." + vp + std::to_string(ix) + ".", false);
-          const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
-          if (cf != nullptr)
-            MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, cf, w.xn, w.qkv, w.att, w.hid, s));
-          for (int r = 0; r < reps; ++r)
-            MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, nullptr, w.xn, w.qkv, w.att, w.hid, s));
-        }
-      }
-    }
-    LC(CAT_TOKEN, launch_layernorm(w.xs, dim, dim, dim, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"), 1e-6f, w.xn, dim, Rs, dim, s));
-  }
-  // ---- token build (:463-499) ----
+  // ---- token build arguments (:463-499); the launch itself follows the SPT unless the SPT kernel fuses it ----
   TokenArgs ta{};
   ta.xn = w.xn;
   for (int v = 0; v < V; ++v) {
@@ -579,7 +549,42 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   ta.ray_layout = m->ray_layout;
   ta.V = V; ta.J = J; ta.d = dim; ta.tok_w = m->tok_w;
   ta.tok = w.tok;
-  LC(CAT_TOKEN, launch_token_build(ta, s));
+  // the single-kernel SPT computes the embedding in its prologue and writes the FPT tokens from its epilogue
+  const bool fuse_embed = m->spt_fused && ea.spatial_pos_mode != 2;
+  const bool fuse_token = m->spt_fused;
+  if (!fuse_embed) LC(CAT_EMBED, launch_embed(ea, s));
+  // ---- SPT blocks (multiview_mpl.py:400-410): conf-weighted pass, last block twice; then Spatial_norm (:412) ----
+  const int64_t Rs = (int64_t)V * Bc * J;
+  if (m->spt_fused) {
+    const void* wp[kMaxViews];
+    for (int v = 0; v < V; ++v) wp[v] = P.dv("sptpack:" + std::to_string(m->multi ? v : 0));
+    SptIo io{ea, ta};
+    LC(CAT_SPT_FUSED, launch_spt_fused(fuse_embed ? nullptr : w.xs, fuse_token ? nullptr : w.xn, wp, V, Bc, m->depth,
+                                       P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"), fuse_embed ? nullptr : w.conf,
+                                       d.confidence_as_attention_uncertainty_weight ? 1 : 0, &io, s));
+  } else {
+    if (!d.no_transformer_spt && m->depth > 0) {
+      const int hd = dim / m->H;
+      const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
+      const int stacks = m->multi ? V : 1;
+      const int64_t rows_per_stack = (m->multi ? 1 : V) * Bc * J;
+      for (int st = 0; st < stacks; ++st) {
+        float* x = w.xs + (int64_t)st * rows_per_stack * dim;
+        const float* cf = w.conf ? w.conf + (int64_t)st * rows_per_stack : nullptr;
+        const std::string vp = m->multi ? std::to_string(st) + "." : std::string("");
+        for (int ix = 0; ix < m->depth; ++ix) {
+          const BlockW bw = block_weights(m, P, "Spatial_blocks." + vp + std::to_string(ix) + ".", false);
+          const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
+          if (cf != nullptr)
+            MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, cf, w.xn, w.qkv, w.att, w.hid, s));
+          for (int r = 0; r < reps; ++r)
+            MPL_TRY(block_f32(m, false, bw, x, rows_per_stack, rows_per_stack / J, J, dim, m->spt_hidden, scale, nullptr, w.xn, w.qkv, w.att, w.hid, s));
+        }
+      }
+    }
+    LC(CAT_TOKEN, launch_layernorm(w.xs, dim, dim, dim, P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"), 1e-6f, w.xn, dim, Rs, dim, s));
+  }
+  if (!fuse_token) LC(CAT_TOKEN, launch_token_build(ta, s));
   // ---- FPT blocks (multiview_mpl.py:416-423) ----
   if (!d.no_transformer_fpt && m->depth > 0) {
     const int D = m->fpt_dim, N = m->fpt_tokens;

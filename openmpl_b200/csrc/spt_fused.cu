@@ -119,15 +119,24 @@ __device__ __forceinline__ void gemm_tile2(float (&c0)[4], float (&c1)[4], const
 }
 
 struct SptArgs {
-  const float* x_in;                  // [V, B, J, 32] joint embeddings
-  float* x_out;                       // [V, B, J, 32] after the stack and Spatial_norm
+  const float* x_in;                  // [V, B, J, 32] joint embeddings (null: the embedding is computed here, io.embed)
+  float* x_out;                       // [V, B, J, 32] after the stack and Spatial_norm (null: tokens are written here, io.token)
   const uint32_t* wpack[kMaxViews];   // per view stack: [depth][LAYER_WORDS]
   const float* sn_w;
   const float* sn_b;
-  const float* conf;                  // [V, B, J] or null: confidence_as_attention_uncertainty_weight
+  const float* conf;                  // [V, B, J] or null: confidence_as_attention_uncertainty_weight (unfused embed only)
   int64_t B;
   int depth;
+  int conf_weighted;                  // the confidence-weighted extra pass per block is live
+  SptIo io;                           // fused K1 embedding in front, fused FPT token build behind
 };
+
+// confidence of token row `gr` of `view` straight from the pose record (x, y, conf)
+__device__ __forceinline__ float pose_conf(const SptArgs& a, int view, int64_t gr) {
+  const int64_t b = gr / J;
+  const int j = (int)(gr - b * J);
+  return __ldg(a.io.embed.poses[view] + b * a.io.embed.pose_stride + j * 3 + 2);
+}
 
 __device__ __forceinline__ void load_layer_async(uint32_t* dst, const uint32_t* src) {
   constexpr int CHUNKS = LAYER_WORDS * 4 / 16;  // 1112 x 16 bytes
@@ -172,12 +181,48 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
     const int64_t gr0 = tile * ROWS + lr[mt], gr1 = gr0 + 8;
     ok[mt][0] = lr[mt] < ROWS && gr0 < rows_in_view;
     ok[mt][1] = lr[mt] + 8 < ROWS && gr1 < rows_in_view;
+    if (args.x_in != nullptr) {
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
-      if (ok[mt][0]) v0 = *reinterpret_cast<const float2*>(args.x_in + (view_row0 + gr0) * D + 8 * nt + 2 * t);
-      if (ok[mt][1]) v1 = *reinterpret_cast<const float2*>(args.x_in + (view_row0 + gr1) * D + 8 * nt + 2 * t);
-      x[mt][nt][0] = v0.x; x[mt][nt][1] = v0.y; x[mt][nt][2] = v1.x; x[mt][nt][3] = v1.y;
+      for (int nt = 0; nt < 4; ++nt) {
+        float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+        if (ok[mt][0]) v0 = *reinterpret_cast<const float2*>(args.x_in + (view_row0 + gr0) * D + 8 * nt + 2 * t);
+        if (ok[mt][1]) v1 = *reinterpret_cast<const float2*>(args.x_in + (view_row0 + gr1) * D + 8 * nt + 2 * t);
+        x[mt][nt][0] = v0.x; x[mt][nt][1] = v0.y; x[mt][nt][2] = v1.x; x[mt][nt][3] = v1.y;
+      }
+    } else {
+      // K1 joint embedding fused in front (multiview_mpl.py:349-398): x = W_e (x, y[, conf]) + b_e [+/* conf embedding]
+      // + Spatial_pos_embed [+ learnable 3D position], computed straight into the C-fragment layout
+      const EmbedArgs& e = args.io.embed;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t gr = h ? gr1 : gr0;
+        float px = 0.f, py = 0.f, pc = 0.f;
+        int j = 0;
+        if (ok[mt][h]) {
+          const int64_t b = gr / J;
+          j = (int)(gr - b * J);
+          const float* pp = e.poses[view] + b * e.pose_stride + j * 3;
+          px = __ldg(pp); py = __ldg(pp + 1); pc = __ldg(pp + 2);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c = 8 * nt + 2 * t + i;
+            const float* W = e.We[view] + c * e.in_ch;
+            float val = fmaf(__ldg(W + 1), py, fmaf(__ldg(W), px, __ldg(e.be[view] + c)));
+            if (e.in_ch == 3) val = fmaf(__ldg(W + 2), pc, val);
+            if (e.add_conf || e.mult_conf) {
+              const float ce = fmaf(__ldg(e.Wc[view] + c), pc, __ldg(e.bc[view] + c));
+              if (e.add_conf) val += ce;
+              if (e.mult_conf) val *= ce;
+            }
+            val += __ldg(e.Ps[view] + j * D + c);
+            if (e.spatial_pos_mode == 1) val += __ldg(e.pos3d + j * e.pos3d_ld + c);
+            x[mt][nt][2 * h + i] = ok[mt][h] ? val : 0.f;
+          }
+        }
+      }
     }
   }
 
@@ -189,9 +234,10 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
   const int rb = two ? ra + 1 : ra;
   const int aset0 = aset * J;  // first row of the set
   float aconf_a = 1.0f, aconf_b = 1.0f;
-  if (args.conf != nullptr) {
-    if (tile * ROWS + ra < rows_in_view) aconf_a = __ldg(args.conf + view_row0 + tile * ROWS + ra);
-    if (tile * ROWS + rb < rows_in_view) aconf_b = __ldg(args.conf + view_row0 + tile * ROWS + rb);
+  if (args.conf_weighted) {
+    const int64_t ga = tile * ROWS + ra, gb = tile * ROWS + rb;
+    if (ga < rows_in_view) aconf_a = args.conf != nullptr ? __ldg(args.conf + view_row0 + ga) : pose_conf(args, view, ga);
+    if (gb < rows_in_view) aconf_b = args.conf != nullptr ? __ldg(args.conf + view_row0 + gb) : pose_conf(args, view, gb);
   }
 
   for (int layer = 0; layer < args.depth; ++layer) {
@@ -202,9 +248,9 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
     if (layer + 1 < args.depth) load_layer_async(wbuf + ((layer + 1) & 1) * LAYER_WORDS, wsrc + (size_t)(layer + 1) * LAYER_WORDS);
 
     // block applications of this layer (multiview_mpl.py:405-410): [confidence-weighted], [last layer: once more], plain
-    const int n_apps = (args.conf != nullptr ? 1 : 0) + (layer == args.depth - 1 ? 2 : 1);
+    const int n_apps = (args.conf_weighted ? 1 : 0) + (layer == args.depth - 1 ? 2 : 1);
     for (int app = 0; app < n_apps; ++app) {
-      const bool weighted = (args.conf != nullptr) && app == 0;
+      const bool weighted = args.conf_weighted && app == 0;
       // ---- LN1 + QKV -> fp16 staging (q pre-scaled by scale * log2 e through the packed weights) ----
       {
         uint32_t a0[2][4], a1[2][4];
@@ -307,10 +353,10 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
         for (int nt = 0; nt < 8; ++nt) {
           float c0[4], c1[4];
           gemm_tile2<2>(c0, c1, a0, a1, w + OFF_FC1, nt, wv + F_FC1B, lane, t);
-          h0[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(gelu_tanh_fit(c0[0]), gelu_tanh_fit(c0[1]));
-          h0[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(gelu_tanh_fit(c0[2]), gelu_tanh_fit(c0[3]));
-          h1[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(gelu_tanh_fit(c1[0]), gelu_tanh_fit(c1[1]));
-          h1[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(gelu_tanh_fit(c1[2]), gelu_tanh_fit(c1[3]));
+          h0[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c0[0], c0[1]));
+          h0[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c0[2], c0[3]));
+          h1[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c1[0], c1[1]));
+          h1[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c1[2], c1[3]));
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -339,16 +385,72 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
     }
     const float rs0 = rsqrtf(quad_sum(q0) * (1.0f / D) + 1e-6f), rs1 = rsqrtf(quad_sum(q1) * (1.0f / D) + 1e-6f);
     const int64_t gr0 = tile * ROWS + lr[mt], gr1 = gr0 + 8;
+    float y[4][4];  // Spatial_norm output, same fragment layout as x
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const float2 wg = __ldg(reinterpret_cast<const float2*>(args.sn_w + 8 * nt + 2 * t));
       const float2 bg = __ldg(reinterpret_cast<const float2*>(args.sn_b + 8 * nt + 2 * t));
-      if (ok[mt][0])
-        *reinterpret_cast<float2*>(args.x_out + (view_row0 + gr0) * D + 8 * nt + 2 * t) =
-            make_float2((x[mt][nt][0] - m0) * rs0 * wg.x + bg.x, (x[mt][nt][1] - m0) * rs0 * wg.y + bg.y);
-      if (ok[mt][1])
-        *reinterpret_cast<float2*>(args.x_out + (view_row0 + gr1) * D + 8 * nt + 2 * t) =
-            make_float2((x[mt][nt][2] - m1) * rs1 * wg.x + bg.x, (x[mt][nt][3] - m1) * rs1 * wg.y + bg.y);
+      y[nt][0] = (x[mt][nt][0] - m0) * rs0 * wg.x + bg.x; y[nt][1] = (x[mt][nt][1] - m0) * rs0 * wg.y + bg.y;
+      y[nt][2] = (x[mt][nt][2] - m1) * rs1 * wg.x + bg.x; y[nt][3] = (x[mt][nt][3] - m1) * rs1 * wg.y + bg.y;
+    }
+    if (args.x_out != nullptr) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (ok[mt][0]) *reinterpret_cast<float2*>(args.x_out + (view_row0 + gr0) * D + 8 * nt + 2 * t) = make_float2(y[nt][0], y[nt][1]);
+        if (ok[mt][1]) *reinterpret_cast<float2*>(args.x_out + (view_row0 + gr1) * D + 8 * nt + 2 * t) = make_float2(y[nt][2], y[nt][3]);
+      }
+      continue;
+    }
+    // FPT token build fused behind (multiview_mpl.py:463-499): [+ confidence embedding] [| ray embedding] + 3D position,
+    // written straight into tok [B, V, tok_w] (8-byte stores, 32 contiguous bytes per quad)
+    const TokenArgs& k = args.io.token;
+    const int V = gridDim.y;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!ok[mt][h]) continue;
+      const int64_t gr = h ? gr1 : gr0;
+      const int64_t b = gr / J;
+      const int j = (int)(gr - b * J);
+      float* trow = k.tok + (b * V + view) * (int64_t)k.tok_w;
+      const bool need_dir = k.ray_layout != 0 || k.pos_table == nullptr;
+      float dx = 0.f, dy = 0.f, dz = 0.f, inv = 0.f;
+      if (need_dir) {
+        const float* r = k.rays[view] + b * k.pose_stride + j * 3;
+        const float* ce = k.centers[view] + b * k.center_stride;
+        dx = __ldg(r) - __ldg(ce); dy = __ldg(r + 1) - __ldg(ce + 1); dz = __ldg(r + 2) - __ldg(ce + 2);
+        inv = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);  // F.normalize eps
+      }
+      const float pc = (k.Wcf != nullptr) ? __ldg(k.poses[view] + b * k.pose_stride + j * 3 + 2) : 0.f;
+      auto pos_at = [&](int pos_c) {  // 3D position code of channel pos_c of this joint
+        if (k.pos_table != nullptr) return __ldg(k.pos_table + j * k.pos_w + pos_c);
+        const float* wl = k.Wl + pos_c * 3;
+        return fmaf(__ldg(wl + 2), dz * inv, fmaf(__ldg(wl + 1), dy * inv, fmaf(__ldg(wl), dx * inv, __ldg(k.bl + pos_c))));
+      };
+      const int slot = (k.ray_layout == 1) ? 2 * D : D;  // channels per joint slot of the pose part
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = 8 * nt + 2 * t;
+        float v0 = y[nt][2 * h], v1 = y[nt][2 * h + 1];
+        if (k.Wcf != nullptr) {
+          v0 += fmaf(__ldg(k.Wcf + c), pc, __ldg(k.bcf + c));
+          v1 += fmaf(__ldg(k.Wcf + c + 1), pc, __ldg(k.bcf + c + 1));
+        }
+        v0 += pos_at(c);
+        v1 += pos_at(c + 1);
+        *reinterpret_cast<float2*>(trow + j * slot + c) = make_float2(v0, v1);
+        if (k.ray_layout != 0) {
+          const float* w0 = k.Wr + c * 3;
+          float r0 = fmaf(__ldg(w0 + 2), dz, fmaf(__ldg(w0 + 1), dy, fmaf(__ldg(w0), dx, __ldg(k.br + c))));
+          float r1 = fmaf(__ldg(w0 + 5), dz, fmaf(__ldg(w0 + 4), dy, fmaf(__ldg(w0 + 3), dx, __ldg(k.br + c + 1))));
+          if (k.ray_layout == 1) {  // [x | ray] per joint, the position code spans both halves
+            r0 += pos_at(D + c);
+            r1 += pos_at(D + c + 1);
+            *reinterpret_cast<float2*>(trow + j * slot + D + c) = make_float2(r0, r1);
+          } else {                  // J pose tokens then J ray tokens (no position code on the ray tokens)
+            *reinterpret_cast<float2*>(trow + (J + j) * D + c) = make_float2(r0, r1);
+          }
+        }
+      }
     }
   }
 }
@@ -423,11 +525,18 @@ int launch_spt_pack_layer(const float* n1w, const float* n1b, const float* qkvw,
 }
 
 int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_per_view, int V, int64_t B, int depth,
-                     const float* sn_w, const float* sn_b, const float* conf, cudaStream_t s) {
+                     const float* sn_w, const float* sn_b, const float* conf, int conf_weighted, const SptIo* io,
+                     cudaStream_t s) {
   if (B == 0 || V == 0) return MPL_OK;
+  if ((x_in == nullptr || x_out == nullptr) && io == nullptr) {
+    set_error("launch_spt_fused: fused embedding / token build need their argument blocks");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
   SptArgs a{};
   a.x_in = x_in;
   a.x_out = x_out;
+  a.conf_weighted = conf_weighted;
+  if (io != nullptr) a.io = *io;
   for (int v = 0; v < V; ++v) a.wpack[v] = reinterpret_cast<const uint32_t*>(wpack_per_view[v]);
   a.sn_w = sn_w;
   a.sn_b = sn_b;

@@ -135,12 +135,20 @@ _FUSED_SPT_KW = dict(num_joints=17, embed_dim_ratio=32, num_heads=8, depth=3, nu
     dict(qkv_bias=False, qk_scale=0.3, pose_3d_emb_learnable=True),
     dict(add_confidence_input=True, mult_confidence_emb=True, no_transformer_fpt=True),
     dict(depth=1, input_rays_as_token=True),
-], ids=["confattn_multi", "confattn_single", "noqkvbias_scale", "spt_only", "depth1_raytok"])
+    dict(confidence_in_FPT=True, input_rays_as_token=True, add_3D_pos_encoding_to_rays=True, multiple_spatial_blocks=True),
+    dict(add_3D_pos_encoding_in_Spatial=True, pose_3d_emb_learnable=True, confidence_in_FPT=True),
+    dict(add_3D_pos_encoding_in_Spatial=True, input_rays_as_token=True, add_3D_pos_encoding_to_rays=True),
+    dict(FPT_blocks_view_keypoint_tokens=True, confidence_input_as_third=True),
+], ids=["confattn_multi", "confattn_single", "noqkvbias_scale", "spt_only", "depth1_raytok", "conffpt_interleave",
+        "pos3d_spatial_learn", "pos3d_spatial_linear", "kptok_linearpos"])
 @pytest.mark.parametrize("B", [5, 77])
 def test_fused_spt_kernel_variants_against_oracle(flags, B):
     """The single-kernel SPT (bf16 mode, d = 32, H = 8, J = 17) under the constructor flags that change what it does:
     the confidence-weighted extra pass per block (multiview_mpl.py:406-407), shared vs per-view stacks, no qkv bias,
-    explicit qk_scale, depth 1 (the only block runs twice) and batches that do not fill a 32-set CTA tile."""
+    explicit qk_scale, depth 1 (the only block runs twice), batches that do not fill a CTA tile, and every variant of
+    the joint embedding fused into its prologue (confidence add / mult, learnable 3D position; the ray-direction
+    position falls back to the separate embed kernel) and of the token build fused into its epilogue (three ray
+    layouts, confidence-in-FPT, table vs Linear(normalize(ray)) position codes)."""
     kw = dict(_FUSED_SPT_KW, **flags)
     cfg = spec.make_config(**kw)
     weights = synth.named_weights(spec.param_spec(cfg), seed=5)
