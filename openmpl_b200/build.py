@@ -17,6 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpl_b200.so")
 SOURCES = ["model.cu", "kernels_generic.cu", "gemm_tcgen05.cu", "metric_inputs.cu", "spt_fused.cu", "io_kernels.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "ptx.cuh", os.path.join("..", "..", "include", "mpl_b200.h")]
+# per-file extra nvcc flags (none at present)
+EXTRA_FLAGS = {}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -47,7 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             log = open(o + ".log", "w")
-            procs.append((s, log, subprocess.Popen([nvcc, *NVCC_FLAGS, "-c", s, "-o", o], stdout=log, stderr=subprocess.STDOUT)))
+            procs.append((s, log, subprocess.Popen([nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(os.path.basename(s), []), "-c", s, "-o", o],
+                                                    stdout=log, stderr=subprocess.STDOUT)))
     failed = []
     for s, log, p in procs:
         rc = p.wait()

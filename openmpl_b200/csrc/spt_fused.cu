@@ -156,6 +156,7 @@ __device__ __forceinline__ __half2 ex2_h2(__half2 x) {
   return h2(r);
 }
 
+// (measured: __maxnreg__(112) removes the spills but only one CTA then fits per SM -> 16.3 ms instead of 13.2 ms per step)
 __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem);
