@@ -167,6 +167,8 @@ def run_ours(args):
     model = MultiView_MPL(**kw, precision=args.precision)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
     model = model.to(dev).eval()
+    if os.environ.get("MPL_CHUNK"):
+        model.set_chunk_poses(int(os.environ["MPL_CHUNK"]))
 
     # ---- synthetic inputs of this rank's shard of the global pose range ----
     start, _ = mdist.shard_range(B * world, rank, world)
@@ -248,7 +250,8 @@ def run_ours(args):
     D, Hf, M = cfg.fpt_dim, cfg.fpt_hidden, B * cfg.fpt_tokens
     flops_per_launch = {"fpt_gemm_qkv": 2.0 * M * 3 * D * D, "fpt_gemm_proj": 2.0 * M * D * D,
                         "fpt_gemm_fc1": 2.0 * M * Hf * D, "fpt_gemm_fc2": 2.0 * M * D * Hf}
-    chunks = -(-B // 32768)
+    chunk_poses = int(os.environ.get("MPL_CHUNK", "0")) or int(model.chunk_poses())
+    chunks = -(-B // chunk_poses)
     roofline, breakdown = None, {}
     try:      # per-launch DRAM traffic of the GEMM launches from the committed `ncu --set full` capture (profiles/)
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -277,7 +280,7 @@ def run_ours(args):
                     "traffic": None, "note": "fp32 CUDA-core path: no tensor-core kernel in this mode"}
 
     # ---- HBM-bound kernels: algorithmic bytes per launch / measured launch time vs the measured copy bandwidth ----
-    Bc = min(B, 32768)
+    Bc = min(B, chunk_poses)
     rows_f = Bc * cfg.fpt_tokens
     esz = 2 if args.precision == "bf16" else 4
     alg_bytes = {

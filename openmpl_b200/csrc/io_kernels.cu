@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(256) token_build_vec_kernel(const TokenArgs a)
 // The E -> 3J Linear reads each weight row once per pose pair (L1-resident, 3J*E*4 = 111 KB) and reduces across lanes.
 // ---------------------------------------------------------------------------------------------------------------------
 // View_norm -> view-weighted sum -> head LayerNorm for TWO poses at once (independent load / reduction chains interleave)
-template <int NV>
-__device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int64_t bb, int lane, float (&pa)[NV], float (&pb)[NV]) {
+template <int NV, bool FULL>  // FULL: E == 32 * NV, no channel predicates
+__device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int64_t bb, int lane, const int (&colv)[NV],
+                                              float (&pa)[NV], float (&pb)[NV]) {
   const int E = a.E;
   const float invE = 1.0f / (float)E;
   const float wmb = __ldg(a.wm_b);
@@ -176,11 +177,9 @@ __device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int
     float sa = 0.f, sb = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int e0 = 32 * i;  // warp-uniform: the whole 32-channel group sits in one segment (seg_len % 32 == 0)
-      const int col = (e0 / a.seg_len) * a.seg_stride + (e0 % a.seg_len);
-      const bool ok = e0 + lane < E;
-      xa[i] = ok ? ra[col] : 0.f;
-      xb[i] = ok ? rb[col] : 0.f;
+      const bool ok = FULL || 32 * i + lane < E;
+      xa[i] = ok ? ra[colv[i]] : 0.f;
+      xb[i] = ok ? rb[colv[i]] : 0.f;
       sa += xa[i];
       sb += xb[i];
     }
@@ -188,7 +187,7 @@ __device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int
     float qa = 0.f, qb = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const bool ok = 32 * i + lane < E;
+      const bool ok = FULL || 32 * i + lane < E;
       const float ta = ok ? xa[i] - ma : 0.f, tb = ok ? xb[i] - mb : 0.f;
       qa = fmaf(ta, ta, qa);
       qb = fmaf(tb, tb, qb);
@@ -198,7 +197,7 @@ __device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int e = 32 * i + lane;
-      if (e < E) {
+      if (FULL || e < E) {
         const float g = __ldg(a.vn_w + e), bt = __ldg(a.vn_b + e);
         pa[i] = fmaf(wv, fmaf((xa[i] - ma) * rsa, g, bt), pa[i]);
         pb[i] = fmaf(wv, fmaf((xb[i] - mb) * rsb, g, bt), pb[i]);
@@ -207,12 +206,12 @@ __device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int
   }
   float sa = 0.f, sb = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { const bool ok = 32 * i + lane < E; sa += ok ? pa[i] : 0.f; sb += ok ? pb[i] : 0.f; }
+  for (int i = 0; i < NV; ++i) { const bool ok = FULL || 32 * i + lane < E; sa += ok ? pa[i] : 0.f; sb += ok ? pb[i] : 0.f; }
   const float ma = warp_sum(sa) * invE, mb = warp_sum(sb) * invE;
   float qa = 0.f, qb = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const bool ok = 32 * i + lane < E;
+    const bool ok = FULL || 32 * i + lane < E;
     const float ta = ok ? pa[i] - ma : 0.f, tb = ok ? pb[i] - mb : 0.f;
     qa = fmaf(ta, ta, qa);
     qb = fmaf(tb, tb, qb);
@@ -221,63 +220,104 @@ __device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int e = 32 * i + lane;
-    const float g = (e < E) ? __ldg(a.hn_w + e) : 0.f, bt = (e < E) ? __ldg(a.hn_b + e) : 0.f;
+    const float g = (FULL || e < E) ? __ldg(a.hn_w + e) : 0.f, bt = (FULL || e < E) ? __ldg(a.hn_b + e) : 0.f;
     pa[i] = fmaf((pa[i] - ma) * rsa, g, bt);
     pb[i] = fmaf((pb[i] - mb) * rsb, g, bt);
   }
 }
 
-// One warp per group of PG poses.  Phase 1 (per pose): View_norm -> view-weighted sum -> head LayerNorm in registers
-// (lane = channel % 32), result parked in shared memory as [channel][pose].  Phase 2: lane l owns outputs l and l + 32
-// for all PG poses: it walks the E channels reading the transposed, 64-padded head weight (coalesced, L1-resident,
-// each element read once per PG poses) and the PG pooled values of that channel (one broadcast 16-byte load) -- no
-// cross-lane reduction at all.
-constexpr int HEAD_PG = 4;
+// One CTA (8 warps) per group of 32 poses.
+//   Phase 1: each warp pools its 4 poses (View_norm -> view-weighted sum -> head LayerNorm, registers + shuffles only,
+//            lane = channel % 32) and parks the result in shared memory as pool[channel][pose].
+//   Phase 2: the E channels are split over the warps; lane l owns outputs l and l + 32 of ALL 32 poses, so every element
+//            of the transposed, 64-padded head weight is read once per 32 poses (coalesced) and feeds 64 FMAs; the pooled
+//            values of a channel arrive as eight broadcast 16-byte shared-memory loads.
+//   Phase 3: the 8 per-warp partial sums of every (pose, output) are added in a fixed order through shared memory.
+constexpr int HEAD_PB = 32;       // poses per CTA iteration
+constexpr int HEAD_WARPS = 8;
 
-template <int NV>
-__global__ void __launch_bounds__(256, 2) head_warp_kernel(const HeadArgs a) {
-  extern __shared__ __align__(16) float hsm[];  // [warps][E][HEAD_PG]
+template <int NV, bool FULL>
+__global__ void __launch_bounds__(HEAD_WARPS * 32, 2) head_block_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float hsm[];  // pool [E][HEAD_PB]; reused as partial [HEAD_WARPS][HEAD_PB][64]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int E = a.E;
-  float* pool = hsm + (size_t)warp * E * HEAD_PG;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t groups = (a.B + HEAD_PG - 1) / HEAD_PG;
-  const float hb0 = (lane < a.out_dim) ? __ldg(a.hb + lane) : 0.f;
-  const float hb1 = (32 + lane < a.out_dim) ? __ldg(a.hb + 32 + lane) : 0.f;
-  for (int64_t gi = warp_global; gi < groups; gi += warps_total) {
-    const int64_t b0 = gi * HEAD_PG;
+  const int64_t groups = (a.B + HEAD_PB - 1) / HEAD_PB;
+  const int e_per_warp = (E + HEAD_WARPS - 1) / HEAD_WARPS;
+  // column of channel group i in the token row: 32-channel segments seg_stride apart (ray halves stripped, d = 32) or
+  // one contiguous row (seg_len == E, seg_stride == 32 passed by the launcher): one multiply, no division
+  int colv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) colv[i] = i * a.seg_stride;
+  for (int64_t gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+    const int64_t b0 = gi * HEAD_PB;
+    // ---- phase 1 ----
 #pragma unroll 1
-    for (int pi = 0; pi < HEAD_PG; pi += 2) {
+    for (int pi = 0; pi < HEAD_PB / HEAD_WARPS; pi += 2) {
+      const int p0 = warp * (HEAD_PB / HEAD_WARPS) + pi;
       float pa[NV], pb[NV];
-      head_pool_two<NV>(a, min(b0 + pi, a.B - 1), min(b0 + pi + 1, a.B - 1), lane, pa, pb);
+      head_pool_two<NV, FULL>(a, min(b0 + p0, a.B - 1), min(b0 + p0 + 1, a.B - 1), lane, colv, pa, pb);
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (32 * i + lane < E) *reinterpret_cast<float2*>(pool + (32 * i + lane) * HEAD_PG + pi) = make_float2(pa[i], pb[i]);
+        if (FULL || 32 * i + lane < E) *reinterpret_cast<float2*>(hsm + (32 * i + lane) * HEAD_PB + p0) = make_float2(pa[i], pb[i]);
     }
-    __syncwarp();
-    float acc0[HEAD_PG], acc1[HEAD_PG];
+    __syncthreads();
+    // ---- phase 2 ----
+    float acc0[HEAD_PB], acc1[HEAD_PB];
 #pragma unroll
-    for (int pi = 0; pi < HEAD_PG; ++pi) { acc0[pi] = hb0; acc1[pi] = hb1; }
+    for (int p = 0; p < HEAD_PB; ++p) { acc0[p] = 0.f; acc1[p] = 0.f; }
+    const int e_lo = warp * e_per_warp, e_hi = min(E, e_lo + e_per_warp);
     const float* wt = a.hwT + lane;
-#pragma unroll 8
-    for (int e = 0; e < E; ++e) {
-      const float w0 = __ldg(wt + e * 64), w1 = __ldg(wt + e * 64 + 32);
-      const float4 pv = *reinterpret_cast<const float4*>(pool + e * HEAD_PG);
-      acc0[0] = fmaf(pv.x, w0, acc0[0]); acc1[0] = fmaf(pv.x, w1, acc1[0]);
-      acc0[1] = fmaf(pv.y, w0, acc0[1]); acc1[1] = fmaf(pv.y, w1, acc1[1]);
-      acc0[2] = fmaf(pv.z, w0, acc0[2]); acc1[2] = fmaf(pv.z, w1, acc1[2]);
-      acc0[3] = fmaf(pv.w, w0, acc0[3]); acc1[3] = fmaf(pv.w, w1, acc1[3]);
-    }
+    // weights of 4 channels are fetched (L2 / L1) one 4-channel step ahead of their use
+    float wn[4][2];
 #pragma unroll
-    for (int pi = 0; pi < HEAD_PG; ++pi) {
-      if (b0 + pi < a.B) {
-        float* out = a.out + (b0 + pi) * a.out_dim;
-        if (lane < a.out_dim) out[lane] = acc0[pi];
-        if (32 + lane < a.out_dim) out[32 + lane] = acc1[pi];
+    for (int u = 0; u < 4; ++u) {
+      const int e = min(e_lo + u, E - 1);
+      wn[u][0] = __ldg(wt + e * 64); wn[u][1] = __ldg(wt + e * 64 + 32);
+    }
+#pragma unroll 1
+    for (int e4 = e_lo; e4 < e_hi; e4 += 4) {
+      float wc[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { wc[u][0] = wn[u][0]; wc[u][1] = wn[u][1]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = min(e4 + 4 + u, E - 1);
+        wn[u][0] = __ldg(wt + e * 64); wn[u][1] = __ldg(wt + e * 64 + 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (e4 + u >= e_hi) break;
+        const float w0 = wc[u][0], w1 = wc[u][1];
+        const float4* pv = reinterpret_cast<const float4*>(hsm + (e4 + u) * HEAD_PB);
+#pragma unroll
+        for (int p4 = 0; p4 < HEAD_PB / 4; ++p4) {
+          const float4 v = pv[p4];
+          acc0[4 * p4] = fmaf(v.x, w0, acc0[4 * p4]);         acc1[4 * p4] = fmaf(v.x, w1, acc1[4 * p4]);
+          acc0[4 * p4 + 1] = fmaf(v.y, w0, acc0[4 * p4 + 1]); acc1[4 * p4 + 1] = fmaf(v.y, w1, acc1[4 * p4 + 1]);
+          acc0[4 * p4 + 2] = fmaf(v.z, w0, acc0[4 * p4 + 2]); acc1[4 * p4 + 2] = fmaf(v.z, w1, acc1[4 * p4 + 2]);
+          acc0[4 * p4 + 3] = fmaf(v.w, w0, acc0[4 * p4 + 3]); acc1[4 * p4 + 3] = fmaf(v.w, w1, acc1[4 * p4 + 3]);
+        }
       }
     }
-    __syncwarp();  // the pooled values are reused by the next group
+    __syncthreads();  // every warp is done reading the pooled values: the buffer becomes the partial-sum exchange
+    // ---- phase 3 ----
+    float* part = hsm + (size_t)warp * HEAD_PB * 64;
+#pragma unroll
+    for (int p = 0; p < HEAD_PB; ++p) {
+      part[p * 64 + lane] = acc0[p];
+      part[p * 64 + 32 + lane] = acc1[p];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < HEAD_PB * 64; idx += HEAD_WARPS * 32) {
+      const int p = idx >> 6, o = idx & 63;
+      if (o < a.out_dim && b0 + p < a.B) {
+        float sum = __ldg(a.hb + o);
+#pragma unroll
+        for (int w = 0; w < HEAD_WARPS; ++w) sum += hsm[(size_t)w * HEAD_PB * 64 + idx];
+        a.out[(b0 + p) * a.out_dim + o] = sum;
+      }
+    }
+    __syncthreads();  // the buffer is reused by the next group
   }
 }
 
@@ -328,21 +368,22 @@ int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s) {
 }
 
 int try_launch_head_warp(const HeadArgs& a, cudaStream_t s) {
-  if (a.E > 32 * 17 || a.out_dim > 64 || a.seg_len % 32 != 0 || a.hwT == nullptr) return 1;
+  if (a.E > 32 * 17 || a.out_dim > 64 || a.hwT == nullptr || !(a.seg_len == 32 || a.seg_len == a.E)) return 1;
   if (a.B == 0) return MPL_OK;
-  const int64_t blocks = std::min<int64_t>(ceil_div(a.B, 8 * HEAD_PG), (int64_t)kNumSMs * 2);
-  const size_t smem = (size_t)8 * a.E * HEAD_PG * sizeof(float);
-  static bool attr_set[64][2] = {};
+  const int64_t blocks = std::min<int64_t>(ceil_div(a.B, HEAD_PB), (int64_t)kNumSMs * 2);
+  const size_t smem = std::max((size_t)a.E * HEAD_PB, (size_t)HEAD_WARPS * HEAD_PB * 64) * sizeof(float);
+  static bool attr_set[64][3] = {};
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
-  const int which = a.E > 32 * 9 ? 1 : 0;
+  const int which = (a.E == 32 * 17) ? 2 : (a.E > 32 * 9 ? 1 : 0);
+  auto kern = which == 2 ? head_block_kernel<17, true> : (which == 1 ? head_block_kernel<17, false> : head_block_kernel<9, false>);
   if (dev < 0 || dev >= 64 || !attr_set[dev][which]) {
-    if (which) MPL_CUDA(cudaFuncSetAttribute(head_warp_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else MPL_CUDA(cudaFuncSetAttribute(head_warp_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) attr_set[dev][which] = true;
   }
-  if (which) head_warp_kernel<17><<<(unsigned)blocks, 256, smem, s>>>(a);
-  else head_warp_kernel<9><<<(unsigned)blocks, 256, smem, s>>>(a);
+  HeadArgs b = a;
+  if (a.seg_len == a.E) b.seg_stride = 32;  // contiguous row: channel group i starts at column 32 i
+  kern<<<(unsigned)blocks, HEAD_WARPS * 32, smem, s>>>(b);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

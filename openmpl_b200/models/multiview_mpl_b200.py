@@ -182,6 +182,10 @@ class MultiView_MPL(nn.Module):
         for h in self._h.ptrs.values():
             _lib.check(_lib.lib().mpl_set_chunk_poses(h, int(chunk)))
 
+    def chunk_poses(self) -> int:
+        """Poses per forward chunk (the workspace stops growing there)."""
+        return int(_lib.lib().mpl_chunk_poses(self._get_handle()))
+
     def set_profile(self, enabled: bool):
         """Bracket every kernel launch of the next forwards with CUDA events (see `profile()`)."""
         _lib.check(_lib.lib().mpl_set_profile(self._get_handle(), int(bool(enabled))))
