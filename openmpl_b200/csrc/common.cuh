@@ -55,21 +55,6 @@ __device__ __forceinline__ float warp_max(float v) {
 // nn.GELU() default: exact erf form (multiview_mpl.py:22,27)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// erf-form GELU for results that are rounded to bf16 right after: Abramowitz-Stegun 7.1.25 (|erf error| < 2.5e-5),
-// branch-free, two MUFU ops (rcp.approx, ex2.approx) + ~10 FMA-pipe instructions instead of the ~30-instruction erff
-// with its slow path; the exact erff stays on every fp32 path.
-//   0.5 x (1 + erf(x / sqrt 2)) = hx + |hx| (1 - erfc(|z|)),  hx = x / 2, z = |x| / sqrt 2
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t, ex;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.47047f, z, 1.0f)));
-  const float poly = t * fmaf(t, fmaf(t, 0.7478556f, -0.0958798f), 0.3480242f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * (-1.4426950408889634f * z)));
-  const float e = poly * ex;  // erfc(|z|)
-  const float hx = 0.5f * x;
-  return fmaf(-fabsf(hx), e, hx + fabsf(hx));
-}
-
 // erf-form GELU (nn.GELU() default, multiview_mpl.py:22,27) for results that are rounded to fp16 / bf16 right after:
 // 0.5 x (1 + tanh(x (c0 + c1 x^2))) with (c0, c1) fitted to the ERF form (max |error| 2.7e-4 over all x, at |x| ~ 2 where
 // the bf16 half-ulp is 4e-3; tanh.approx adds <= 2^-11 relative).  6 FMA-pipe instructions + one MUFU.

@@ -574,11 +574,14 @@ __global__ void __launch_bounds__(256) attention_narrow_kernel(const TI* __restr
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T, int CE> struct ChunkIO;
 template <> struct ChunkIO<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  using Pack = uint4;
+  static __device__ __forceinline__ void unpack(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    unpack(*reinterpret_cast<const uint4*>(p), f);
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
     uint4 u;
@@ -589,11 +592,13 @@ template <> struct ChunkIO<__nv_bfloat16, 8> {
   }
 };
 template <> struct ChunkIO<__nv_bfloat16, 4> {
+  using Pack = uint2;
+  static __device__ __forceinline__ void unpack(const uint2& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[4]) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    unpack(*reinterpret_cast<const uint2*>(p), f);
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[4]) {
     uint2 u;
@@ -604,10 +609,9 @@ template <> struct ChunkIO<__nv_bfloat16, 4> {
   }
 };
 template <> struct ChunkIO<float, 4> {
-  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
-    const float4 u = *reinterpret_cast<const float4*>(p);
-    f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
-  }
+  using Pack = float4;
+  static __device__ __forceinline__ void unpack(const float4& u, float (&f)[4]) { f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; }
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) { unpack(*reinterpret_cast<const float4*>(p), f); }
   static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
   }
@@ -623,26 +627,33 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
   const int c = threadIdx.x;
   float* part = sm;
   float* prob = sm + (size_t)nchunks * V * V;
+  // The q / k / v chunks of the pose stay PACKED in registers (one 16- or 8-byte word per view and operand) and are
+  // widened at the point of use: the kernel is HBM-bound and register-limited, and the packed form doubles the number
+  // of poses in flight per SM.
+  using Pack = typename ChunkIO<T, CE>::Pack;
   for (int64_t pose = blockIdx.x; pose < poses; pose += gridDim.x) {
     const T* row0 = qkv + pose * V * 3 * (int64_t)D;
-    float q[V][CE], k[V][CE];
+    Pack q[V], k[V], vv[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      ChunkIO<T, CE>::load(row0 + (int64_t)v * 3 * D + c * CE, q[v]);
-      ChunkIO<T, CE>::load(row0 + (int64_t)v * 3 * D + D + c * CE, k[v]);
+      q[v] = *reinterpret_cast<const Pack*>(row0 + (int64_t)v * 3 * D + c * CE);
+      k[v] = *reinterpret_cast<const Pack*>(row0 + (int64_t)v * 3 * D + D + c * CE);
+      vv[v] = *reinterpret_cast<const Pack*>(row0 + (int64_t)v * 3 * D + 2 * D + c * CE);
     }
-    float vv[V][CE];
 #pragma unroll
-    for (int v = 0; v < V; ++v) ChunkIO<T, CE>::load(row0 + (int64_t)v * 3 * D + 2 * D + c * CE, vv[v]);
-#pragma unroll
-    for (int i = 0; i < V; ++i)
+    for (int i = 0; i < V; ++i) {
+      float qi[CE];
+      ChunkIO<T, CE>::unpack(q[i], qi);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
+        float kj[CE];
+        ChunkIO<T, CE>::unpack(k[j], kj);
         float a = 0.f;
 #pragma unroll
-        for (int e = 0; e < CE; ++e) a = fmaf(q[i][e], k[j][e], a);
+        for (int e = 0; e < CE; ++e) a = fmaf(qi[e], kj[e], a);
         part[c * (V * V) + i * V + j] = a;
       }
+    }
     __syncthreads();
     // H * V query rows: sum the head's chunk partials, softmax over the V keys
     for (int r = threadIdx.x; r < H * V; r += blockDim.x) {
@@ -665,22 +676,29 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
     }
     __syncthreads();
     const int h = c / cph;
+    float o[V][CE];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float o[CE];
+    for (int i = 0; i < V; ++i)
 #pragma unroll
-      for (int e = 0; e < CE; ++e) o[e] = 0.f;
+      for (int e = 0; e < CE; ++e) o[i][e] = 0.f;
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
+    for (int j = 0; j < V; ++j) {
+      float vj[CE];
+      ChunkIO<T, CE>::unpack(vv[j], vj);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
         const float pj = prob[h * (V * V) + i * V + j];
 #pragma unroll
-        for (int e = 0; e < CE; ++e) o[e] = fmaf(pj, vv[j][e], o[e]);
+        for (int e = 0; e < CE; ++e) o[i][e] = fmaf(pj, vj[e], o[i][e]);
       }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
       if (TF32_OUT) {
 #pragma unroll
-        for (int e = 0; e < CE; ++e) o[e] = round_tf32(o[e]);
+        for (int e = 0; e < CE; ++e) o[i][e] = round_tf32(o[i][e]);
       }
-      ChunkIO<T, CE>::store(out + (pose * V + i) * (int64_t)D + c * CE, o);
+      ChunkIO<T, CE>::store(out + (pose * V + i) * (int64_t)D + c * CE, o[i]);
     }
     __syncthreads();  // prob / part are reused by the next pose
   }
