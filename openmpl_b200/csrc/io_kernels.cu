@@ -226,14 +226,15 @@ __device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int
   }
 }
 
-// One CTA (8 warps) per group of 32 poses.
+// One CTA (8 warps) per group of HEAD_PB poses.
 //   Phase 1: each warp pools its 4 poses (View_norm -> view-weighted sum -> head LayerNorm, registers + shuffles only,
 //            lane = channel % 32) and parks the result in shared memory as pool[channel][pose].
 //   Phase 2: the E channels are split over the warps; lane l owns outputs l and l + 32 of ALL 32 poses, so every element
 //            of the transposed, 64-padded head weight is read once per 32 poses (coalesced) and feeds 64 FMAs; the pooled
 //            values of a channel arrive as eight broadcast 16-byte shared-memory loads.
 //   Phase 3: the 8 per-warp partial sums of every (pose, output) are added in a fixed order through shared memory.
-constexpr int HEAD_PB = 32;       // poses per CTA iteration
+constexpr int HEAD_PB = 16;       // poses per CTA iteration (16: pooled values + exchange buffer stay at 35 KB per CTA, so the
+                                  // 139 KB transposed head weight remains L1-resident next to two CTAs per SM)
 constexpr int HEAD_WARPS = 8;
 
 template <int NV, bool FULL>
