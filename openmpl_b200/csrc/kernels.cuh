@@ -153,7 +153,7 @@ struct SptIo {
 };
 int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_per_view, int V, int64_t B, int depth,
                      const float* sn_w, const float* sn_b, const float* conf, int conf_weighted, const SptIo* io,
-                     cudaStream_t s);
+                     int precise, cudaStream_t s);  // precise: fp32 softmax arithmetic + exact erf GELU (tf32 mode)
 
 // ---- metric + input builder -----------------------------------------------------------------------------------------
 int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t B, int J, float unit_scale,

@@ -58,7 +58,7 @@ struct MplModel {
   int ray_layout;  // 0 none, 1 interleave, 2 append
   int n_out;
   bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
-  bool spt_fused;  // the SPT stack runs as the single fused bf16-mma kernel (bf16 mode, d=32, H=8, J=17)
+  bool spt_fused;  // the SPT stack runs as the single fused fp16-mma kernel (bf16 / tf32 modes, d=32, H=8, J=17)
   bool ln_fused;   // bf16 mode: the FPT LayerNorms are folded into the projection GEMMs (no LayerNorm kernel)
   int ln_slots;    // statistics slots per row written by the residual-emit GEMMs
   std::vector<ParamInfo> params;
@@ -561,7 +561,8 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
     SptIo io{ea, ta};
     LC(CAT_SPT_FUSED, launch_spt_fused(fuse_embed ? nullptr : w.xs, fuse_token ? nullptr : w.xn, wp, V, Bc, m->depth,
                                        P.f("Spatial_norm.weight"), P.f("Spatial_norm.bias"), fuse_embed ? nullptr : w.conf,
-                                       d.confidence_as_attention_uncertainty_weight ? 1 : 0, &io, s));
+                                       d.confidence_as_attention_uncertainty_weight ? 1 : 0, &io,
+                                       d.precision == MPL_PREC_TF32 ? 1 : 0, s));
   } else {
     if (!d.no_transformer_spt && m->depth > 0) {
       const int hd = dim / m->H;
@@ -724,7 +725,7 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
     delete m;
     return st;
   }
-  m->spt_fused = d.precision == MPL_PREC_BF16 && !d.no_transformer_spt && m->depth > 0 &&
+  m->spt_fused = d.precision != MPL_PREC_FP32 && !d.no_transformer_spt && m->depth > 0 &&
                  spt_fused_supports(m->J, m->dim, m->H, m->spt_hidden);
   m->fpt_tc = false;
   if (d.precision != MPL_PREC_FP32 && !d.no_transformer_fpt && m->depth > 0) {

@@ -157,6 +157,9 @@ __device__ __forceinline__ __half2 ex2_h2(__half2 x) {
 }
 
 // (measured: __maxnreg__(112) removes the spills but only one CTA then fits per SM -> 16.3 ms instead of 13.2 ms per step)
+// PRECISE (tf32 mode): softmax / PV arithmetic in fp32 on the fp16-staged q, k, v and the exact erf GELU -- every
+// rounding left is a 2^-11 operand rounding, the same class as kind::tf32's; bf16 mode takes the packed-half2 forms.
+template <bool PRECISE>
 __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem);
@@ -269,7 +272,56 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
       }
       __syncthreads();
       // ---- attention: softmax(q k^T * scale) v over the 17 tokens of the row's set; two heads per half2 lane pair ----
-      {
+      if constexpr (PRECISE) {
+        uint4* rowps[2] = {reinterpret_cast<uint4*>(qkv_w + ra * QPW), reinterpret_cast<uint4*>(qkv_w + rb * QPW)};
+        const float rsc[2] = {weighted ? aconf_a : 1.0f, weighted ? aconf_b : 1.0f};
+        const uint4* setp = reinterpret_cast<const uint4*>(qkv_w + aset0 * QPW);
+        constexpr int RP4 = QPW / 4;
+#pragma unroll 1
+        for (int pp = 0; pp < 2; ++pp) {
+          const int p = ahh + 2 * pp;
+#pragma unroll 1
+          for (int rr = 0; rr < 2; ++rr) {
+            if (rr == 1 && !two) break;
+            const uint4 qu = rowps[rr][p];
+            const float2 q0 = __half22float2(h2(qu.x)), q1 = __half22float2(h2(qu.y)), q2 = __half22float2(h2(qu.z)),
+                         q3 = __half22float2(h2(qu.w));  // word d = (head 2p dim d, head 2p+1 dim d)
+            float s0[J], s1[J];
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+              const uint4 ku = setp[j * RP4 + 4 + p];
+              const float2 k0 = __half22float2(h2(ku.x)), k1 = __half22float2(h2(ku.y)), k2 = __half22float2(h2(ku.z)),
+                           k3 = __half22float2(h2(ku.w));
+              s0[j] = fmaf(q3.x, k3.x, fmaf(q2.x, k2.x, fmaf(q1.x, k1.x, q0.x * k0.x)));
+              s1[j] = fmaf(q3.y, k3.y, fmaf(q2.y, k2.y, fmaf(q1.y, k1.y, q0.y * k0.y)));
+              m0 = fmaxf(m0, s0[j]);
+              m1 = fmaxf(m1, s1[j]);
+            }
+            float sum0 = 0.f, sum1 = 0.f;
+            float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+              const uint4 vu = setp[j * RP4 + 8 + p];
+              const float2 v0 = __half22float2(h2(vu.x)), v1 = __half22float2(h2(vu.y)), v2 = __half22float2(h2(vu.z)),
+                           v3 = __half22float2(h2(vu.w));
+              float e0, e1;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0[j] - m0));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1[j] - m1));
+              sum0 += e0; sum1 += e1;
+              o0.x = fmaf(e0, v0.x, o0.x); o0.y = fmaf(e1, v0.y, o0.y);
+              o1.x = fmaf(e0, v1.x, o1.x); o1.y = fmaf(e1, v1.y, o1.y);
+              o2.x = fmaf(e0, v2.x, o2.x); o2.y = fmaf(e1, v2.y, o2.y);
+              o3.x = fmaf(e0, v3.x, o3.x); o3.y = fmaf(e1, v3.y, o3.y);
+            }
+            const float i0 = rsc[rr] / sum0, i1 = rsc[rr] / sum1;
+            uint4 o;
+            o.x = pack_f16(o0.x * i0, o0.y * i1); o.y = pack_f16(o1.x * i0, o1.y * i1);
+            o.z = pack_f16(o2.x * i0, o2.y * i1); o.w = pack_f16(o3.x * i0, o3.y * i1);
+            rowps[rr][p] = o;  // the q slot of this row / head pair is consumed: it now holds the attention output
+          }
+        }
+      } else       {
         const float sa = weighted ? aconf_a : 1.0f, sb = weighted ? aconf_b : 1.0f;
         uint4* rowpa = reinterpret_cast<uint4*>(qkv_w + ra * QPW);
         uint4* rowpb = reinterpret_cast<uint4*>(qkv_w + rb * QPW);
@@ -354,10 +406,17 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
         for (int nt = 0; nt < 8; ++nt) {
           float c0[4], c1[4];
           gemm_tile2<2>(c0, c1, a0, a1, w + OFF_FC1, nt, wv + F_FC1B, lane, t);
-          h0[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c0[0], c0[1]));
-          h0[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c0[2], c0[3]));
-          h1[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c1[0], c1[1]));
-          h1[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c1[2], c1[3]));
+          if constexpr (PRECISE) {
+            h0[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(gelu_erf(c0[0]), gelu_erf(c0[1]));
+            h0[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(gelu_erf(c0[2]), gelu_erf(c0[3]));
+            h1[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(gelu_erf(c1[0]), gelu_erf(c1[1]));
+            h1[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(gelu_erf(c1[2]), gelu_erf(c1[3]));
+          } else {
+            h0[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c0[0], c0[1]));
+            h0[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c0[2], c0[3]));
+            h1[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c1[0], c1[1]));
+            h1[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c1[2], c1[3]));
+          }
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -527,7 +586,7 @@ int launch_spt_pack_layer(const float* n1w, const float* n1b, const float* qkvw,
 
 int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_per_view, int V, int64_t B, int depth,
                      const float* sn_w, const float* sn_b, const float* conf, int conf_weighted, const SptIo* io,
-                     cudaStream_t s) {
+                     int precise, cudaStream_t s) {
   if (B == 0 || V == 0) return MPL_OK;
   if ((x_in == nullptr || x_out == nullptr) && io == nullptr) {
     set_error("launch_spt_fused: fused embedding / token build need their argument blocks");
@@ -544,15 +603,16 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
   a.conf = conf;
   a.B = B;
   a.depth = depth;
-  static bool attr_set[64] = {};  // per device: function attributes live in the device's context (DataParallel replicas)
+  static bool attr_set[64][2] = {};  // per device: function attributes live in the device's context (DataParallel replicas)
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    MPL_CUDA(cudaFuncSetAttribute(spt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  auto kern = precise ? spt_fused_kernel<true> : spt_fused_kernel<false>;
+  if (dev < 0 || dev >= 64 || !attr_set[dev][precise ? 1 : 0]) {
+    MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    if (dev >= 0 && dev < 64) attr_set[dev][precise ? 1 : 0] = true;
   }
   dim3 grid((unsigned)ceil_div(B, SETS), (unsigned)V);
-  spt_fused_kernel<<<grid, THREADS, SMEM_TOTAL, s>>>(a);
+  kern<<<grid, THREADS, SMEM_TOTAL, s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
