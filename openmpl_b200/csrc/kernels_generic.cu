@@ -567,6 +567,95 @@ __global__ void __launch_bounds__(256) attention_narrow_kernel(const TI* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Keypoint-token attention of the FPT in bf16 mode (FPT_blocks_view_keypoint_tokens: N = V * 17 <= 136 tokens of width 32,
+// 8 heads of 4): a CTA keeps G whole token sets in shared memory as fp16 with the channels of each head PAIR interleaved
+// (word = (head 2p, head 2p+1) at one head-dim, q pre-scaled by scale * log2 e), exactly the staging format of the SPT
+// kernel, so the softmax of two heads runs in packed half2 arithmetic straight from 16-byte shared-memory loads.  One
+// thread per (token row, head pair), two passes over the keys (max; then exp2 / sum / PV with the scores recomputed --
+// N is too long for registers).  Partial sums are kept in fp16 for 17 keys at a time and flushed into fp32.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+__global__ void __launch_bounds__(256) attention_kp_h4_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                             int64_t sets, int N, int G, float scale_log2e) {
+  constexpr int QP = 104, QPW = QP / 2, RP4 = QPW / 4;  // fp16 row pitch 208 B (see spt_fused.cu)
+  extern __shared__ __align__(16) uint32_t kp_sm[];       // [G * N][QPW]
+  const int64_t set0 = (int64_t)blockIdx.x * G;
+  const int g_here = (int)min((int64_t)G, sets - set0);
+  const int rows = g_here * N;
+  // stage: 12 groups of 8 channels per row, bf16 -> fp16, interleave the two heads of a group
+  for (int it = threadIdx.x; it < rows * 12; it += blockDim.x) {
+    const int r = it / 12, grp = it - r * 12;
+    const uint4 u = *reinterpret_cast<const uint4*>(qkv + ((set0 * N + r) * 96 + grp * 8));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    const float sc = grp < 4 ? scale_log2e : 1.0f;
+    uint4 o;
+    uint32_t* op = &o.x;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(op[d]) : "f"(f[4 + d] * sc), "f"(f[d] * sc));
+    }
+    *reinterpret_cast<uint4*>(kp_sm + r * QPW + grp * 4) = o;
+  }
+  __syncthreads();
+  for (int it = threadIdx.x; it < rows * 4; it += blockDim.x) {
+    const int r = it >> 2, p = it & 3;
+    const int s0 = (r / N) * N;  // first row of the row's set
+    const uint4* setp = reinterpret_cast<const uint4*>(kp_sm + s0 * QPW);
+    const uint4 q = reinterpret_cast<const uint4*>(kp_sm + r * QPW)[p];
+    __half2 mx = __float2half2_rn(-60000.f);
+    for (int j = 0; j < N; ++j) {
+      const uint4 k = setp[j * RP4 + 4 + p];
+      __half2 s = __hmul2(as_h2(q.x), as_h2(k.x));
+      s = __hfma2(as_h2(q.y), as_h2(k.y), s);
+      s = __hfma2(as_h2(q.z), as_h2(k.z), s);
+      s = __hfma2(as_h2(q.w), as_h2(k.w), s);
+      mx = __hmax2(mx, s);
+    }
+    float sum0 = 0.f, sum1 = 0.f, o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j0 = 0; j0 < N; j0 += 17) {
+      const __half2 z = __float2half2_rn(0.f);
+      __half2 hs = z, a0 = z, a1 = z, a2 = z, a3 = z;
+#pragma unroll
+      for (int jj = 0; jj < 17; ++jj) {
+        const int j = j0 + jj;
+        if (j < N) {
+          const uint4 k = setp[j * RP4 + 4 + p];
+          const uint4 v = setp[j * RP4 + 8 + p];
+          __half2 s = __hmul2(as_h2(q.x), as_h2(k.x));
+          s = __hfma2(as_h2(q.y), as_h2(k.y), s);
+          s = __hfma2(as_h2(q.z), as_h2(k.z), s);
+          s = __hfma2(as_h2(q.w), as_h2(k.w), s);
+          const __half2 d = __hsub2(s, mx);
+          uint32_t eu;
+          asm("ex2.approx.f16x2 %0, %1;" : "=r"(eu) : "r"(*reinterpret_cast<const uint32_t*>(&d)));
+          const __half2 e = as_h2(eu);
+          hs = __hadd2(hs, e);
+          a0 = __hfma2(e, as_h2(v.x), a0);
+          a1 = __hfma2(e, as_h2(v.y), a1);
+          a2 = __hfma2(e, as_h2(v.z), a2);
+          a3 = __hfma2(e, as_h2(v.w), a3);
+        }
+      }
+      const float2 fs = __half22float2(hs), f0 = __half22float2(a0), f1 = __half22float2(a1), f2 = __half22float2(a2),
+                   f3 = __half22float2(a3);
+      sum0 += fs.x; sum1 += fs.y;
+      o0[0] += f0.x; o1[0] += f0.y; o0[1] += f1.x; o1[1] += f1.y; o0[2] += f2.x; o1[2] += f2.y; o0[3] += f3.x; o1[3] += f3.y;
+    }
+    const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
+    __nv_bfloat162 b[4] = {__floats2bfloat162_rn(o0[0] * i0, o0[1] * i0), __floats2bfloat162_rn(o0[2] * i0, o0[3] * i0),
+                           __floats2bfloat162_rn(o1[0] * i1, o1[1] * i1), __floats2bfloat162_rn(o1[2] * i1, o1[3] * i1)};
+    uint4 ou;
+    ou.x = *reinterpret_cast<uint32_t*>(&b[0]); ou.y = *reinterpret_cast<uint32_t*>(&b[1]);
+    ou.z = *reinterpret_cast<uint32_t*>(&b[2]); ou.w = *reinterpret_cast<uint32_t*>(&b[3]);
+    *reinterpret_cast<uint4*>(out + (set0 * N + r) * 32 + p * 8) = ou;  // channels 8p .. 8p+7 = heads 2p, 2p+1
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // K4 view-token attention of the FPT (N = V tokens of width D, hd = D / H = 136 | 68): HBM-bound, 3 D in / D out per
 // row.  One CTA per pose, one thread per CE-element chunk of the row (D / CE threads): each thread loads its chunk of
 // q, k, v for all V views with 16- or 8-byte loads, forms partial V x V scores over its chunk, the chunks of a head are
@@ -745,6 +834,25 @@ static int launch_attention_any(const TI* qkv, TO* out, int64_t sets, int N, int
         if (aligned && hd % 4 == 0 && C / 4 <= 288 && C / 4 >= H * N)
           return launch_attention_views<TI, 4, TF32_OUT>(qkv, out, sets, N, C, hd, scale, s);
       }
+    }
+  }
+  // (2a) bf16 keypoint tokens, 8 heads of 4: fp16 head-pair staging + packed half2 softmax
+  if constexpr (std::is_same<TI, __nv_bfloat16>::value && std::is_same<TO, __nv_bfloat16>::value) {
+    if (conf == nullptr && hd == 4 && H == 8 && N <= 272 &&
+        (reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) % 16 == 0) {
+      const size_t per_set = (size_t)N * 208;
+      const int G = (int)std::max<size_t>(1, std::min<size_t>(56 * 1024 / per_set, 8));
+      const size_t smem = per_set * G;
+      static bool attr_set[64] = {};
+      int dev = 0;
+      MPL_CUDA(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        MPL_CUDA(cudaFuncSetAttribute(attention_kp_h4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 57 * 1024));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+      }
+      attention_kp_h4_kernel<<<(unsigned)ceil_div(sets, G), 256, smem, s>>>(qkv, out, sets, N, G, scale * 1.4426950408889634f);
+      MPL_LAUNCH_CHECK();
+      return MPL_OK;
     }
   }
   // (2) narrow heads: whole sets staged in shared memory
