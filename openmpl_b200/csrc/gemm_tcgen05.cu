@@ -77,8 +77,10 @@ __device__ __forceinline__ float round_tf32_dev(float x) {
 // (sum, sum of squares) of its column slice into a fixed slot -> no LayerNorm kernel, no atomics, bitwise reproducible.
 struct GemmLn {
   const float* colsum;      // [N]  sum_k bf16(W'[n,k])                       (EPI 4 / 5)
-  const float2* stats_in;   // [M, slots_in] partial (sum x, sum x^2) per row   (EPI 4 / 5)
-  float2* stats_out;        // [M, slots_out]                                   (EPI 6)
+  const float2* stats_in;   // [slots_in][stats_ld] partial (sum x, sum x^2) per row, slot-major: a warp's 32 rows of one
+                            // slot are one coalesced 256-byte access                           (EPI 4 / 5)
+  float2* stats_out;        // [slots_out][stats_ld]                                            (EPI 6)
+  int64_t stats_ld;         // rows per slot plane (M rounded up to a multiple of 256)
   __nv_bfloat16* xb;        // [M, N] bf16 copy of the updated residual         (EPI 6)
   float* y_raw;             // [M, N] the fp32 residual (read in the epilogue)  (EPI 6)
   int slots_in, slots_out;
@@ -309,11 +311,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // LayerNorm statistics of this lane's row from the producer's per-slice partial sums (fixed order: reproducible)
         float s1 = 0.f, s2 = 0.f;
         if (row_ok) {
-          const float2* sp = ln.stats_in + my_row * ln.slots_in;
+          const float2* sp = ln.stats_in + my_row;
           for (int i0 = 0; i0 < ln.slots_in; i0 += 16) {  // 16 independent loads in flight, summed in slot order
             float2 t[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] = (i0 + i < ln.slots_in) ? sp[i0 + i] : make_float2(0.f, 0.f);
+            for (int i = 0; i < 16; ++i) t[i] = (i0 + i < ln.slots_in) ? sp[(i0 + i) * ln.stats_ld] : make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 16; ++i) { s1 += t[i].x; s2 += t[i].y; }
           }
@@ -389,7 +391,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             s1[it] += __shfl_xor_sync(0xffffffffu, s1[it], o);
             s2[it] += __shfl_xor_sync(0xffffffffu, s2[it], o);
           }
-          if (c4 == 0) ln.stats_out[((int64_t)row0 + 4 * it + rs) * ln.slots_out + 2 * n_blk + half] = make_float2(s1[it], s2[it]);
+          if (c4 == 0) ln.stats_out[(2 * n_blk + half) * ln.stats_ld + row0 + 4 * it + rs] = make_float2(s1[it], s2[it]);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -612,6 +614,7 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
     ln.xb = reinterpret_cast<__nv_bfloat16*>(lnargs->xb);
     ln.y_raw = reinterpret_cast<float*>(Y);
     ln.slots_in = lnargs->slots_in;
+    ln.stats_ld = (int64_t)align_up((size_t)M, 256);
     ln.slots_out = gemm_ln_slots(N);
     ln.inv_k = 1.0f / (float)K;
     ln.eps = lnargs->eps;

@@ -114,10 +114,10 @@ int launch_to_tf32(const float* src, float* dst, int64_t n, cudaStream_t s);
 enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_LN_BIAS = 4, EPI_LN_BIAS_GELU = 5, EPI_RESIDUAL_EMIT = 6 };
 // LayerNorm fused around the bf16 projections (see gemm_tcgen05.cu):
 //   EPI_RESIDUAL_EMIT  Y(fp32) = Y + A W^T + bias, plus xb = bf16(Y) and per-row partial (sum, sum^2) into stats_out
-//                      [M, gemm_ln_slots(N)] float2.  Y, xb and stats_out must be ALLOCATED for M rounded up to a
+//                      [gemm_ln_slots(N)][M rounded up to 256] float2 (slot-major).  Y, xb and stats_out must be ALLOCATED for M rounded up to a
 //                      multiple of 256 rows (the epilogue reads and writes whole row tiles unpredicated), N % 32 == 0;
 //   EPI_LN_BIAS(_GELU) Y = act(rstd * (A W'^T - mu * colsum) + bias) with A = xb (raw residual rows), W' = W diag(gamma),
-//                      bias = b + W beta, (mu, rstd) from stats_in [M, slots_in].
+//                      bias = b + W beta, (mu, rstd) from stats_in [slots_in][M rounded up to 256].
 struct GemmLnArgs {
   const float* colsum;
   const void* stats_in;

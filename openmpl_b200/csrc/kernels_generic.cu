@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(256) ln_prep_kernel(const float* __restrict__ 
   }
   s = warp_sum(s);
   q = warp_sum(q);
-  for (int i = lane; i < slots; i += 32) stats[row * slots + i] = (i == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
+  const int64_t ld = (int64_t)((rows + 255) / 256 * 256);  // slot-major planes of `rows` rounded up to 256 (see gemm_tcgen05.cu)
+  for (int i = lane; i < slots; i += 32) stats[i * ld + row] = (i == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
 }
 
 int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, int64_t ldb, void* stats, int slots, int64_t rows, int C,
