@@ -254,6 +254,12 @@ class MultiView_MPL(nn.Module):
             n = last_shape[0] * last_shape[1]
             return [t[:, v] for v in range(V)], V * n
 
+        # Host inputs larger than one forward chunk: the host->device copy of chunk i+1 runs on a side stream while
+        # chunk i computes (same result, the copy disappears behind the kernels).
+        pipelined = self._pipeline_plan(poses, rays, centers, device)
+        if pipelined is not None:
+            return self._forward_pipelined(pipelined, device)
+
         p_list, p_stride = prep(poses, (J, 3), "poses")
         r_list, r_stride = prep(rays, (J, 3), "rays")
         c_list, c_stride = prep(centers, (1, 3), "centers")
@@ -279,6 +285,100 @@ class MultiView_MPL(nn.Module):
         if self.cfg.kw["head_kadkhod"]:
             return out, [aux[0], aux[1]]
         return out
+
+
+    # ---- pipelined host -> device staging ---------------------------------------------------------------------------
+    def _pipeline_plan(self, poses, rays, centers, device):
+        """(host tensors per kind, strides, B) when every input lives on the host, has the exact expected layout and
+        spans more than one forward chunk; None otherwise (the plain path validates and reports errors)."""
+        V, J = self.cfg.V, self.cfg.J
+        plan, B = {}, None
+        for kind, x, last in (("poses", poses, (J, 3)), ("rays", rays, (J, 3)), ("centers", centers, (1, 3))):
+            if x is None:
+                plan[kind] = None
+                continue
+            ts = list(x) if isinstance(x, (list, tuple)) else [x]
+            packed = not isinstance(x, (list, tuple))
+            want = ((V,) + last) if packed else last
+            for t in ts:
+                if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
+                        and t.dim() == len(want) + 1 and tuple(t.shape[1:]) == want):
+                    return None
+                if B is None:
+                    B = t.shape[0]
+                if t.shape[0] != B:
+                    return None
+            if not packed and len(ts) != V:
+                return None
+            plan[kind] = (ts, packed)
+        if plan["poses"] is None or B is None:
+            return None
+        if plan["rays"] is not None and plan["rays"][1] != plan["poses"][1]:
+            return None
+        chunk = int(_lib.lib().mpl_chunk_poses(self._get_handle(device.index)))
+        if B <= chunk:
+            return None
+        return plan, B, chunk
+
+    def _forward_pipelined(self, planned, device):
+        plan, B, chunk = planned
+        V, J = self.cfg.V, self.cfg.J
+        L = _lib.lib()
+        with torch.cuda.device(device):
+            st = self._state(device)
+            h = self._get_handle(device.index)
+            main = torch.cuda.current_stream(device)
+            side = st.get("copy_stream")
+            if side is None:
+                side = st["copy_stream"] = torch.cuda.Stream(device)
+            dev = {k: ([torch.empty(t.shape, dtype=torch.float32, device=device) for t in v[0]] if v is not None else None)
+                   for k, v in plan.items()}
+            side.wait_stream(main)                       # the fresh buffers may still be in use on the main stream
+            starts = list(range(0, B, chunk))
+            events = []
+            with torch.cuda.stream(side):
+                for b0 in starts:
+                    b1 = min(B, b0 + chunk)
+                    for k, v in plan.items():
+                        if v is not None:
+                            for d, t in zip(dev[k], v[0]):
+                                d[b0:b1].copy_(t[b0:b1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
+            out = torch.empty((B, J, 3), dtype=torch.float32, device=device)
+            kad = self.cfg.kw["head_kadkhod"]
+            aux = [torch.empty_like(out), torch.empty_like(out)] if kad else [None, None]
+            need = L.mpl_workspace_bytes(h, B)
+            ws = st["workspace"]
+            if ws is None or ws.numel() < need:
+                st["workspace"] = ws = torch.empty(need, dtype=torch.uint8, device=device)
+
+            def views(k, row):                             # per-view device tensors and the pose stride of kind k
+                if dev[k] is None:
+                    return None, 0
+                if plan[k][1]:
+                    return [dev[k][0][:, v] for v in range(V)], V * row
+                return dev[k], row
+
+            p_list, p_stride = views("poses", J * 3)
+            r_list, _ = views("rays", J * 3)
+            c_list, c_stride = views("centers", 3)
+            launches = 0
+            for ev, b0 in zip(events, starts):
+                b1 = min(B, b0 + chunk)
+                main.wait_event(ev)
+                arr = lambda ts: (ctypes.c_void_p * V)(*[t[b0:].data_ptr() for t in ts]) if ts is not None else None
+                _lib.check(L.mpl_forward(h, st["packed"].data_ptr(), arr(p_list), arr(r_list), arr(c_list), p_stride, c_stride,
+                                         out[b0:].data_ptr(), aux[0][b0:].data_ptr() if kad else None,
+                                         aux[1][b0:].data_ptr() if kad else None, b1 - b0, ws.data_ptr(), ws.numel(),
+                                         main.cuda_stream))
+                launches += int(L.mpl_last_launch_count(h))
+            for ts in dev.values():
+                for t in ts or []:
+                    t.record_stream(side)
+            self.last_launches = launches
+        return (out, [aux[0], aux[1]]) if kad else out
 
 
 class MultiView_MPL_G(nn.Module):

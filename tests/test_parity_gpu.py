@@ -205,3 +205,26 @@ def test_data_parallel_replicas_like_the_reference_runner(precision):
     torch.cuda.synchronize()
     assert out.shape == (64, 17, 3) and out.device.index == 0
     np.testing.assert_array_equal(out.cpu().numpy(), single)
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_pipelined_host_staging_equals_device_resident_inputs(packed):
+    """Host inputs spanning several forward chunks take the pipelined path (copy of chunk i+1 overlapped with the compute
+    of chunk i on a side stream); the result must be bitwise the result of the same call on device-resident inputs."""
+    case = CASES["cmu0_v2_d2"]
+    cfg, weights, _ = make_inputs(case)
+    batch = synth.make_batch(1000, synth.make_rig(cfg.V, "cmu"), seed=12)
+    m = build_module(case["kw"], weights, "bf16")
+    m.set_chunk_poses(256)                                           # 1000 = 3 * 256 + 232
+    ref = run_module(m, batch, packed=packed)[0]                     # device-resident inputs
+    V = cfg.V
+    if packed:
+        args = [torch.from_numpy(batch[k]).pin_memory() for k in ("poses", "rays", "centers")]
+    else:
+        args = [[torch.from_numpy(np.ascontiguousarray(batch[k][:, v])).pin_memory() for v in range(V)]
+                for k in ("poses", "rays", "centers")]
+    with torch.no_grad():
+        out = m(args[0], rays=args[1], centers=args[2])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    assert m.last_launches > 0
