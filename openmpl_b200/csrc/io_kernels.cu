@@ -2,6 +2,8 @@
 // the K5 fused head, written so that every global access is a 16-byte (or a coalesced 128-byte-per-warp) transaction
 // and the per-element index arithmetic of the generic kernels (kernels_generic.cu) disappears.  The generic kernels stay
 // as the path for odd widths / unaligned pointers; launch_* in kernels_generic.cu dispatch here first.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "kernels.cuh"
@@ -161,89 +163,109 @@ __global__ void __launch_bounds__(256) token_build_vec_kernel(const TokenArgs a)
 // 128-byte line); View_norm and the head LayerNorm reduce with shuffles only — no shared memory, no block barriers.
 // The E -> 3J Linear reads each weight row once per pose pair (L1-resident, 3J*E*4 = 111 KB) and reduces across lanes.
 // ---------------------------------------------------------------------------------------------------------------------
-// View_norm -> view-weighted sum -> head LayerNorm for TWO poses at once (independent load / reduction chains interleave)
+// View_norm -> view-weighted sum -> head LayerNorm of ONE pose, the views taken four at a time: all 4 x NV loads of a
+// group are in flight together and the four row reductions interleave (the kernel is latency bound on these loads).
 template <int NV, bool FULL>  // FULL: E == 32 * NV, no channel predicates
-__device__ __forceinline__ void head_pool_two(const HeadArgs& a, int64_t ba, int64_t bb, int lane, const int (&colv)[NV],
-                                              float (&pa)[NV], float (&pb)[NV]) {
+__device__ __forceinline__ void head_pool_pose(const HeadArgs& a, int64_t b, int lane, const int (&colv)[NV], float (&p)[NV]) {
   const int E = a.E;
   const float invE = 1.0f / (float)E;
   const float wmb = __ldg(a.wm_b);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { pa[i] = wmb; pb[i] = wmb; }
-  for (int v = 0; v < a.V; ++v) {
-    const float* ra = a.tok + (ba * a.V + v) * (int64_t)a.tok_w + lane;
-    const float* rb = a.tok + (bb * a.V + v) * (int64_t)a.tok_w + lane;
-    float xa[NV], xb[NV];
-    float sa = 0.f, sb = 0.f;
+  for (int i = 0; i < NV; ++i) p[i] = wmb;
+  for (int v0 = 0; v0 < a.V; v0 += 4) {
+    float x[4][NV];
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const bool ok = FULL || 32 * i + lane < E;
-      xa[i] = ok ? ra[colv[i]] : 0.f;
-      xb[i] = ok ? rb[colv[i]] : 0.f;
-      sa += xa[i];
-      sb += xb[i];
-    }
-    const float ma = warp_sum(sa) * invE, mb = warp_sum(sb) * invE;
-    float qa = 0.f, qb = 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const bool vok = v0 + u < a.V;
+      const float* r = a.tok + (b * a.V + min(v0 + u, a.V - 1)) * (int64_t)a.tok_w + lane;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const bool ok = FULL || 32 * i + lane < E;
-      const float ta = ok ? xa[i] - ma : 0.f, tb = ok ? xb[i] - mb : 0.f;
-      qa = fmaf(ta, ta, qa);
-      qb = fmaf(tb, tb, qb);
+      for (int i = 0; i < NV; ++i) {
+        x[u][i] = (vok && (FULL || 32 * i + lane < E)) ? r[colv[i]] : 0.f;
+        s[u] += x[u][i];
+      }
     }
-    const float rsa = rsqrtf(warp_sum(qa) * invE + 1e-6f), rsb = rsqrtf(warp_sum(qb) * invE + 1e-6f);
-    const float wv = __ldg(a.wm_w + v);
+    float m[4], q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m[u] = warp_sum(s[u]) * invE;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float d = (FULL || 32 * i + lane < E) ? x[u][i] - m[u] : 0.f;
+        q[u] = fmaf(d, d, q[u]);
+      }
+    float rs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rs[u] = (v0 + u < a.V) ? rsqrtf(warp_sum(q[u]) * invE + 1e-6f) * __ldg(a.wm_w + min(v0 + u, a.V - 1)) : 0.f;
+    const float wsum = ((v0 < a.V) ? __ldg(a.wm_w + v0) : 0.f) + ((v0 + 1 < a.V) ? __ldg(a.wm_w + v0 + 1) : 0.f) +
+                       ((v0 + 2 < a.V) ? __ldg(a.wm_w + v0 + 2) : 0.f) + ((v0 + 3 < a.V) ? __ldg(a.wm_w + v0 + 3) : 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int e = 32 * i + lane;
       if (FULL || e < E) {
-        const float g = __ldg(a.vn_w + e), bt = __ldg(a.vn_b + e);
-        pa[i] = fmaf(wv, fmaf((xa[i] - ma) * rsa, g, bt), pa[i]);
-        pb[i] = fmaf(wv, fmaf((xb[i] - mb) * rsb, g, bt), pb[i]);
+        // sum_v w_v ((x - m_v) rstd_v gamma + beta) = gamma * sum_v (w_v rstd_v)(x - m_v) + beta * sum_v w_v
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc = fmaf(rs[u], x[u][i] - m[u], acc);
+        p[i] += fmaf(acc, __ldg(a.vn_w + e), wsum * __ldg(a.vn_b + e));
       }
     }
   }
-  float sa = 0.f, sb = 0.f;
+  float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { const bool ok = FULL || 32 * i + lane < E; sa += ok ? pa[i] : 0.f; sb += ok ? pb[i] : 0.f; }
-  const float ma = warp_sum(sa) * invE, mb = warp_sum(sb) * invE;
-  float qa = 0.f, qb = 0.f;
+  for (int i = 0; i < NV; ++i) s += (FULL || 32 * i + lane < E) ? p[i] : 0.f;
+  const float mean = warp_sum(s) * invE;
+  float q = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const bool ok = FULL || 32 * i + lane < E;
-    const float ta = ok ? pa[i] - ma : 0.f, tb = ok ? pb[i] - mb : 0.f;
-    qa = fmaf(ta, ta, qa);
-    qb = fmaf(tb, tb, qb);
+    const float d = (FULL || 32 * i + lane < E) ? p[i] - mean : 0.f;
+    q = fmaf(d, d, q);
   }
-  const float rsa = rsqrtf(warp_sum(qa) * invE + 1e-5f), rsb = rsqrtf(warp_sum(qb) * invE + 1e-5f);  // head LN: eps 1e-5 (multiview_mpl.py:284)
+  const float rstd = rsqrtf(warp_sum(q) * invE + 1e-5f);  // head LayerNorm: default eps (multiview_mpl.py:284)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int e = 32 * i + lane;
-    const float g = (FULL || e < E) ? __ldg(a.hn_w + e) : 0.f, bt = (FULL || e < E) ? __ldg(a.hn_b + e) : 0.f;
-    pa[i] = fmaf((pa[i] - ma) * rsa, g, bt);
-    pb[i] = fmaf((pb[i] - mb) * rsb, g, bt);
+    p[i] = (FULL || e < E) ? fmaf((p[i] - mean) * rstd, __ldg(a.hn_w + e), __ldg(a.hn_b + e)) : 0.f;
   }
 }
 
-// One CTA (8 warps) per group of HEAD_PB poses.
-//   Phase 1: each warp pools its 4 poses (View_norm -> view-weighted sum -> head LayerNorm, registers + shuffles only,
-//            lane = channel % 32) and parks the result in shared memory as pool[channel][pose].
-//   Phase 2: the E channels are split over the warps; lane l owns outputs l and l + 32 of ALL 32 poses, so every element
-//            of the transposed, 64-padded head weight is read once per 32 poses (coalesced) and feeds 64 FMAs; the pooled
-//            values of a channel arrive as eight broadcast 16-byte shared-memory loads.
-//   Phase 3: the 8 per-warp partial sums of every (pose, output) are added in a fixed order through shared memory.
-constexpr int HEAD_PB = 16;       // poses per CTA iteration (16: pooled values + exchange buffer stay at 35 KB per CTA, so the
-                                  // 139 KB transposed head weight remains L1-resident next to two CTAs per SM)
+// One CTA (8 warps) per group of 16 poses (= one MMA row tile).
+//   Phase 1: each warp pools two poses, one after the other, four views in flight at a time (ray-half strip -> View_norm -> view-weighted sum -> head LayerNorm; registers +
+//            shuffles only, lane = channel % 32) and parks the result in shared memory as pool[pose][channel].
+//   Phase 2: the E -> 3J Linear on the tensor cores at fp32-grade accuracy: both operands are split into fp16 hi + lo
+//            parts (x = hi + lo to ~2^-22; the weights are scaled by 2^10 first so their lo parts stay normal) and every
+//            product is three mma.sync m16n8k16 (hi*hi + hi*lo + lo*hi, fp32 accumulate).  The k tiles are dealt round-
+//            robin to the warps; the pre-split weights sit in fragment order (one 16-byte load per lane, k tile and n tile).
+//   Phase 3: the per-warp partial tiles are added in a fixed order through shared memory, the bias is added, 3J floats
+//            per pose are written.
+// The head serves every precision mode, hence the split: a single bf16 / fp16 product would cost ~2e-3 of output scale.
+constexpr int HEAD_PB = 16;
 constexpr int HEAD_WARPS = 8;
+constexpr float HEAD_WSCALE = 1024.0f;
+
+__device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma_f16_acc(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 template <int NV, bool FULL>
 __global__ void __launch_bounds__(HEAD_WARPS * 32, 2) head_block_kernel(const HeadArgs a) {
-  extern __shared__ __align__(16) float hsm[];  // pool [E][HEAD_PB]; reused as partial [HEAD_WARPS][HEAD_PB][64]
+  extern __shared__ __align__(16) float hsm[];  // pool [HEAD_PB][pitch]; reused as partial [HEAD_WARPS][HEAD_PB][64]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int E = a.E;
+  const int pitch = E + 8;          // (E + 8) % 32 == 8 for E % 32 == 0: conflict-free 8-byte A-fragment loads
+  const int ktiles = E >> 4, ntiles = (a.out_dim + 7) >> 3;
   const int64_t groups = (a.B + HEAD_PB - 1) / HEAD_PB;
-  const int e_per_warp = (E + HEAD_WARPS - 1) / HEAD_WARPS;
   // column of channel group i in the token row: 32-channel segments seg_stride apart (ray halves stripped, d = 32) or
   // one contiguous row (seg_len == E, seg_stride == 32 passed by the launcher): one multiply, no division
   int colv[NV];
@@ -253,50 +275,37 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, 2) head_block_kernel(const He
     const int64_t b0 = gi * HEAD_PB;
     // ---- phase 1 ----
 #pragma unroll 1
-    for (int pi = 0; pi < HEAD_PB / HEAD_WARPS; pi += 2) {
-      const int p0 = warp * (HEAD_PB / HEAD_WARPS) + pi;
-      float pa[NV], pb[NV];
-      head_pool_two<NV, FULL>(a, min(b0 + p0, a.B - 1), min(b0 + p0 + 1, a.B - 1), lane, colv, pa, pb);
+    for (int pi = 0; pi < 2; ++pi) {
+      const int p0 = warp * 2 + pi;
+      float pp[NV];
+      head_pool_pose<NV, FULL>(a, min(b0 + p0, a.B - 1), lane, colv, pp);
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        if (FULL || 32 * i + lane < E) *reinterpret_cast<float2*>(hsm + (32 * i + lane) * HEAD_PB + p0) = make_float2(pa[i], pb[i]);
+        if (FULL || 32 * i + lane < E) hsm[p0 * pitch + 32 * i + lane] = pp[i];
     }
     __syncthreads();
     // ---- phase 2 ----
-    float acc0[HEAD_PB], acc1[HEAD_PB];
+    float acc[8][4];
 #pragma unroll
-    for (int p = 0; p < HEAD_PB; ++p) { acc0[p] = 0.f; acc1[p] = 0.f; }
-    const int e_lo = warp * e_per_warp, e_hi = min(E, e_lo + e_per_warp);
-    const float* wt = a.hwT + lane;
-    // weights of 4 channels are fetched (L2 / L1) one 4-channel step ahead of their use
-    float wn[4][2];
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+    for (int kt = warp; kt < ktiles; kt += HEAD_WARPS) {
+      const float* r0 = hsm + g * pitch + 16 * kt + 2 * t;
+      const float* r1 = r0 + 8 * pitch;
+      const float2 x0 = *reinterpret_cast<const float2*>(r0), x1 = *reinterpret_cast<const float2*>(r1);
+      const float2 x2 = *reinterpret_cast<const float2*>(r0 + 8), x3 = *reinterpret_cast<const float2*>(r1 + 8);
+      uint32_t ah[4], al[4];
+      split_f16(x0.x, x0.y, ah[0], al[0]);
+      split_f16(x1.x, x1.y, ah[1], al[1]);
+      split_f16(x2.x, x2.y, ah[2], al[2]);
+      split_f16(x3.x, x3.y, ah[3], al[3]);
+      const uint4* wb = reinterpret_cast<const uint4*>(a.hwT) + ((size_t)kt * ntiles) * 32 + lane;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = min(e_lo + u, E - 1);
-      wn[u][0] = __ldg(wt + e * 64); wn[u][1] = __ldg(wt + e * 64 + 32);
-    }
-#pragma unroll 1
-    for (int e4 = e_lo; e4 < e_hi; e4 += 4) {
-      float wc[4][2];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { wc[u][0] = wn[u][0]; wc[u][1] = wn[u][1]; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = min(e4 + 4 + u, E - 1);
-        wn[u][0] = __ldg(wt + e * 64); wn[u][1] = __ldg(wt + e * 64 + 32);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (e4 + u >= e_hi) break;
-        const float w0 = wc[u][0], w1 = wc[u][1];
-        const float4* pv = reinterpret_cast<const float4*>(hsm + (e4 + u) * HEAD_PB);
-#pragma unroll
-        for (int p4 = 0; p4 < HEAD_PB / 4; ++p4) {
-          const float4 v = pv[p4];
-          acc0[4 * p4] = fmaf(v.x, w0, acc0[4 * p4]);         acc1[4 * p4] = fmaf(v.x, w1, acc1[4 * p4]);
-          acc0[4 * p4 + 1] = fmaf(v.y, w0, acc0[4 * p4 + 1]); acc1[4 * p4 + 1] = fmaf(v.y, w1, acc1[4 * p4 + 1]);
-          acc0[4 * p4 + 2] = fmaf(v.z, w0, acc0[4 * p4 + 2]); acc1[4 * p4 + 2] = fmaf(v.z, w1, acc1[4 * p4 + 2]);
-          acc0[4 * p4 + 3] = fmaf(v.w, w0, acc0[4 * p4 + 3]); acc1[4 * p4 + 3] = fmaf(v.w, w1, acc1[4 * p4 + 3]);
+      for (int nt = 0; nt < 8; ++nt) {
+        if (nt < ntiles) {
+          const uint4 w = __ldg(wb + nt * 32);  // (hi b0, hi b1, lo b0, lo b1)
+          mma_f16_acc(acc[nt], ah, w.x, w.y);
+          mma_f16_acc(acc[nt], ah, w.z, w.w);
+          mma_f16_acc(acc[nt], al, w.x, w.y);
         }
       }
     }
@@ -304,30 +313,38 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, 2) head_block_kernel(const He
     // ---- phase 3 ----
     float* part = hsm + (size_t)warp * HEAD_PB * 64;
 #pragma unroll
-    for (int p = 0; p < HEAD_PB; ++p) {
-      part[p * 64 + lane] = acc0[p];
-      part[p * 64 + 32 + lane] = acc1[p];
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<float2*>(part + g * 64 + 8 * nt + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(part + (g + 8) * 64 + 8 * nt + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < HEAD_PB * 64; idx += HEAD_WARPS * 32) {
       const int p = idx >> 6, o = idx & 63;
       if (o < a.out_dim && b0 + p < a.B) {
-        float sum = __ldg(a.hb + o);
+        float sum = 0.f;
 #pragma unroll
         for (int w = 0; w < HEAD_WARPS; ++w) sum += hsm[(size_t)w * HEAD_PB * 64 + idx];
-        a.out[(b0 + p) * a.out_dim + o] = sum;
+        a.out[(b0 + p) * a.out_dim + o] = fmaf(sum, 1.0f / HEAD_WSCALE, __ldg(a.hb + o));
       }
     }
     __syncthreads();  // the buffer is reused by the next group
   }
 }
 
-// head.1.weight [out_dim, E] -> transposed and padded [E, 64] (pack time)
-__global__ void head_transpose_kernel(const float* __restrict__ W, float* __restrict__ WT, int out_dim, int E) {
+// head.1.weight [out_dim, E] -> fp16 hi / lo parts of 2^10 * W in mma B-fragment order: [k tile][n tile][lane] x uint4
+// (hi b0, hi b1, lo b0, lo b1), b0 = W[8nt+g][16kt+2t, +1], b1 = W[8nt+g][16kt+2t+8, +9]   (pack time)
+__global__ void head_transpose_kernel(const float* __restrict__ W, uint4* __restrict__ WB, int out_dim, int E) {
+  const int ntiles = (out_dim + 7) >> 3, ktiles = E >> 4;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= E * 64) return;
-  const int e = idx >> 6, o = idx & 63;
-  WT[idx] = (o < out_dim) ? W[(int64_t)o * E + e] : 0.f;
+  if (idx >= ktiles * ntiles * 32) return;
+  const int lane = idx & 31, nt = (idx >> 5) % ntiles, kt = (idx >> 5) / ntiles;
+  const int g = lane >> 2, t = lane & 3;
+  const int n = 8 * nt + g, k = 16 * kt + 2 * t;
+  auto w = [&](int kk) { return n < out_dim ? W[(int64_t)n * E + kk] * HEAD_WSCALE : 0.f; };
+  uint4 o;
+  split_f16(w(k), w(k + 1), o.x, o.z);
+  split_f16(w(k + 8), w(k + 9), o.y, o.w);
+  WB[idx] = o;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -369,10 +386,10 @@ int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s) {
 }
 
 int try_launch_head_warp(const HeadArgs& a, cudaStream_t s) {
-  if (a.E > 32 * 17 || a.out_dim > 64 || a.hwT == nullptr || !(a.seg_len == 32 || a.seg_len == a.E)) return 1;
+  if (a.E > 32 * 17 || a.E % 32 != 0 || a.out_dim > 64 || a.hwT == nullptr || !(a.seg_len == 32 || a.seg_len == a.E)) return 1;
   if (a.B == 0) return MPL_OK;
   const int64_t blocks = std::min<int64_t>(ceil_div(a.B, HEAD_PB), (int64_t)kNumSMs * 2);
-  const size_t smem = std::max((size_t)a.E * HEAD_PB, (size_t)HEAD_WARPS * HEAD_PB * 64) * sizeof(float);
+  const size_t smem = std::max((size_t)(a.E + 8) * HEAD_PB, (size_t)HEAD_WARPS * HEAD_PB * 64) * sizeof(float);
   static bool attr_set[64][3] = {};
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
@@ -390,7 +407,8 @@ int try_launch_head_warp(const HeadArgs& a, cudaStream_t s) {
 }
 
 int launch_head_transpose(const float* W, float* WT, int out_dim, int E, cudaStream_t s) {
-  head_transpose_kernel<<<(unsigned)ceil_div((int64_t)E * 64, 256), 256, 0, s>>>(W, WT, out_dim, E);
+  const int64_t n = (int64_t)(E >> 4) * ((out_dim + 7) >> 3) * 32;
+  head_transpose_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(W, reinterpret_cast<uint4*>(WT), out_dim, E);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

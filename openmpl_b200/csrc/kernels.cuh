@@ -95,7 +95,8 @@ struct HeadArgs {
   const float* wm_w; const float* wm_b;  // weighted_mean (Conv1d) [V], [1]
   const float* hn_w; const float* hn_b;  // head.0 LayerNorm
   const float* hw;   const float* hb;    // head.1 Linear [out_dim, E]
-  const float* hwT;                      // the same weight transposed and padded to [E, 64] (or null: generic kernel)
+  const float* hwT;                      // the same weight x 2^10, split into fp16 hi / lo parts in mma B-fragment order
+                                         // (launch_head_transpose; E * 64 floats reserved), or null: generic kernel
   float* out;                            // [B, out_dim]
 };
 int launch_head_fused(const HeadArgs& a, cudaStream_t s);
