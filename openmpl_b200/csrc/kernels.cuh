@@ -156,6 +156,10 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
                      const float* sn_w, const float* sn_b, const float* conf, int conf_weighted, const SptIo* io,
                      int precise, cudaStream_t s);  // precise: fp32 softmax arithmetic + exact erf GELU (tf32 mode)
 
+// the keypoint-token FPT stack (FPT_blocks_view_keypoint_tokens, width 32, 8 heads, bf16 mode) as one launch of the
+// same kernel: tok [B, V * 17, 32] fp32 in place, wpack = [depth] layers packed by launch_spt_pack_layer from blocks.{l}.*
+int launch_fpt_kp_fused(float* tok, const void* wpack, int V, int64_t B, int depth, cudaStream_t s);
+
 // ---- metric + input builder -----------------------------------------------------------------------------------------
 int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t B, int J, float unit_scale,
                             double* acc, cudaStream_t s);

@@ -60,6 +60,7 @@ struct MplModel {
   bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
   bool spt_fused;  // the SPT stack runs as the single fused fp16-mma kernel (bf16 / tf32 modes, d=32, H=8, J=17)
   bool ln_fused;   // bf16 mode: the FPT LayerNorms are folded into the projection GEMMs (no LayerNorm kernel)
+  bool fpt_kp_fused;  // bf16 mode, keypoint-token FPT (width 32, 8 heads, J = 17): the whole FPT stack is one kernel launch
   int ln_slots;    // statistics slots per row written by the residual-emit GEMMs
   std::vector<ParamInfo> params;
   std::unordered_map<std::string, int> index;
@@ -234,6 +235,7 @@ static void build_tables(MplModel* m) {
     const int stacks = m->multi ? V : 1;
     for (int st = 0; st < stacks; ++st) add_derived(m, "sptpack:" + std::to_string(st), (int64_t)m->depth * spt_fused_layer_bytes(), 1);
   }
+  if (m->fpt_kp_fused) add_derived(m, "fptpack", (int64_t)m->depth * spt_fused_layer_bytes(), 1);
   if (m->fpt_tc) {
     const int esz = (d.precision == MPL_PREC_BF16) ? 2 : 4;
     const char* tag = (d.precision == MPL_PREC_BF16) ? "bf16:" : "tf32:";
@@ -314,7 +316,7 @@ static Workspace layout_workspace(const MplModel* m, int64_t Bc, uint8_t* base) 
   // LayerNorm-fused mode: the residual-emit epilogue touches whole 256-row tiles -> rows padded (pad rows are scratch)
   const int64_t tok_rows_pad = m->ln_fused ? (int64_t)align_up((size_t)(Bc * m->fpt_tokens), 256) * m->fpt_dim : 0;
   w.tok = (float*)take(std::max<int64_t>(Bc * (int64_t)m->V * m->tok_w, tok_rows_pad) * 4);
-  if (!m->d.no_transformer_fpt) {
+  if (!m->d.no_transformer_fpt && !m->fpt_kp_fused) {
     const int64_t Rf = m->ln_fused ? (int64_t)align_up((size_t)(Bc * m->fpt_tokens), 256) : Bc * m->fpt_tokens;
     const int64_t D = m->fpt_dim, Hf = m->fpt_hidden;
     const int esz = (m->fpt_tc && m->d.precision == MPL_PREC_BF16) ? 2 : 4;
@@ -343,7 +345,7 @@ static Workspace layout_workspace(const MplModel* m, int64_t Bc, uint8_t* base) 
 // ---- forward ---------------------------------------------------------------------------------------------------------
 enum ProfCat {
   CAT_EMBED = 0, CAT_SPT_LN, CAT_SPT_LINEAR, CAT_SPT_ATTN, CAT_TOKEN, CAT_FPT_LN, CAT_FPT_QKV, CAT_FPT_ATTN, CAT_FPT_PROJ,
-  CAT_FPT_FC1, CAT_FPT_FC2, CAT_HEAD, CAT_SPT_FUSED, CAT_COUNT
+  CAT_FPT_FC1, CAT_FPT_FC2, CAT_HEAD, CAT_SPT_FUSED, CAT_FPT_FUSED, CAT_COUNT
 };
 
 static cudaEvent_t prof_event(MplModel* m) {
@@ -587,7 +589,9 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   }
   if (!fuse_token) LC(CAT_TOKEN, launch_token_build(ta, s));
   // ---- FPT blocks (multiview_mpl.py:416-423) ----
-  if (!d.no_transformer_fpt && m->depth > 0) {
+  if (m->fpt_kp_fused) {
+    LC(CAT_FPT_FUSED, launch_fpt_kp_fused(w.tok, P.dv("fptpack"), V, Bc, m->depth, s));
+  } else if (!d.no_transformer_fpt && m->depth > 0) {
     const int D = m->fpt_dim, N = m->fpt_tokens;
     const int hd = D / m->H;
     const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
@@ -727,8 +731,11 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
   }
   m->spt_fused = d.precision != MPL_PREC_FP32 && !d.no_transformer_spt && m->depth > 0 &&
                  spt_fused_supports(m->J, m->dim, m->H, m->spt_hidden);
+  // keypoint-token FPT: same block shape as the SPT (width 32, 8 heads, hidden 64, sets of 17 rows) -> same kernel, grouped
+  m->fpt_kp_fused = d.precision == MPL_PREC_BF16 && d.FPT_blocks_view_keypoint_tokens && !d.no_transformer_fpt && m->depth > 0 &&
+                    m->V <= 16 && spt_fused_supports(m->J, m->fpt_dim, m->H, m->fpt_hidden);
   m->fpt_tc = false;
-  if (d.precision != MPL_PREC_FP32 && !d.no_transformer_fpt && m->depth > 0) {
+  if (d.precision != MPL_PREC_FP32 && !d.no_transformer_fpt && m->depth > 0 && !m->fpt_kp_fused) {
     const bool ok = gemm_tcgen05_supports(3 * m->fpt_dim, m->fpt_dim, d.precision) &&
                     gemm_tcgen05_supports(m->fpt_dim, m->fpt_dim, d.precision) &&
                     gemm_tcgen05_supports(m->fpt_hidden, m->fpt_dim, d.precision) &&
@@ -772,7 +779,7 @@ int mpl_profile_categories(void) { return CAT_COUNT; }
 const char* mpl_profile_category_name(int cat) {
   static const char* names[CAT_COUNT] = {"embed", "spt_layernorm", "spt_linear", "spt_attention", "token_build", "fpt_layernorm",
                                          "fpt_gemm_qkv", "fpt_attention", "fpt_gemm_proj", "fpt_gemm_fc1", "fpt_gemm_fc2", "head",
-                                         "spt_fused"};
+                                         "spt_fused", "fpt_kp_fused"};
   return (cat >= 0 && cat < CAT_COUNT) ? names[cat] : "";
 }
 
@@ -877,6 +884,18 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
                                       P.f(p + "mlp.fc1.weight"), P.f(p + "mlp.fc1.bias"), P.f(p + "mlp.fc2.weight"),
                                       P.f(p + "mlp.fc2.bias"), spt_scale, base + dd.offset + (size_t)l * spt_fused_layer_bytes(), s));
       }
+    }
+  }
+  if (m->fpt_kp_fused) {
+    const Derived& dd = m->derived[m->dindex.at("fptpack")];
+    const float kp_scale = m->d.qk_scale != 0.f ? m->d.qk_scale : 1.0f / sqrtf((float)(m->fpt_dim / m->H));
+    for (int l = 0; l < m->depth; ++l) {
+      const std::string p = "blocks." + std::to_string(l) + ".";
+      MPL_TRY(launch_spt_pack_layer(P.f(p + "norm1.weight"), P.f(p + "norm1.bias"), P.f(p + "attn.qkv.weight"),
+                                    m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr, P.f(p + "attn.proj.weight"),
+                                    P.f(p + "attn.proj.bias"), P.f(p + "norm2.weight"), P.f(p + "norm2.bias"),
+                                    P.f(p + "mlp.fc1.weight"), P.f(p + "mlp.fc1.bias"), P.f(p + "mlp.fc2.weight"),
+                                    P.f(p + "mlp.fc2.bias"), kp_scale, base + dd.offset + (size_t)l * spt_fused_layer_bytes(), s));
     }
   }
   if (m->fpt_tc) {

@@ -128,6 +128,9 @@ struct SptArgs {
   int64_t B;
   int depth;
   int conf_weighted;                  // the confidence-weighted extra pass per block is live
+  int group;                          // GROUPED: sets attending together (V views of a pose); 1 in the SPT
+  int rows_used;                      // rows of a CTA tile that carry data: ROWS, or (16 / group) * group * 17 when GROUPED
+  int final_norm;                     // apply Spatial_norm at the end (SPT) or store the residual as is (GROUPED)
   SptIo io;                           // fused K1 embedding in front, fused FPT token build behind
 };
 
@@ -159,7 +162,12 @@ __device__ __forceinline__ __half2 ex2_h2(__half2 x) {
 // (measured: __maxnreg__(112) removes the spills but only one CTA then fits per SM -> 16.3 ms instead of 13.2 ms per step)
 // PRECISE (tf32 mode): softmax / PV arithmetic in fp32 on the fp16-staged q, k, v and the exact erf GELU -- every
 // rounding left is a 2^-11 operand rounding, the same class as kind::tf32's; bf16 mode takes the packed-half2 forms.
-template <bool PRECISE>
+// GROUPED: the same block stack as the keypoint-token FPT (FPT_blocks_view_keypoint_tokens: tokens = V * 17 joints of one
+// pose, width 32, one weight stack, multiview_mpl.py:261-266,416-423,496-497): `group` = V consecutive 17-row sets attend
+// together, so the whole V * J <= 136-token set of a pose lives in this CTA's shared memory for all depth + 1 block
+// applications; keys are walked in two passes (max, then exp2 / sum / PV with the scores recomputed), fp16 partial
+// sums flushed into fp32 every 17 keys.  Rows come from and go back to the fp32 token buffer in place.
+template <bool PRECISE, bool GROUPED>
 __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem);
@@ -182,9 +190,9 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
     lr[mt] = warp * 32 + mt * 16 + g;
-    const int64_t gr0 = tile * ROWS + lr[mt], gr1 = gr0 + 8;
-    ok[mt][0] = lr[mt] < ROWS && gr0 < rows_in_view;
-    ok[mt][1] = lr[mt] + 8 < ROWS && gr1 < rows_in_view;
+    const int64_t gr0 = tile * args.rows_used + lr[mt], gr1 = gr0 + 8;
+    ok[mt][0] = lr[mt] < args.rows_used && gr0 < rows_in_view;
+    ok[mt][1] = lr[mt] + 8 < args.rows_used && gr1 < rows_in_view;
     if (args.x_in != nullptr) {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
   const int aset0 = aset * J;  // first row of the set
   float aconf_a = 1.0f, aconf_b = 1.0f;
   if (args.conf_weighted) {
-    const int64_t ga = tile * ROWS + ra, gb = tile * ROWS + rb;
+    const int64_t ga = tile * args.rows_used + ra, gb = tile * args.rows_used + rb;
     if (ga < rows_in_view) aconf_a = args.conf != nullptr ? __ldg(args.conf + view_row0 + ga) : pose_conf(args, view, ga);
     if (gb < rows_in_view) aconf_b = args.conf != nullptr ? __ldg(args.conf + view_row0 + gb) : pose_conf(args, view, gb);
   }
@@ -272,7 +280,72 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
       }
       __syncthreads();
       // ---- attention: softmax(q k^T * scale) v over the 17 tokens of the row's set; two heads per half2 lane pair ----
-      if constexpr (PRECISE) {
+      if constexpr (GROUPED) {
+        if (aset * J < args.rows_used) {
+          const int g0row = (aset / args.group) * args.group * J;  // first row of the pose's token set
+          const int nkeys = args.group * J;
+          uint4* rowpa = reinterpret_cast<uint4*>(qkv_w + ra * QPW);
+          uint4* rowpb = reinterpret_cast<uint4*>(qkv_w + rb * QPW);
+          const uint4* setp = reinterpret_cast<const uint4*>(qkv_w + g0row * QPW);
+          constexpr int RP4 = QPW / 4;
+#pragma unroll 1
+          for (int pp = 0; pp < 2; ++pp) {
+            const int p = ahh + 2 * pp;
+            const uint4 qa = rowpa[p], qb = rowpb[p];
+            __half2 mxa = __float2half2_rn(-60000.f), mxb = mxa;
+            for (int j = 0; j < nkeys; ++j) {
+              const uint4 k = setp[j * RP4 + 4 + p];
+              __half2 s0 = __hmul2(h2(qa.x), h2(k.x)), s1 = __hmul2(h2(qb.x), h2(k.x));
+              s0 = __hfma2(h2(qa.y), h2(k.y), s0); s1 = __hfma2(h2(qb.y), h2(k.y), s1);
+              s0 = __hfma2(h2(qa.z), h2(k.z), s0); s1 = __hfma2(h2(qb.z), h2(k.z), s1);
+              s0 = __hfma2(h2(qa.w), h2(k.w), s0); s1 = __hfma2(h2(qb.w), h2(k.w), s1);
+              mxa = __hmax2(mxa, s0);
+              mxb = __hmax2(mxb, s1);
+            }
+            float2 fsa = make_float2(0.f, 0.f), fsb = fsa;
+            float2 oa[4], ob[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) { oa[d] = make_float2(0.f, 0.f); ob[d] = oa[d]; }
+            for (int j0 = 0; j0 < nkeys; j0 += J) {
+              const __half2 z = __float2half2_rn(0.f);
+              __half2 suma = z, a0 = z, a1 = z, a2 = z, a3 = z, sumb = z, b0 = z, b1 = z, b2 = z, b3 = z;
+#pragma unroll
+              for (int jj = 0; jj < J; ++jj) {
+                const int j = j0 + jj;
+                const uint4 k = setp[j * RP4 + 4 + p];
+                const uint4 v = setp[j * RP4 + 8 + p];
+                __half2 s0 = __hmul2(h2(qa.x), h2(k.x)), s1 = __hmul2(h2(qb.x), h2(k.x));
+                s0 = __hfma2(h2(qa.y), h2(k.y), s0); s1 = __hfma2(h2(qb.y), h2(k.y), s1);
+                s0 = __hfma2(h2(qa.z), h2(k.z), s0); s1 = __hfma2(h2(qb.z), h2(k.z), s1);
+                s0 = __hfma2(h2(qa.w), h2(k.w), s0); s1 = __hfma2(h2(qb.w), h2(k.w), s1);
+                const __half2 ea = ex2_h2(__hsub2(s0, mxa)), eb = ex2_h2(__hsub2(s1, mxb));
+                suma = __hadd2(suma, ea); sumb = __hadd2(sumb, eb);
+                a0 = __hfma2(ea, h2(v.x), a0); b0 = __hfma2(eb, h2(v.x), b0);
+                a1 = __hfma2(ea, h2(v.y), a1); b1 = __hfma2(eb, h2(v.y), b1);
+                a2 = __hfma2(ea, h2(v.z), a2); b2 = __hfma2(eb, h2(v.z), b2);
+                a3 = __hfma2(ea, h2(v.w), a3); b3 = __hfma2(eb, h2(v.w), b3);
+              }
+              auto flush = [](float2& acc, __half2 h) { const float2 f = __half22float2(h); acc.x += f.x; acc.y += f.y; };
+              flush(fsa, suma); flush(oa[0], a0); flush(oa[1], a1); flush(oa[2], a2); flush(oa[3], a3);
+              flush(fsb, sumb); flush(ob[0], b0); flush(ob[1], b1); flush(ob[2], b2); flush(ob[3], b3);
+            }
+            {
+              const float i0 = 1.0f / fsa.x, i1 = 1.0f / fsa.y;
+              uint4 o;
+              o.x = pack_f16(oa[0].x * i0, oa[0].y * i1); o.y = pack_f16(oa[1].x * i0, oa[1].y * i1);
+              o.z = pack_f16(oa[2].x * i0, oa[2].y * i1); o.w = pack_f16(oa[3].x * i0, oa[3].y * i1);
+              rowpa[p] = o;
+            }
+            if (two) {
+              const float i0 = 1.0f / fsb.x, i1 = 1.0f / fsb.y;
+              uint4 o;
+              o.x = pack_f16(ob[0].x * i0, ob[0].y * i1); o.y = pack_f16(ob[1].x * i0, ob[1].y * i1);
+              o.z = pack_f16(ob[2].x * i0, ob[2].y * i1); o.w = pack_f16(ob[3].x * i0, ob[3].y * i1);
+              rowpb[p] = o;
+            }
+          }
+        }
+      } else       if constexpr (PRECISE) {
         uint4* rowps[2] = {reinterpret_cast<uint4*>(qkv_w + ra * QPW), reinterpret_cast<uint4*>(qkv_w + rb * QPW)};
         const float rsc[2] = {weighted ? aconf_a : 1.0f, weighted ? aconf_b : 1.0f};
         const uint4* setp = reinterpret_cast<const uint4*>(qkv_w + aset0 * QPW);
@@ -444,10 +517,14 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
       q1 += d2 * d2 + d3 * d3;
     }
     const float rs0 = rsqrtf(quad_sum(q0) * (1.0f / D) + 1e-6f), rs1 = rsqrtf(quad_sum(q1) * (1.0f / D) + 1e-6f);
-    const int64_t gr0 = tile * ROWS + lr[mt], gr1 = gr0 + 8;
+    const int64_t gr0 = tile * args.rows_used + lr[mt], gr1 = gr0 + 8;
     float y[4][4];  // Spatial_norm output, same fragment layout as x
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
+      if (!args.final_norm) {  // GROUPED: there is no norm behind the FPT stack, the residual goes out as is
+        y[nt][0] = x[mt][nt][0]; y[nt][1] = x[mt][nt][1]; y[nt][2] = x[mt][nt][2]; y[nt][3] = x[mt][nt][3];
+        continue;
+      }
       const float2 wg = __ldg(reinterpret_cast<const float2*>(args.sn_w + 8 * nt + 2 * t));
       const float2 bg = __ldg(reinterpret_cast<const float2*>(args.sn_b + 8 * nt + 2 * t));
       y[nt][0] = (x[mt][nt][0] - m0) * rs0 * wg.x + bg.x; y[nt][1] = (x[mt][nt][1] - m0) * rs0 * wg.y + bg.y;
@@ -596,6 +673,9 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
   a.x_in = x_in;
   a.x_out = x_out;
   a.conf_weighted = conf_weighted;
+  a.group = 1;
+  a.rows_used = ROWS;
+  a.final_norm = 1;
   if (io != nullptr) a.io = *io;
   for (int v = 0; v < V; ++v) a.wpack[v] = reinterpret_cast<const uint32_t*>(wpack_per_view[v]);
   a.sn_w = sn_w;
@@ -606,12 +686,44 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
   static bool attr_set[64][2] = {};  // per device: function attributes live in the device's context (DataParallel replicas)
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
-  auto kern = precise ? spt_fused_kernel<true> : spt_fused_kernel<false>;
+  auto kern = precise ? spt_fused_kernel<true, false> : spt_fused_kernel<false, false>;
   if (dev < 0 || dev >= 64 || !attr_set[dev][precise ? 1 : 0]) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     if (dev >= 0 && dev < 64) attr_set[dev][precise ? 1 : 0] = true;
   }
   dim3 grid((unsigned)ceil_div(B, SETS), (unsigned)V);
+  kern<<<grid, THREADS, SMEM_TOTAL, s>>>(a);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// The keypoint-token FPT stack (bf16 mode) in one launch: tok [B, V * 17, 32] fp32 updated in place by depth + 1 block
+// applications (last block twice, multiview_mpl.py:420-423), attention over the V * 17 tokens of each pose.
+int launch_fpt_kp_fused(float* tok, const void* wpack, int V, int64_t B, int depth, cudaStream_t s) {
+  if (B == 0 || depth == 0) return MPL_OK;
+  if (V < 1 || V > SETS) {
+    set_error("launch_fpt_kp_fused: %d views do not fit one CTA tile of %d sets", V, SETS);
+    return MPL_ERR_UNSUPPORTED;
+  }
+  SptArgs a{};
+  a.x_in = tok;
+  a.x_out = tok;
+  a.wpack[0] = reinterpret_cast<const uint32_t*>(wpack);
+  a.B = B * V;                       // "poses" of the kernel = 17-row sets
+  a.depth = depth;
+  a.group = V;
+  const int sets_used = (SETS / V) * V;
+  a.rows_used = sets_used * J;
+  a.final_norm = 0;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  MPL_CUDA(cudaGetDevice(&dev));
+  auto kern = spt_fused_kernel<false, true>;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  dim3 grid((unsigned)ceil_div(B * V, sets_used), 1);
   kern<<<grid, THREADS, SMEM_TOTAL, s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
