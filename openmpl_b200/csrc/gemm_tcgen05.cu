@@ -32,16 +32,19 @@ constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter: even / odd 32-c
 constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
 
-template <int CG>
+template <int CG, int EPI = 0>
 struct Cfg {
   static constexpr int A_BYTES = BM * KB_BYTES;             // 16 KB
   static constexpr int B_ROWS = BN / CG;                    // W rows staged per CTA
   static constexpr int B_BYTES = B_ROWS * KB_BYTES;         // 32 KB / 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // 48 KB / 32 KB
-  static constexpr int STAGES = (CG == 1) ? 4 : 6;          // 192 KB of operand ring: the kernel is load-latency bound
+  // 192 KB of operand ring.  The residual-emit epilogue (EPI 6) trades two stages for a shared-memory prefetch ring of
+  // old residual values (measured: the ring depth does not matter for K = 1088 and costs K = 2176 little)
+  static constexpr int XRING_BYTES = (EPI == 6) ? NUM_EPI_WARPS * 2 * 4096 : 0;  // two 4 KB chunks per epilogue warp
+  static constexpr int STAGES = (EPI == 6) ? ((CG == 1) ? 2 : 4) : ((CG == 1) ? 4 : 6);
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096; // per epilogue warp: one 32-row x 128-byte output box
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + XRING_BYTES + BAR_BYTES;
 };
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1 (sm_100)
@@ -68,7 +71,8 @@ __device__ __forceinline__ float round_tf32_dev(float x) {
 }
 
 // EPI: 0 bias -> operand dtype, 1 bias + GELU -> operand dtype, 2 Y(fp32) += acc + bias, 3 bias -> fp32,
-//      4 / 5 = 0 / 1 with LayerNorm folded in (see GemmLn), 6 residual update that also emits the next LayerNorm's inputs.
+//      4 / 5 = 0 / 1 with LayerNorm folded in (see GemmLn), 6 / 7 residual update that also emits the next LayerNorm's inputs
+//      (6: shared-memory prefetch ring of the old residual, 7: register prefetch).
 //
 // LayerNorm fused around the projections (bf16 mode).  LN(x) W^T + b = rstd * (x W'^T - mu * colsum(W')) + b' with
 // W' = W diag(gamma), b' = b + W beta: the consumer GEMM (QKV, fc1; EPI 4 / 5) multiplies the RAW residual rows (a bf16
@@ -160,14 +164,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int64_t M, int N, int K,
                     int bn, const GemmLn ln) {  // bn: output-tile width (256 / 192 / 128), chosen so that no interior tile is narrow
-  using C = Cfg<CG>;
+  using C = Cfg<CG, EPI>;
   constexpr int ESZ = (KIND == 0) ? 2 : 4;
   constexpr int BK = KB_BYTES / ESZ;  // K elements per stage
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte aligned bases
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;  // 1024-aligned: stage sizes are multiples of 1 KB
-  const uint32_t bar_base = staging_base + C::STAGING_BYTES;
+  const uint32_t xring_base = staging_base + C::STAGING_BYTES;
+  const uint32_t bar_base = xring_base + C::XRING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
@@ -175,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + 8 * (2 * C::STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + C::XRING_BYTES + 8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
@@ -298,6 +303,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t leader_tempty0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : 0u;
+    // ---- EPI 6: prefetch ring of old residual values.  This warp's 32 x 32 chunks form one stream across its tiles; a
+    // fetch cursor runs TWO chunks ahead of the consumer and copies each chunk with cp.async (16 bytes per lane and row
+    // group, the coalesced layout the consumer reads back) into one of two 4 KB slots: no registers are tied up and the
+    // DRAM latency of a chunk is covered by two chunk times, across tile boundaries too.
+    const int e6_rs = lane >> 3, e6_c4 = lane & 7;
+    auto e6_chunk_col = [&](int ci) { return half * 64 + (ci >> 1) * 128 + (ci & 1) * 32; };
+    const uint32_t e6_ring = xring_base + (uint32_t)(warp - 4) * 8192u + (uint32_t)lane * 16u;
+    int64_t f_tile = first_tile;  // fetch cursor
+    int f_ci = -1;
+    uint32_t f_seq = 0, c_seq = 0;
+    auto e6_fetch_next = [&]() {  // advance the cursor to the next chunk of the stream and start copying it
+      if constexpr (EPI == 6) {
+        for (;;) {
+          if (f_tile >= total_tiles) break;
+          ++f_ci;
+          const int nn = (int)(f_tile % n_tiles);
+          if (f_ci < BN / 64 && e6_chunk_col(f_ci) < min(bn, N - nn * bn)) {
+            const float* p = ln.y_raw + ((f_tile / n_tiles) * BM * CG + cta_rank * BM + q * 32 + e6_rs) * (int64_t)N + nn * bn +
+                             4 * e6_c4 + e6_chunk_col(f_ci);
+            const uint32_t dst = e6_ring + (f_seq & 1u) * 4096u;
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 512), "l"(p + (int64_t)it * 4 * N) : "memory");
+            break;
+          }
+          f_tile += tile_stride;
+          f_ci = -1;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per call, empty past the end of the stream
+        ++f_seq;
+      }
+    };
+    if constexpr (EPI == 6) { e6_fetch_next(); e6_fetch_next(); }
     for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const int64_t m_blk = tile / n_tiles;
       const int n_blk = (int)(tile % n_tiles);
@@ -324,6 +362,80 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         rstd = rsqrtf(fmaxf(fmaf(-mu, mu, s2 * ln.inv_k), 0.f) + ln.eps);
       }
       if constexpr (EPI == 6) {
+        // Residual update x_new = x_old + acc + bias, 32-column chunks.  The accumulator arrives one row per lane; the
+        // residual is read and written in a COALESCED layout instead (lane = (row & 3, 16-byte column group): 4 rows x
+        // 128 B per instruction), the staging box doing the transpose; x_old comes from the prefetch ring above.
+        // No predicates: N % 32 == 0 makes a chunk valid for all lanes or none, and the caller pads the residual, its
+        // bf16 copy and the statistics to a multiple of BM * CG rows, so rows past M are scratch (read, updated, ignored).
+        const int rs = e6_rs, c4 = e6_c4;
+        float* const lp = ln.y_raw + ((int64_t)row0 + rs) * N + ncol0 + 4 * c4;
+        __nv_bfloat16* const lb = ln.xb + ((int64_t)row0 + rs) * N + ncol0 + 4 * c4;
+        const int64_t rowstep = 4 * (int64_t)N;
+        float s1[8], s2[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) { s1[it] = 0.f; s2[it] = 0.f; }
+        ptx::mbar_wait(tfull_bar(acc), acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        const uint32_t rd_base = box + rs * 128;  // this lane reads rows 4*it + rs of the box: (4*it + rs) & 7 = ((it & 1) * 4 + rs)
+        const uint32_t rd_sw0 = (uint32_t)((c4 ^ rs) << 4), rd_sw1 = (uint32_t)((c4 ^ (4 + rs)) << 4);
+#pragma unroll
+        for (int ci = 0; ci < BN / 64; ++ci) {  // at most 4 chunks of 32 columns per warp and tile
+          const int cc = e6_chunk_col(ci);
+          if (cc >= n_size) break;
+          uint32_t va[32];
+          ptx::tmem_ld_32x32(taddr + cc, va);
+          ptx::tmem_ld_wait();
+          float f[32];
+          epilogue_math<KIND, 0>(va, bias, ncol0 + cc, N, f);
+          stage_row_f32(box, lane, f);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");  // this chunk's old values have landed (own copies only)
+          __syncwarp();
+          const uint32_t xsrc = e6_ring + (c_seq & 1u) * 4096u;
+          float* sp = lp + cc;
+          __nv_bfloat16* sb = lb + cc;
+#pragma unroll
+          for (int it = 0; it < 8; ++it, sp += rowstep, sb += rowstep) {
+            float4 v, o;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(rd_base + it * 512 + ((it & 1) ? rd_sw1 : rd_sw0)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(xsrc + it * 512));
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            s1[it] += (v.x + v.y) + (v.z + v.w);
+            s2[it] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[it]))));
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<float4*>(sp) = v;
+            *reinterpret_cast<uint2*>(sb) = pk;
+          }
+          ++c_seq;
+          e6_fetch_next();  // the slot just consumed takes the chunk two ahead
+          __syncwarp();     // every lane is done reading the box before the next chunk is staged
+        }
+        // per-row partial statistics: sum over the 8 lanes that share a row, fixed order
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            s1[it] += __shfl_xor_sync(0xffffffffu, s1[it], o);
+            s2[it] += __shfl_xor_sync(0xffffffffu, s2[it], o);
+          }
+          if (c4 == 0) ln.stats_out[(2 * n_blk + half) * ln.stats_ld + row0 + 4 * it + rs] = make_float2(s1[it], s2[it]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
+          else ptx::mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
+      if constexpr (EPI == 7) {
+        // Residual update, register-prefetch form (long K: the main loop hides the epilogue, all six ring stages kept).
         // Residual update x_new = x_old + acc + bias, 32-column chunks.  The accumulator arrives one row per lane; the
         // residual is read and written in a COALESCED layout instead (lane = (row & 3, 16-byte column group): 4 rows x
         // 128 B per instruction), the staging box doing the transpose.  x_old of the next chunk is prefetched into
@@ -465,6 +577,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if constexpr (EPI == 6) asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) ptx::bulk_wait_all();  // every output tile has landed before the CTA retires
     __syncwarp();
   }
@@ -522,7 +635,7 @@ int g_gemm_cta_group = 2;  // CTA pairs by default: half the operand traffic per
 template <int CG, int KIND, int EPI>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const float* bias, int64_t M, int N,
                int K, int bn, const GemmLn& ln, cudaStream_t s) {
-  using C = Cfg<CG>;
+  using C = Cfg<CG, EPI>;
   auto kern = gemm_tcgen05_kernel<CG, KIND, EPI>;
   static bool attr_set[64] = {};  // per instantiation and device (function attributes live in the device's context)
   int dev = 0;
@@ -567,6 +680,7 @@ int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
       case 4: return launch_one<CG, KIND, 4>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
       case 5: return launch_one<CG, KIND, 5>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
       case 6: return launch_one<CG, KIND, 6>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+      case 7: return launch_one<CG, KIND, 7>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
       default: break;
     }
   }
@@ -656,7 +770,10 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
   const int kind = (dtype == MPL_PREC_BF16) ? 0 : 1;
   // output boxes: 32 rows x 128 bytes (64 bf16 or 32 fp32 columns), 128B swizzle like the staging writes
   const bool out_bf16 = kind == 0 && (epi == 0 || epi == 1 || epi == 4 || epi == 5);
-  const int bn = pick_tile_n(N, epi == 2 || epi == 6);  // tf32 EPI 0 / 1 / 3 store through 64-column steps: keep 64-multiples
+  // residual-emit: short K (proj) is epilogue-bound -> shared-memory prefetch ring on a 4-stage operand ring (EPI 6);
+  // long K (fc2) hides the epilogue behind the main loop -> register prefetch, all 6 stages (EPI 7)
+  if (epi == 6 && K > 1536) epi = 7;
+  const int bn = pick_tile_n(N, epi == 2 || epi == 6 || epi == 7);  // tf32 EPI 0 / 1 / 3 store through 64-column steps: keep 64-multiples
   MPL_TRY(make_tmap(&tmB, W, N, K, esz, bn / cg));
   MPL_TRY(make_tmap(&tmY, Y, M, N, out_bf16 ? 2 : 4, 32, out_bf16 ? 64 : 32));
   if (cg == 1) {
