@@ -8,6 +8,8 @@
 //   warps 4-11 epilogue       tcgen05.ld -> registers -> bias / GELU -> 128B-swizzled staging tile in shared memory ->
 //                             TMA store (bf16 / fp32) or TMA reduce-add (the fp32 residual stream is updated in L2,
 //                             never read by the SM).  Two warps per TMEM lane quarter, 64 columns per step.
+//                             bf16 mode folds the LayerNorms in: LN-apply epilogues (EPI 4 / 5) for QKV / fc1 and
+//                             residual-emit epilogues (EPI 6 / 7) for proj / fc2, see GemmLn below.
 // CG = 1: one CTA per 128 x 256 output tile.  CG = 2: a CTA pair (cluster 2x1x1, cta_group::2) per 256 x 256 tile, each
 // CTA staging half of A and half of W, which halves the shared-memory and L2 operand traffic per MMA.
 // Every FPT width is a multiple of 17 (D = 1088 = 17*64): ragged N tiles use a narrower UMMA N (multiple of 16) and
