@@ -302,11 +302,15 @@ def run_ours(args):
             memory_kernels[k] = {"avg_launch_ms": ms_l, "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": gbs,
                                  "frac_of_hbm_peak": gbs / pk.get("hbm_gbs", 6650.0)}
 
-    # ---- one collective: MPJPE accumulators all-reduced over ranks (NCCL) ----
+    # ---- the collectives: MPJPE / P-MPJPE accumulators all-reduced over ranks (NCCL) ----
     acc = metric.MpjpeAccumulator(cfg.J, output_in_meter=True, device=dev)
     acc.update(out, devin["target"])
     acc.all_reduce()
     res = acc.result()
+    pacc = metric.PmpjpeAccumulator(cfg.J, output_in_meter=True, device=dev)
+    pacc.update(out, devin["target"])
+    pacc.all_reduce()
+    pres = pacc.result()
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -333,8 +337,9 @@ def run_ours(args):
             "roofline": roofline, "whole_path_tflops": value / world * flops / 1e12,
             "breakdown": breakdown, "memory_bound_kernels": memory_kernels, "hbm_peak_gbs": pk.get("hbm_gbs"),
             "cpu_baseline": cpu, "parity": parity,
-            "mpjpe_cm": {"absolute": res["mpjpe_abs"], "root_relative": res["mpjpe_rel"], "poses": res["n"],
-                         "note": "random-init weights: the value only exercises the accumulator + all-reduce"},
+            "mpjpe_cm": {"absolute": res["mpjpe_abs"], "root_relative": res["mpjpe_rel"], "procrustes_aligned": pres["p_mpjpe"],
+                         "poses": res["n"],
+                         "note": "random-init weights: the values only exercise the accumulators + all-reduce"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

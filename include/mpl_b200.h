@@ -9,6 +9,7 @@
  *   MPL/lib/models/multiview_mpl.py:450-525  MultiView_MPL.forward   (poses, rays, centers -> mpl_forward)
  *   MPL/lib/utils/utils.py:148-153           load_state_dict of checkpoints (-> mpl_param_* / mpl_pack_weights)
  *   MPL/lib/core/evaluate.py:91-125          calc_mpjpe / calc_distance_per_dim (-> mpl_mpjpe_accumulate)
+ *   MPL/lib/utils/pose_utils.py:61-143       PoseUtils.procrustes (-> mpl_pmpjpe_accumulate)
  *   MPL/lib/dataset/joints_dataset_mpl.py:615-648,701-715,762-772,817-820,872-904
  *                                            per-sample input construction (-> mpl_build_inputs)
  *
@@ -151,6 +152,16 @@ int mpl_profile_collect(MplModel* m, double* ms_per_category, int64_t* launches_
 #define MPL_METRIC_ACC_LEN(J) (11 * (J) + 1)
 int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t batch, int num_joints,
                          float unit_scale, double* acc, mpl_stream_t stream);
+
+/* Procrustes-aligned error (P-MPJPE) as running fp64 sums: per pose, PoseUtils.procrustes(A = gt, B = pred)
+ * (MPL/lib/utils/pose_utils.py:61-143) after the unit rule above, then the per-joint distances of calc_mpjpe between the
+ * aligned prediction Z and gt.  scaling: 1 = similarity (the reference default), 0 = rigid.  reflection: -1 = 'best'
+ * (the reference default: whatever the SVD gives), 0 = forbid, 1 = force (pose_utils.py:112-120).
+ *   acc layout (doubles): [0,J) sum_b ||Z_j - gt_j||; [J] sum_b d (normalised residual); [J+1] sum_b scale;
+ *   [J+2] pose count. */
+#define MPL_PMETRIC_ACC_LEN(J) ((J) + 3)
+int mpl_pmpjpe_accumulate(const float* pred, const float* gt, int64_t batch, int num_joints, float unit_scale,
+                          int scaling, int reflection, double* acc, mpl_stream_t stream);
 
 /* Per-sample input construction of the dataset (joints_dataset_mpl.py:615-648,701-715,762-772,817-820,872-904),
  * batched: raw detector output (u, v, conf) in pixels + per-view calibration -> the model's poses / rays / centers.

@@ -28,6 +28,7 @@ EXPORTS = [
     "mpl_forward", "mpl_last_launch_count", "mpl_mpjpe_accumulate", "mpl_build_inputs", "mpl_test_gemm",
     "mpl_set_gemm_cta_group", "mpl_get_gemm_cta_group", "mpl_set_profile", "mpl_profile_categories",
     "mpl_profile_category_name", "mpl_profile_collect", "mpl_set_ln_fusion", "mpl_get_ln_fusion", "mpl_synth_project",
+    "mpl_pmpjpe_accumulate",
 ]
 
 _DESC_FLAGS = [
@@ -102,6 +103,7 @@ def lib():
         L.mpl_last_launch_count.argtypes = [c_void_p]
         L.mpl_last_launch_count.restype = c_int64
         L.mpl_mpjpe_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]
+        L.mpl_pmpjpe_accumulate.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p]
         L.mpl_build_inputs.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         L.mpl_test_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]

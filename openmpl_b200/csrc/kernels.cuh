@@ -163,6 +163,8 @@ int launch_fpt_kp_fused(float* tok, const void* wpack, int V, int64_t B, int dep
 // ---- metric + input builder -----------------------------------------------------------------------------------------
 int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t B, int J, float unit_scale,
                             double* acc, cudaStream_t s);
+int launch_pmpjpe_accumulate(const float* pred, const float* gt, int64_t B, int J, float unit_scale, int scaling,
+                             int reflection, double* acc, cudaStream_t s);
 int launch_build_inputs(const float* pix, const double* calib, int64_t B, int V, int J, float* poses, float* rays,
                         float* centers, cudaStream_t s);
 int launch_synth_project(uint64_t seed, int64_t start, int64_t B, int V, int J, const double* calib, const double* room,

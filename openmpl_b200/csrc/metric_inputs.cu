@@ -1,4 +1,5 @@
-// K6: MPJPE accumulators (evaluate.py:91-125 + function_mpl.py:674-687) and the batched input builder
+// K6: MPJPE accumulators (evaluate.py:91-125 + function_mpl.py:674-687), P-MPJPE accumulators (pose_utils.py:61-143)
+// and the batched input builder
 // (joints_dataset_mpl.py:615-648,701-715,762-772,817-820,872-904).  Both are HBM-bound streaming kernels.
 #include "kernels.cuh"
 
@@ -75,6 +76,222 @@ int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* con
   const int64_t want = ceil_div(B, 8 * 16);  // 8 warps per block, ~16 poses per warp
   const unsigned grid = (unsigned)(want < 1 ? 1 : (want > 8 * kNumSMs ? 8 * kNumSMs : want));
   mpjpe_kernel<<<grid, 256, (size_t)(11 * J + 1) * sizeof(double), s>>>(pred, gt, conf3d, B, J, unit_scale, acc);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+// ---- P-MPJPE: Procrustes-aligned error (pose_utils.py:61-143) -----------------------------------------------------
+// One thread per pose, fp64 throughout; a tile of poses is staged through shared memory with coalesced loads (a pose
+// is 3 J consecutive floats, so per-thread global reads would be strided).  Per pose, with A = gt, B = pred (x unit):
+// centre both, normalise by their Frobenius norms, M = A0^T B0 (3x3) = U S V^T, R = V U^T, optional reflection rule
+// on the smallest singular value, then Z = a_norm * tr(S) * B0 R + mean(A) (scaling) or b_norm * B0 R + mean(A).
+// acc layout (doubles), L = MPL_PMETRIC_ACC_LEN(J) = J + 3:
+//   [0,J) sum_b ||Z_j - A_j||;  [J] sum_b d (normalised residual);  [J+1] sum_b scale;  [J+2] pose count
+
+// One-sided Jacobi on the columns of G (3x3): on return G = U diag(sigma) with orthogonal columns and the rotations
+// accumulated in V, i.e. M = U diag(sigma) V^T.  Unordered sigma >= 0.
+__device__ __forceinline__ void svd3_one_sided(double (&G)[3][3], double (&V)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) V[i][k] = i == k ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {              // converges in <= 4 sweeps in practice
+    bool rotated = false;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        alpha = fma(G[i][p], G[i][p], alpha);
+        beta = fma(G[i][q], G[i][q], beta);
+        gamma = fma(G[i][p], G[i][q], gamma);
+      }
+      if (gamma * gamma <= 1e-30 * alpha * beta) continue;   // columns orthogonal to 1e-15 relative
+      rotated = true;
+      const double zeta = (beta - alpha) / (2.0 * gamma);
+      const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      const double c = rsqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double gp = G[i][p], gq = G[i][q];
+        G[i][p] = c * gp - sn * gq;
+        G[i][q] = sn * gp + c * gq;
+        const double vp = V[i][p], vq = V[i][q];
+        V[i][p] = c * vp - sn * vq;
+        V[i][q] = sn * vp + c * vq;
+      }
+    }
+    if (!rotated) break;
+  }
+}
+
+__global__ void __launch_bounds__(64) pmpjpe_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                    int64_t B, int J, float unit, int scaling, int reflection,
+                                                    double* __restrict__ acc) {
+  extern __shared__ __align__(16) unsigned char psm[];
+  const int tile = blockDim.x, row = 3 * J;
+  double* sacc = reinterpret_cast<double*>(psm);                       // J + 3
+  float* sp = reinterpret_cast<float*>(sacc + (J + 3 + 1) / 2 * 2);    // [tile][3 J]
+  float* sg = sp + (size_t)tile * row;
+  for (int i = threadIdx.x; i < J + 3; i += blockDim.x) sacc[i] = 0.0;
+  const int64_t n_tiles = (B + tile - 1) / tile;
+  for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const int64_t b0 = tl * tile;
+    const int n = (int)(B - b0 < tile ? B - b0 : tile);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * row; i += blockDim.x) {
+      sp[i] = pred[b0 * row + i];
+      sg[i] = gt[b0 * row + i];
+    }
+    __syncthreads();
+    const bool live = (int)threadIdx.x < n;
+    const float* p = sp + (size_t)threadIdx.x * row;
+    const float* g = sg + (size_t)threadIdx.x * row;
+    const double u = (double)unit;
+    double am[3] = {0, 0, 0}, bm[3] = {0, 0, 0}, R[3][3], zs = 0.0, d = 0.0, scale = 0.0;
+    if (live) {
+      for (int j = 0; j < J; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          am[k] += (double)g[j * 3 + k] * u;
+          bm[k] += (double)p[j * 3 + k] * u;
+        }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        am[k] /= (double)J;
+        bm[k] /= (double)J;
+      }
+      double ssx = 0, ssy = 0, G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, V[3][3];
+      for (int j = 0; j < J; ++j) {
+        double a0[3], c0[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          a0[k] = (double)g[j * 3 + k] * u - am[k];
+          c0[k] = (double)p[j * 3 + k] * u - bm[k];
+          ssx = fma(a0[k], a0[k], ssx);
+          ssy = fma(c0[k], c0[k], ssy);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) G[i][k] = fma(a0[i], c0[k], G[i][k]);
+      }
+      const double a_norm = sqrt(ssx), b_norm = sqrt(ssy), inv = 1.0 / (a_norm * b_norm);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) G[i][k] *= inv;
+      svd3_one_sided(G, V);
+      double sig[3], U[3][3];
+      int imin = 0, imax = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        sig[c] = sqrt(G[0][c] * G[0][c] + G[1][c] * G[1][c] + G[2][c] * G[2][c]);
+        if (sig[c] < sig[imin]) imin = c;
+        if (sig[c] > sig[imax]) imax = c;
+      }
+      // left vectors; a vanishing singular value (planar / collinear prediction) gets the completion of the others
+      const double tiny = 1e-14 * sig[imax];
+      int n_ok = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const bool ok = sig[c] > tiny;
+        n_ok += ok;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) U[i][c] = ok ? G[i][c] / sig[c] : 0.0;
+      }
+      if (n_ok == 2) {
+        const int c = imin, a = (c + 1) % 3, b = (c + 2) % 3;
+        U[0][c] = U[1][a] * U[2][b] - U[2][a] * U[1][b];
+        U[1][c] = U[2][a] * U[0][b] - U[0][a] * U[2][b];
+        U[2][c] = U[0][a] * U[1][b] - U[1][a] * U[0][b];
+      }
+      if (reflection >= 0) {                                  // :112-120, det(R) = det(V) det(U)
+        double detR;
+        {
+          double Rt[3][3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) Rt[a][b] = V[a][0] * U[b][0] + V[a][1] * U[b][1] + V[a][2] * U[b][2];
+          detR = Rt[0][0] * (Rt[1][1] * Rt[2][2] - Rt[1][2] * Rt[2][1]) - Rt[0][1] * (Rt[1][0] * Rt[2][2] - Rt[1][2] * Rt[2][0]) +
+                 Rt[0][2] * (Rt[1][0] * Rt[2][1] - Rt[1][1] * Rt[2][0]);
+        }
+        if ((reflection != 0) != (detR < 0.0)) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c == imin) {
+              V[0][c] = -V[0][c];
+              V[1][c] = -V[1][c];
+              V[2][c] = -V[2][c];
+              sig[c] = -sig[c];
+            }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) R[a][b] = V[a][0] * U[b][0] + V[a][1] * U[b][1] + V[a][2] * U[b][2];
+      const double s_trace = sig[0] + sig[1] + sig[2];
+      if (scaling) {
+        scale = s_trace * a_norm / b_norm;
+        d = 1.0 - s_trace * s_trace;
+        zs = scale;                                           // a_norm * s_trace * (B0 / b_norm)
+      } else {
+        scale = 1.0;
+        d = 1.0 + ssy / ssx - 2.0 * s_trace * b_norm / a_norm;
+        zs = 1.0;                                             // b_norm * (B0 / b_norm)
+      }
+    }
+    const int lane = threadIdx.x & 31;
+    for (int j = 0; j < J; ++j) {
+      double e = 0.0;
+      if (live) {
+        double c0[3], acc2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) c0[k] = (double)p[j * 3 + k] * u - bm[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double z = zs * (c0[0] * R[0][k] + c0[1] * R[1][k] + c0[2] * R[2][k]) + am[k];
+          const double df = z - (double)g[j * 3 + k] * u;
+          acc2 = fma(df, df, acc2);
+        }
+        e = sqrt(acc2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      if (lane == 0) atomicAdd(&sacc[j], e);
+    }
+    double sd = live ? d : 0.0, ssc = live ? scale : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      ssc += __shfl_xor_sync(0xffffffffu, ssc, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&sacc[J], sd);
+      atomicAdd(&sacc[J + 1], ssc);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < J + 2; i += blockDim.x) atomicAdd(&acc[i], sacc[i]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&acc[J + 2], (double)B);
+}
+
+int launch_pmpjpe_accumulate(const float* pred, const float* gt, int64_t B, int J, float unit_scale, int scaling,
+                             int reflection, double* acc, cudaStream_t s) {
+  if (B == 0) return MPL_OK;
+  int tile = 64;
+  auto smem = [&](int t) { return (size_t)((J + 3 + 1) / 2 * 2) * sizeof(double) + (size_t)2 * t * 3 * J * sizeof(float); };
+  if (smem(tile) > 48 * 1024) tile = 32;
+  if (smem(tile) > 48 * 1024) {
+    set_error("mpl_pmpjpe_accumulate: num_joints too large for the shared-memory pose tile");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  const int64_t n_tiles = ceil_div(B, (int64_t)tile);
+  const unsigned grid = (unsigned)(n_tiles > 16 * kNumSMs ? 16 * kNumSMs : n_tiles);
+  pmpjpe_kernel<<<grid, tile, smem(tile), s>>>(pred, gt, B, J, unit_scale, scaling, reflection, acc);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

@@ -1020,6 +1020,17 @@ int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d
   return launch_mpjpe_accumulate(pred, gt, conf3d, batch, num_joints, unit_scale, acc, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int mpl_pmpjpe_accumulate(const float* pred, const float* gt, int64_t batch, int num_joints, float unit_scale,
+                          int scaling, int reflection, double* acc, mpl_stream_t stream) {
+  if (batch == 0 && acc != nullptr) return MPL_OK;
+  if (pred == nullptr || gt == nullptr || acc == nullptr || batch < 0 || num_joints < 1 || reflection < -1 || reflection > 1) {
+    set_error("mpl_pmpjpe_accumulate: bad argument");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  return launch_pmpjpe_accumulate(pred, gt, batch, num_joints, unit_scale, scaling != 0, reflection, acc,
+                                  reinterpret_cast<cudaStream_t>(stream));
+}
+
 int mpl_build_inputs(const float* pix, const double* calib, int64_t batch, int num_views, int num_joints, float* poses,
                      float* rays, float* centers, mpl_stream_t stream) {
   if (batch == 0) return MPL_OK;

@@ -7,9 +7,10 @@
 
 Per micro-batch, entirely on the device: `mpl_synth_project` (3D poses from the counter-based generator keyed by the
 GLOBAL pose index, projected through the V calibrations) -> `mpl_build_inputs` (clip, confidence zeroing, screen
-normalisation, rays) -> `mpl_forward` -> `mpl_mpjpe_accumulate` (fp64 running sums).  Predictions never leave the GPU;
-ranks own contiguous slices of the index range, and ONE all-reduce of the 11 J + 1 sums at the end gives the MPJPE the
-reference's `evaluate()` would log (`function_mpl.py:670-687`).  Prints one JSON line from rank 0.
+normalisation, rays) -> `mpl_forward` -> `mpl_mpjpe_accumulate` + `mpl_pmpjpe_accumulate` (fp64 running sums).  Predictions never leave the GPU;
+ranks own contiguous slices of the index range, and one all-reduce of the 11 J + 1 (and J + 3 Procrustes) sums at the end
+gives the MPJPE the reference's `evaluate()` would log (`function_mpl.py:670-687`) and the P-MPJPE of
+`pose_utils.py:61-143`.  Prints one JSON line from rank 0.
 """
 from __future__ import annotations
 
@@ -47,17 +48,21 @@ def run(arch="hm0", views=4, depth=None, poses=1 << 20, micro_batch=65536, preci
     the_rig = synth.make_rig(views, rig or DEFAULT_RIG[arch])
     start, stop = mdist.shard_range(poses, rank, world)
     acc = metric.MpjpeAccumulator(cfg.J, output_in_meter=True, device=dev)
+    pacc = metric.PmpjpeAccumulator(cfg.J, output_in_meter=True, device=dev)
 
     def step(s0, n):
         pix, target, calib = inputs.synth_project(n, the_rig, seed=seed, start=s0, device=dev)
         p, r, c = inputs.build_inputs(pix, calib)
         with torch.no_grad():
             out = model(p, rays=r, centers=c)
-        acc.update(out[0] if isinstance(out, tuple) else out, target)
+        out = out[0] if isinstance(out, tuple) else out
+        acc.update(out, target)
+        pacc.update(out, target)
 
     for _ in range(warmup):                            # allocate the workspace, pack the weights
         step(start, min(micro_batch, max(stop - start, 1)))
     acc.acc.zero_()
+    pacc.acc.zero_()
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
@@ -65,11 +70,12 @@ def run(arch="hm0", views=4, depth=None, poses=1 << 20, micro_batch=65536, preci
     e0.record()
     for s0 in range(start, stop, micro_batch):
         step(s0, min(micro_batch, stop - s0))
-    acc.all_reduce()                                   # the one collective of the whole job
+    acc.all_reduce()                                   # the only collectives of the whole job:
+    pacc.all_reduce()                                  # 11 J + 1 and J + 3 doubles
     e1.record()
     torch.cuda.synchronize()
     ms = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
-    res = acc.result()
+    res, pres = acc.result(), pacc.result()
     line = None
     if rank == 0:
         line = {
@@ -78,7 +84,7 @@ def run(arch="hm0", views=4, depth=None, poses=1 << 20, micro_batch=65536, preci
             "dtype": precision, "data": "synthetic (device generator keyed by global pose index)",
             "config": {"workload": f"{arch} V={views} depth={depth} D={cfg.fpt_dim} tokens={cfg.fpt_tokens}",
                        "micro_batch": micro_batch, "rig": rig or DEFAULT_RIG[arch], "flops_per_pose": spec.flops_per_pose(cfg)},
-            "mpjpe_cm": {"absolute": res["mpjpe_abs"], "root_relative": res["mpjpe_rel"],
+            "mpjpe_cm": {"absolute": res["mpjpe_abs"], "root_relative": res["mpjpe_rel"], "procrustes_aligned": pres["p_mpjpe"],
                          "note": "random-init weights: exercises the metric path, not a trained accuracy"},
             "tflops": poses / (ms / 1000.0) * spec.flops_per_pose(cfg) / 1e12 / world,
         }

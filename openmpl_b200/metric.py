@@ -4,6 +4,7 @@ Mirrors `evaluate()` of the reference (`MPL/lib/core/function_mpl.py:670-687`) a
 `calc_distance_per_dim` (`MPL/lib/core/evaluate.py:91-125`): unit rule (x100 when OUTPUT_IN_METER), root-relative
 variant, `joints_3d_conf <= 0` masking with NaN semantics.  Predictions never leave the GPU: each batch adds into
 `11 J + 1` fp64 running sums (layout in include/mpl_b200.h) and ranks are combined with ONE all-reduce at the end.
+`PmpjpeAccumulator` does the same for the Procrustes-aligned error (`MPL/lib/utils/pose_utils.py:61-143`).
 """
 from __future__ import annotations
 
@@ -49,6 +50,52 @@ class MpjpeAccumulator:
 
     def result(self) -> dict:
         return finalize(self.acc.detach().cpu().numpy(), self.J)
+
+
+class PmpjpeAccumulator:
+    """Procrustes-aligned MPJPE (P-MPJPE): every prediction is first aligned to its ground truth with
+    `PoseUtils.procrustes` of the reference (`MPL/lib/utils/pose_utils.py:61-143`; similarity transform, reflection
+    'best' by default), then scored like `calc_mpjpe`.  `J + 3` fp64 running sums on the device, one all-reduce."""
+
+    REFLECTION = {"best": -1, False: 0, True: 1}
+
+    def __init__(self, num_joints: int = 17, output_in_meter: bool = True, scaling: bool = True, reflection="best",
+                 device=None):
+        self.J = num_joints
+        self.unit = 100.0 if output_in_meter else 1.0
+        self.scaling = bool(scaling)
+        self.reflection = self.REFLECTION[reflection]
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.acc = torch.zeros(num_joints + 3, dtype=torch.float64, device=self.device)
+
+    def update(self, pred: torch.Tensor, gt: torch.Tensor):
+        """pred, gt: [B, J, 3] fp32 on the device."""
+        B = pred.shape[0]
+        pred = pred.to(self.device, torch.float32).contiguous()
+        gt = gt.to(self.device, torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.lib().mpl_pmpjpe_accumulate(pred.data_ptr(), gt.data_ptr(), B, self.J, self.unit,
+                                                        int(self.scaling), self.reflection, self.acc.data_ptr(), stream))
+
+    def all_reduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+        return self
+
+    def result(self) -> dict:
+        return finalize_pmpjpe(self.acc.detach().cpu().numpy(), self.J)
+
+
+def finalize_pmpjpe(acc: np.ndarray, J: int) -> dict:
+    """Running sums -> per-joint P-MPJPE, its mean, mean normalised residual d and mean scale."""
+    acc = np.asarray(acc, dtype=np.float64)
+    n = acc[J + 2]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out = {"n": int(round(n)), "pjpe_aligned": acc[0:J] / n, "residual": float(acc[J] / n), "scale": float(acc[J + 1] / n)}
+    out["p_mpjpe"] = float(out["pjpe_aligned"].mean())
+    return out
 
 
 def finalize(acc: np.ndarray, J: int) -> dict:

@@ -1,6 +1,7 @@
 """ORACLE — mint the golden vectors from the UNMODIFIED reference (run in the build container only).
 
     python -m oracle.make_goldens            # writes tests/golden/*.npz and tests/golden/validity_grid.npz
+    python -m oracle.make_goldens --only-procrustes     # just tests/golden/procrustes.npz (PoseUtils.procrustes)
 
 For every case in `oracle/cases.py`: build the reference `MultiView_MPL(**kw)`, load the name-keyed deterministic
 weights (`openmpl_b200.synth.named_weights` — regenerated, not stored), run the seeded synthetic inputs through
@@ -40,8 +41,47 @@ def run_reference(kw, weights, batch, dtype):
     return [out.numpy()]
 
 
+PROCRUSTES_MODES = [(True, "best"), (False, "best"), (True, False), (True, True)]   # (scaling, reflection)
+
+
+def procrustes_inputs(n=48, J=17, seed=11):
+    """Ground-truth poses A and predictions B: noisy similarity transforms of A (some mirrored), plus unrelated pairs."""
+    rng = np.random.default_rng(seed)
+    A = rng.normal(0.0, 0.3, size=(n, J, 3)) + rng.uniform(-2, 2, size=(n, 1, 3))
+    B = np.empty_like(A)
+    for i in range(n):
+        Q = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        if i % 4 == 1:
+            Q[:, 0] *= -1                                    # a mirrored prediction
+        B[i] = rng.uniform(0.5, 2.0) * (A[i] @ Q) + rng.normal(size=3) + rng.normal(0, 0.02 * (1 + i % 5), size=(J, 3))
+        if i % 6 == 5:
+            B[i] = rng.normal(0.0, 0.3, size=(J, 3))         # unrelated pose
+    return A.astype(np.float32), B.astype(np.float32)
+
+
+def mint_procrustes():
+    """PoseUtils.procrustes (pose_utils.py:61-143) of the unmodified reference on seeded pose pairs."""
+    u = ref_loader.load_pose_utils_module().PoseUtils()
+    A, B = procrustes_inputs()
+    arrays = dict(A=A, B=B)
+    for scaling, refl in PROCRUSTES_MODES:
+        tag = f"s{int(scaling)}_r{refl}"
+        res = [u.procrustes(a.astype(np.float64), b.astype(np.float64), scaling=scaling, reflection=refl)
+               for a, b in zip(A, B)]
+        arrays[f"d_{tag}"] = np.array([r[0] for r in res])
+        arrays[f"Z_{tag}"] = np.stack([r[1] for r in res])
+        arrays[f"R_{tag}"] = np.stack([r[2]["rotation"] for r in res])
+        arrays[f"scale_{tag}"] = np.array([float(r[2]["scale"]) for r in res])
+        arrays[f"t_{tag}"] = np.stack([r[2]["translation"] for r in res])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "procrustes.npz"), **arrays)
+    print("procrustes:", A.shape, "modes", PROCRUSTES_MODES)
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    mint_procrustes()
+    if "--only-procrustes" in sys.argv:
+        return
     torch.set_num_threads(os.cpu_count())
     for name, case in CASES.items():
         cfg, weights, batch = make_inputs(case)

@@ -256,6 +256,62 @@ def metric_sums(pred, gt, conf_3d=None, output_in_meter=True):
 
 
 # --------------------------------------------------------------------------------------------------
+# Procrustes-aligned error (P-MPJPE): MPL/lib/utils/pose_utils.py:61-143
+# --------------------------------------------------------------------------------------------------
+
+def procrustes(A, B, scaling=True, reflection="best"):
+    """pose_utils.py:61-143 for equal column counts: similarity transform of B onto A.  Returns (d, Z, tform) with
+    d the normalised residual, Z the transformed B and tform = {rotation, scale, translation} (Z = scale*B@R + t when
+    scaling; with scaling=False the reference reports scale 1 and Z = ||B0|| * B0n @ R + mean(A))."""
+    A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
+    a_bar, b_bar = A.mean(0), B.mean(0)                      # :89-93 remove translation
+    A0, B0 = A - a_bar, B - b_bar
+    ssx, ssy = (A0 ** 2).sum(), (B0 ** 2).sum()              # :96-101 remove scale
+    a_norm, b_norm = np.sqrt(ssx), np.sqrt(ssy)
+    A0, B0 = A0 / a_norm, B0 / b_norm
+    U, s, Vt = np.linalg.svd(A0.T @ B0)                      # :107-110 optimum rotation of B
+    V = Vt.T
+    R = V @ U.T
+    if reflection != "best":                                 # :112-120 force / forbid a reflection
+        if bool(reflection) != (np.linalg.det(R) < 0):
+            V = V.copy()
+            s = s.copy()
+            V[:, -1] *= -1
+            s[-1] *= -1
+            R = V @ U.T
+    s_trace = s.sum()
+    if scaling:                                              # :123-131
+        scale = s_trace * a_norm / b_norm
+        d = 1 - s_trace ** 2
+        Z = a_norm * s_trace * (B0 @ R) + a_bar
+    else:                                                    # :132-135
+        scale = 1
+        d = 1 + ssy / ssx - 2 * s_trace * b_norm / a_norm
+        Z = b_norm * (B0 @ R) + a_bar
+    return d, Z, {"rotation": R, "scale": scale, "translation": a_bar - scale * (b_bar @ R)}
+
+
+def pmpjpe_sums(pred, gt, output_in_meter=True, scaling=True, reflection="best"):
+    """The running sums `mpl_pmpjpe_accumulate` keeps (layout in include/mpl_b200.h): per pose, `procrustes(gt, pred)`
+    after the unit rule of function_mpl.py:674-676, then the per-joint distances of calc_mpjpe (evaluate.py:104-110)
+    between the aligned prediction and the ground truth."""
+    pred = np.array(pred, dtype=np.float64)
+    gt = np.array(gt, dtype=np.float64)
+    if output_in_meter:
+        pred, gt = pred * 100, gt * 100
+    B, J, _ = pred.shape
+    acc = np.zeros(J + 3)
+    for b in range(B):
+        d, Z, tf = procrustes(gt[b], pred[b], scaling, reflection)
+        acc[:J] += np.sqrt(((Z - gt[b]) ** 2).sum(-1))
+        acc[J] += d
+        acc[J + 1] += tf["scale"] if scaling else 1.0
+    acc[J + 2] = B
+    return acc
+
+
+# --------------------------------------------------------------------------------------------------
 # input construction: MPL/lib/dataset/joints_dataset_mpl.py:615-648,701-715,762-772,817-820,872-904
 # --------------------------------------------------------------------------------------------------
 

@@ -109,3 +109,15 @@ def load_evaluate_module():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_pose_utils_module():
+    """The reference `utils.pose_utils` module (PoseUtils.procrustes); needs numpy + sklearn only."""
+    import warnings
+    spec = importlib.util.spec_from_file_location("ref_utils_pose_utils",
+                                                  os.path.join(REF_ROOT, "MPL/lib/utils/pose_utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)      # `reflection is not 'best'` in the reference source
+        spec.loader.exec_module(mod)
+    return mod

@@ -27,13 +27,16 @@ def main():
     acc = metric.MpjpeAccumulator(17, output_in_meter=True, device="cpu")
     acc.acc += torch.from_numpy(mpl_oracle.metric_sums(pred, batch["target"]))
     acc.all_reduce()
+    pacc = metric.PmpjpeAccumulator(17, output_in_meter=True, device="cpu")
+    pacc.acc += torch.from_numpy(mpl_oracle.pmpjpe_sums(pred, batch["target"]))
+    pacc.all_reduce()
     slowest = mdist.max_over_ranks(float(rank + 1))
     gathered = [None] * world
     dist.all_gather_object(gathered, (start, stop, pred.tolist()))
     if rank == 0:
         res = acc.result()
         json.dump({"world": world, "n": res["n"], "mpjpe_abs": res["mpjpe_abs"], "mpjpe_rel": res["mpjpe_rel"],
-                   "pjpe_abs": res["pjpe_abs"].tolist(), "slowest": slowest,
+                   "pjpe_abs": res["pjpe_abs"].tolist(), "slowest": slowest, "p_mpjpe": pacc.result()["p_mpjpe"],
                    "shards": [(g[0], g[1]) for g in gathered],
                    "pred": [p for g in gathered for p in g[2]]}, open(out_path, "w"))
     dist.barrier()

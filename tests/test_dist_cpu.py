@@ -60,6 +60,8 @@ def test_two_rank_all_reduce_equals_single_process_metric(tmp_path):
     np.testing.assert_allclose(d["pjpe_abs"], ref_abs["pjpe"], rtol=1e-12)
     assert abs(d["mpjpe_abs"] - ref_abs["mpjpe"]) < 1e-10
     assert abs(d["mpjpe_rel"] - ref_rel["mpjpe"]) < 1e-10
+    whole = mpl_oracle.pmpjpe_sums(pred, gt)                  # Procrustes-aligned sums reduce the same way
+    assert abs(d["p_mpjpe"] - whole[:17].mean() / total) < 1e-10
 
 
 def test_reference_arm_under_torchrun_prints_one_line_from_rank0():

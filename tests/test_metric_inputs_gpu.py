@@ -1,7 +1,11 @@
 """K6 (MPJPE accumulators) and N2 (input builder) kernels against the oracle restatements."""
+import os
+
 import numpy as np
 import pytest
 import torch
+
+from conftest import GOLDEN_DIR
 
 from oracle import mpl_oracle
 from openmpl_b200 import inputs, metric, synth
@@ -37,6 +41,71 @@ def test_mpjpe_accumulator_matches_reference_metric(B, J, masked):
     np.testing.assert_allclose(res["mpjpe_rel"], r["mpjpe"], rtol=1e-9)
     np.testing.assert_allclose(np.nan_to_num(res["dist_abs"]), np.nan_to_num(a["dist_per_dim_per_kp"]), rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(np.nan_to_num(res["dist_rel"]), np.nan_to_num(r["dist_per_dim_per_kp"]), rtol=1e-9, atol=1e-12)
+
+
+PROCRUSTES_MODES = [(True, "best"), (False, "best"), (True, False), (True, True)]
+
+
+@pytest.mark.parametrize("scaling,reflection", PROCRUSTES_MODES)
+def test_pmpjpe_accumulator_matches_reference_procrustes_golden(scaling, reflection):
+    """Device P-MPJPE sums against PoseUtils.procrustes outputs of the unmodified reference (tests/golden/procrustes.npz)."""
+    g = np.load(os.path.join(GOLDEN_DIR, "procrustes.npz"))
+    A, B = g["A"], g["B"]                                   # gt, prediction
+    tag = f"s{int(scaling)}_r{reflection}"
+    J = A.shape[1]
+    acc = metric.PmpjpeAccumulator(J, output_in_meter=False, scaling=scaling, reflection=reflection)
+    acc.update(torch.from_numpy(B).cuda(), torch.from_numpy(A).cuda())
+    got = acc.acc.cpu().numpy()
+    want = np.concatenate([np.sqrt(((g["Z_" + tag] - A.astype(np.float64)) ** 2).sum(-1)).sum(0),
+                           [g["d_" + tag].sum(), g["scale_" + tag].sum(), len(A)]])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("B,J", [(1, 17), (63, 17), (64, 17), (65, 17), (4097, 17), (200, 13), (70, 40), (0, 17)])
+def test_pmpjpe_accumulator_matches_oracle(B, J):
+    rng = np.random.default_rng(B * 7 + J)
+    gt = (rng.normal(0, 0.3, size=(B, J, 3)) + rng.uniform(-2, 2, size=(B, 1, 3))).astype(np.float32)
+    pred = (gt + rng.normal(0, 0.05, size=(B, J, 3))).astype(np.float32)
+    if B > 5:
+        pred[5, :, 2] = 0.25                                # a planar prediction: one singular value vanishes
+    acc = metric.PmpjpeAccumulator(J, output_in_meter=True)
+    half = B // 2
+    for sl in (slice(0, half), slice(half, B)):
+        acc.update(torch.from_numpy(pred[sl]).cuda(), torch.from_numpy(gt[sl]).cuda())
+    got = acc.acc.cpu().numpy()
+    if B == 0:
+        assert np.all(got == 0)
+        return
+    want = mpl_oracle.pmpjpe_sums(pred, gt, output_in_meter=True)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-8)
+    res = acc.result()
+    assert res["n"] == B and abs(res["p_mpjpe"] - want[:J].mean() / B) < 1e-9
+
+
+def test_pmpjpe_properties_at_full_batch():
+    """B = 65 536 (the bench batch): similarity-transformed ground truth scores ~0; the metric is invariant under a
+    similarity transform of the predictions; rigid alignment (scaling off) of a rigidly moved pose scores ~0 too."""
+    B, J = 65536, 17
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    gt = torch.randn(B, J, 3, device="cuda", generator=gen) * 0.3 + torch.rand(B, 1, 3, device="cuda", generator=gen) * 4 - 2
+    Q = torch.linalg.qr(torch.randn(3, 3, device="cuda", generator=gen, dtype=torch.float64))[0].float()
+    moved = 1.3 * gt @ Q + torch.tensor([0.5, -1.0, 2.0], device="cuda")
+    a = metric.PmpjpeAccumulator(J, output_in_meter=True)
+    a.update(moved, gt)
+    r = a.result()
+    assert r["n"] == B and r["p_mpjpe"] < 2e-4 and abs(r["scale"] - 1 / 1.3) < 1e-5      # cm; fp32 input rounding only
+    rigid = metric.PmpjpeAccumulator(J, output_in_meter=True, scaling=False)
+    rigid.update(gt @ Q + 0.7, gt)
+    assert rigid.result()["p_mpjpe"] < 2e-4
+    pred = gt + 0.03 * torch.randn(B, J, 3, device="cuda", generator=gen)
+    p0 = metric.PmpjpeAccumulator(J)
+    p0.update(pred, gt)
+    p1 = metric.PmpjpeAccumulator(J)
+    p1.update(0.6 * pred @ Q - 1.5, gt)
+    assert abs(p0.result()["p_mpjpe"] - p1.result()["p_mpjpe"]) < 2e-4
+    plain = metric.MpjpeAccumulator(J)
+    plain.update(pred, gt)
+    assert p0.result()["p_mpjpe"] < plain.result()["mpjpe_abs"]
 
 
 @pytest.mark.parametrize("kind,V,B", [("h36m", 4, 64), ("cmu", 5, 257), ("h36m", 8, 3), ("cmu", 2, 0)])
@@ -113,3 +182,5 @@ def test_device_evaluation_loop_matches_host_oracle_metric():
     assert line["poses"] == n
     assert abs(line["mpjpe_cm"]["absolute"] - ev_a["mpjpe"]) < 2e-3       # cm; inputs differ by <= 2e-6 from the host generator
     assert abs(line["mpjpe_cm"]["root_relative"] - ev_r["mpjpe"]) < 2e-3
+    pm = mpl_oracle.pmpjpe_sums(ref, batch["target"], output_in_meter=True)
+    assert abs(line["mpjpe_cm"]["procrustes_aligned"] - pm[:17].mean() / n) < 2e-3

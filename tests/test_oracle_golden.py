@@ -1,11 +1,12 @@
 """The oracle (numpy restatement) against the goldens minted from the unmodified reference, and — when
 /root/reference is mounted — against the live reference module. CPU only."""
 import itertools
+import os
 
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import GOLDEN_DIR as GOLDEN, load_golden
 from oracle import mpl_oracle, ref_loader
 from oracle.cases import CASES, GRID_FLAGS, GRID_BASE, make_inputs
 from openmpl_b200 import spec
@@ -125,6 +126,55 @@ def test_metric_vs_live_reference():
         np.testing.assert_allclose(a[0], b[0])
         np.testing.assert_allclose(a[1], b[1])
     np.testing.assert_allclose(ev.calc_distance_per_dim(pred, gt)[0], mpl_oracle.calc_distance_per_dim(pred, gt)[0])
+
+
+PROCRUSTES_MODES = [(True, "best"), (False, "best"), (True, False), (True, True)]
+
+
+@pytest.mark.parametrize("scaling,reflection", PROCRUSTES_MODES)
+def test_procrustes_restatement_matches_reference_golden(scaling, reflection):
+    """tests/golden/procrustes.npz holds PoseUtils.procrustes outputs of the unmodified reference (oracle/make_goldens.py)."""
+    g = np.load(os.path.join(GOLDEN, "procrustes.npz"))
+    tag = f"s{int(scaling)}_r{reflection}"
+    for i, (A, B) in enumerate(zip(g["A"], g["B"])):
+        d, Z, tf = mpl_oracle.procrustes(A, B, scaling, reflection)
+        assert abs(d - g["d_" + tag][i]) < 1e-12
+        np.testing.assert_allclose(Z, g["Z_" + tag][i], atol=1e-11)
+        np.testing.assert_allclose(tf["rotation"], g["R_" + tag][i], atol=1e-12)
+        np.testing.assert_allclose(tf["scale"], g["scale_" + tag][i], rtol=1e-12)
+        np.testing.assert_allclose(tf["translation"], g["t_" + tag][i], atol=1e-11)
+        if reflection != "best":
+            assert (np.linalg.det(tf["rotation"]) < 0) == bool(reflection)
+
+
+def test_pmpjpe_sums_properties():
+    """A similarity-transformed ground truth aligns back exactly; the aligned error never exceeds the raw one in rms."""
+    g = np.load(os.path.join(GOLDEN, "procrustes.npz"))
+    A = g["A"].astype(np.float64)
+    rng = np.random.default_rng(3)
+    Q = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    acc = mpl_oracle.pmpjpe_sums(1.7 * A @ Q + 0.3, A)
+    J = A.shape[1]
+    assert acc[J + 2] == len(A) and np.all(acc[:J] < 1e-9) and abs(acc[J]) < 1e-12
+    np.testing.assert_allclose(acc[J + 1] / len(A), 1 / 1.7, rtol=1e-12)
+    B = g["B"].astype(np.float64)
+    for a, b in zip(A, B):
+        _, Z, _ = mpl_oracle.procrustes(a, b)
+        assert ((Z - a) ** 2).sum() <= ((b - a) ** 2).sum() + 1e-12
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_procrustes_vs_live_reference():
+    u = ref_loader.load_pose_utils_module().PoseUtils()
+    rng = np.random.default_rng(9)
+    for i in range(20):
+        A, B = rng.normal(size=(17, 3)), rng.normal(size=(17, 3))
+        for scaling, reflection in PROCRUSTES_MODES:
+            d, Z, tf = u.procrustes(A.copy(), B.copy(), scaling=scaling, reflection=reflection)
+            d2, Z2, tf2 = mpl_oracle.procrustes(A, B, scaling, reflection)
+            assert abs(d - d2) < 1e-13
+            np.testing.assert_allclose(Z, Z2, atol=1e-12)
+            np.testing.assert_allclose(tf["rotation"], tf2["rotation"], atol=1e-13)
 
 
 @pytest.mark.parametrize("name", [n for n in CASES if not (CASES[n]["kw"].get("deep_head") or CASES[n]["kw"].get("head_kadkhod")
