@@ -191,6 +191,55 @@ def test_g_wrapper_accepts_the_reference_yaml_configs():
         assert all(a.shape == b.shape for a, b in zip(r.state_dict().values(), m.state_dict().values()))
 
 
+def _small_cfg():
+    from types import SimpleNamespace as NS
+    net = NS(NUM_JOINTS=17, DIM=16, TRANSFORMER_DEPTH=2, TRANSFORMER_HEADS=4, TRANSFORMER_DROP_RATE=0.0,
+             TRANSFORMER_ATTN_DROP_RATE=0.0, TRANSFORMER_DROP_PATH_RATE=0.1, TRANSFORMER_ADD_CONFIDENCE_INPUT=False,
+             TRANSFORMER_MULT_CONFIDENCE_EMB=False, TRANSFORMER_CONCAT_CONFIDENCE_EMB=False,
+             TRANSFORMER_CONFIDENCE_INPUT_AS_THIRD=True, POSE_3D_EMB_LEARNABLE=True, TRANSFORMER_LINEAR_WEIGHTED_MEAN=False,
+             TRANSFORMER_ADD_3D_POS_ENCODING_IN_SPATIAL=False, TRANSFORMER_INPUT_RAYS_AS_TOKEN=True,
+             TRANSFORMER_ADD_3D_POS_ENCODING_TO_RAYS=True, TRANSFORMER_CONF_ATTENTION_UNCERTAINTY_WEIGHT=False,
+             TRANSFORMER_MULTIPLE_SPATIAL_BLOCKS=True, TRANSFORMER_NO_SPT=False, TRANSFORMER_NO_FPT=False,
+             TRANSFORMER_CONFIDENCE_IN_FPT=False, TRANSFORMER_OUTPUT_HEAD_DEEP=False, TRANSFORMER_OUTPUT_HEAD_KADKHOD=False,
+             TRANSFORMER_OUTPUT_HEAD_HIDDEN_DIM=64, TRANSFORMER_FPT_BLOCKS_VIEW_KEYPOINT_TOKENS=False,
+             INIT_WEIGHTS_FROM="scratch", INIT_WEIGHTS=True, PRETRAINED="")
+    ds = NS(TEST_DATASET="multiview_h36m_mpl", TRAIN_VIEWS=None, USE_HELPER_CAMERAS=False, TRAIN_VIEWS_HELPER=None,
+            TRAIN_ON_ALL_CAMERAS=False, TEST_ON_ALL_CAMERAS=False, N_VIEWS_TRAIN_TEST_ALL=7)
+    return NS(NETWORK=net, DATASET=ds)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted")
+def test_reference_checkpoint_files_load_like_valid_mpl(tmp_path):
+    """The two files the reference's `save_checkpoint` writes (utils.py:148-153) -- `checkpoint.pth.tar` = a dict with
+    'state_dict' of the DataParallel-unwrapped MultiView_MPL_G, `model_best.pth.tar` = the bare state_dict -- load into
+    the drop-in the way `valid_mpl.py:164-175` and `load_checkpoint` (utils.py:121-126) load them."""
+    import contextlib, io
+    ref = ref_loader.load_model_module()
+    cfg = _small_cfg()
+    torch.manual_seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = ref.MultiView_MPL_G(cfg)
+    for p_ in r.parameters():                                   # "trained" values: nothing left at its init value
+        p_.data.add_(0.01 * torch.randn_like(p_))
+    states = {"epoch": 7, "state_dict": r.state_dict(), "perf": 1.0, "optimizer": {}}
+    torch.save(states, tmp_path / "checkpoint.pth.tar")
+    torch.save(states["state_dict"], tmp_path / "model_best.pth.tar")
+    # valid_mpl.py:171-175: model.load_state_dict(torch.load(model_state_file), strict=False)
+    m = mb.get_multiview_mpl_net(cfg, is_train=False)
+    res = m.load_state_dict(torch.load(tmp_path / "model_best.pth.tar"), strict=False)
+    assert not res.missing_keys and not res.unexpected_keys
+    for (k, a), (k2, b) in zip(r.state_dict().items(), m.state_dict().items()):
+        assert k == k2 and torch.equal(a, b), k
+    # utils.py:121-126: model.module.load_state_dict(checkpoint['state_dict']) on the DataParallel wrapper
+    m2 = torch.nn.DataParallel(mb.get_multiview_mpl_net(cfg, is_train=False), device_ids=None)
+    ck = torch.load(tmp_path / "checkpoint.pth.tar")
+    m2.module.load_state_dict(ck["state_dict"])
+    assert ck["epoch"] == 7 and all(torch.equal(a, b) for a, b in zip(r.state_dict().values(), m2.module.state_dict().values()))
+    # and back: a checkpoint written from the drop-in loads strictly into the reference module
+    torch.save(m.state_dict(), tmp_path / "final_state.pth.tar")
+    r.load_state_dict(torch.load(tmp_path / "final_state.pth.tar"), strict=True)
+
+
 def test_forward_refuses_training_mode_invalid_flags_and_missing_gpu():
     m = mb.MultiView_MPL(depth=1, num_views=2, embed_dim_ratio=8, num_heads=2)
     x = [torch.zeros(2, 17, 3)] * 2
