@@ -158,81 +158,104 @@ __global__ void __launch_bounds__(256) token_build_vec_kernel(const TokenArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K5 fused head (multiview_mpl.py:425-446, 517-523): one WARP per PAIR of poses.  Channel e of the stripped row lives in
-// lane e % 32, register e / 32 (segments are multiples of 32 wide for the shipped d = 32, so every load is a coalesced
-// 128-byte line); View_norm and the head LayerNorm reduce with shuffles only — no shared memory, no block barriers.
-// The E -> 3J Linear reads each weight row once per pose pair (L1-resident, 3J*E*4 = 111 KB) and reduces across lanes.
+// K5 fused head (multiview_mpl.py:425-446, 517-523).  Pooling of ONE pose by one warp: the stripped row is S = E / 32
+// segments of 32 channels; a lane owns two consecutive channels of two segments at a time (lanes 0-15: segment 2k,
+// lanes 16-31: segment 2k + 1), so every access is an 8-byte load of a fully used 128-byte line and the arithmetic runs
+// on packed f32x2 instructions.  View_norm and the head LayerNorm reduce with shuffles only — no shared memory, no block
+// barriers.  The views are taken four at a time: all 4 x NK loads of a group are in flight together.
 // ---------------------------------------------------------------------------------------------------------------------
-// View_norm -> view-weighted sum -> head LayerNorm of ONE pose, the views taken four at a time: all 4 x NV loads of a
-// group are in flight together and the four row reductions interleave (the kernel is latency bound on these loads).
-template <int NV, bool FULL>  // FULL: E == 32 * NV, no channel predicates
-__device__ __forceinline__ void head_pool_pose(const HeadArgs& a, int64_t b, int lane, const int (&colv)[NV], float (&p)[NV]) {
-  const int E = a.E;
-  const float invE = 1.0f / (float)E;
-  const float wmb = __ldg(a.wm_b);
+__device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
+
+// NK: slots of two segments (ceil(S / 2) <= NK); SS: segment stride in floats, 0 = a.seg_stride; ST: S, 0 = a.E / 32
+template <int NK, int SS, int ST>
+__device__ __forceinline__ void head_pool_pose(const HeadArgs& a, int64_t b, int lane, float2 (&p)[NK]) {
+  const int S = ST ? ST : (a.E >> 5), hi = lane >> 4;
+  const int stride = SS ? SS : a.seg_stride;
+  const int col0 = hi * stride + (lane & 15) * 2;  // slot k: + 2 k stride
+  const int ch0 = hi * 32 + (lane & 15) * 2;       // slot k: + 64 k
+  const float invE = 1.0f / (float)a.E;
+  bool ok[NK];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) p[i] = wmb;
+  for (int k = 0; k < NK; ++k) ok[k] = (ST && 2 * k + 1 < ST) || 2 * k + hi < S;
+  float2 acc[NK];  // sum_v (w_v rstd_v) (x_v - m_v)
+#pragma unroll
+  for (int k = 0; k < NK; ++k) acc[k] = f2(0.f);
+  float wsum = 0.f;
   for (int v0 = 0; v0 < a.V; v0 += 4) {
-    float x[4][NV];
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 x[4][NK];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const bool vok = v0 + u < a.V;
-      const float* r = a.tok + (b * a.V + min(v0 + u, a.V - 1)) * (int64_t)a.tok_w + lane;
+      // a view past V re-reads view V - 1 and is dropped by its zero weight below
+      const float* r = a.tok + (b * a.V + min(v0 + u, a.V - 1)) * (int64_t)a.tok_w + col0;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        x[u][i] = (vok && (FULL || 32 * i + lane < E)) ? r[colv[i]] : 0.f;
-        s[u] += x[u][i];
-      }
+      for (int k = 0; k < NK; ++k) x[u][k] = ok[k] ? *reinterpret_cast<const float2*>(r + 2 * k * stride) : f2(0.f);
     }
-    float m[4], q[4] = {0.f, 0.f, 0.f, 0.f};
+    float m[4], rs[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) m[u] = warp_sum(s[u]) * invE;
+    for (int u = 0; u < 4; ++u) {
+      float2 s = x[u][0];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+      for (int k = 1; k < NK; ++k) s = __fadd2_rn(s, x[u][k]);
+      m[u] = s.x + s.y;
+    }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float d = (FULL || 32 * i + lane < E) ? x[u][i] - m[u] : 0.f;
-        q[u] = fmaf(d, d, q[u]);
+    for (int u = 0; u < 4; ++u) m[u] = warp_sum(m[u]) * invE;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 nm = f2(-m[u]);
+      float2 q = f2(0.f);
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        x[u][k] = ok[k] ? __fadd2_rn(x[u][k], nm) : f2(0.f);
+        q = __ffma2_rn(x[u][k], x[u][k], q);
       }
-    float rs[4];
+      rs[u] = q.x + q.y;
+    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) rs[u] = (v0 + u < a.V) ? rsqrtf(warp_sum(q[u]) * invE + 1e-6f) * __ldg(a.wm_w + min(v0 + u, a.V - 1)) : 0.f;
-    const float wsum = ((v0 < a.V) ? __ldg(a.wm_w + v0) : 0.f) + ((v0 + 1 < a.V) ? __ldg(a.wm_w + v0 + 1) : 0.f) +
-                       ((v0 + 2 < a.V) ? __ldg(a.wm_w + v0 + 2) : 0.f) + ((v0 + 3 < a.V) ? __ldg(a.wm_w + v0 + 3) : 0.f);
+    for (int u = 0; u < 4; ++u) {
+      const float w = (v0 + u < a.V) ? __ldg(a.wm_w + min(v0 + u, a.V - 1)) : 0.f;
+      rs[u] = (v0 + u < a.V) ? rsqrtf(warp_sum(rs[u]) * invE + 1e-6f) * w : 0.f;
+      wsum += w;
+    }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int e = 32 * i + lane;
-      if (FULL || e < E) {
-        // sum_v w_v ((x - m_v) rstd_v gamma + beta) = gamma * sum_v (w_v rstd_v)(x - m_v) + beta * sum_v w_v
-        float acc = 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const float2 r2 = f2(rs[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc = fmaf(rs[u], x[u][i] - m[u], acc);
-        p[i] += fmaf(acc, __ldg(a.vn_w + e), wsum * __ldg(a.vn_b + e));
-      }
+      for (int k = 0; k < NK; ++k) acc[k] = __ffma2_rn(r2, x[u][k], acc[k]);
     }
   }
-  float s = 0.f;
+  // sum_v w_v ((x - m_v) rstd_v gamma + beta) + b = gamma * acc + beta * sum_v w_v + b
+  const float2 ws2 = f2(wsum), wmb2 = f2(__ldg(a.wm_b));
+  float2 s = f2(0.f);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) s += (FULL || 32 * i + lane < E) ? p[i] : 0.f;
-  const float mean = warp_sum(s) * invE;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float d = (FULL || 32 * i + lane < E) ? p[i] - mean : 0.f;
-    q = fmaf(d, d, q);
+  for (int k = 0; k < NK; ++k) {
+    const int e = ch0 + 64 * k;
+    p[k] = ok[k] ? __ffma2_rn(acc[k], __ldg(reinterpret_cast<const float2*>(a.vn_w + e)),
+                              __ffma2_rn(ws2, __ldg(reinterpret_cast<const float2*>(a.vn_b + e)), wmb2))
+                 : f2(0.f);
+    s = __fadd2_rn(s, p[k]);
   }
-  const float rstd = rsqrtf(warp_sum(q) * invE + 1e-5f);  // head LayerNorm: default eps (multiview_mpl.py:284)
+  const float2 nmean = f2(-warp_sum(s.x + s.y) * invE);
+  float2 q = f2(0.f);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int e = 32 * i + lane;
-    p[i] = (FULL || e < E) ? fmaf((p[i] - mean) * rstd, __ldg(a.hn_w + e), __ldg(a.hn_b + e)) : 0.f;
+  for (int k = 0; k < NK; ++k) {
+    p[k] = ok[k] ? __fadd2_rn(p[k], nmean) : f2(0.f);
+    q = __ffma2_rn(p[k], p[k], q);
+  }
+  const float2 rstd = f2(rsqrtf(warp_sum(q.x + q.y) * invE + 1e-5f));  // head LayerNorm: default eps (multiview_mpl.py:284)
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int e = ch0 + 64 * k;
+    if (ok[k])
+      p[k] = __ffma2_rn(__fmul2_rn(p[k], rstd), __ldg(reinterpret_cast<const float2*>(a.hn_w + e)),
+                        __ldg(reinterpret_cast<const float2*>(a.hn_b + e)));
   }
 }
 
 // One CTA (8 warps) per group of 16 poses (= one MMA row tile).
-//   Phase 1: each warp pools two poses, one after the other, four views in flight at a time (ray-half strip -> View_norm -> view-weighted sum -> head LayerNorm; registers +
-//            shuffles only, lane = channel % 32) and parks the result in shared memory as pool[pose][channel].
+//   Phase 1: each warp pools two poses, one after the other, four views in flight at a time (ray-half strip ->
+//            View_norm -> view-weighted sum -> head LayerNorm; registers + shuffles only, packed f32x2 arithmetic) and
+//            parks the result in shared memory as pool[pose][channel].
 //   Phase 2: the E -> 3J Linear on the tensor cores at fp32-grade accuracy: both operands are split into fp16 hi + lo
 //            parts (x = hi + lo to ~2^-22; the weights are scaled by 2^10 first so their lo parts stay normal) and every
 //            product is three mma.sync m16n8k16 (hi*hi + hi*lo + lo*hi, fp32 accumulate).  The k tiles are dealt round-
@@ -257,7 +280,7 @@ __device__ __forceinline__ void mma_f16_acc(float (&c)[4], const uint32_t (&a)[4
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int NV, bool FULL>
+template <int NK, int SS, int ST>
 __global__ void __launch_bounds__(HEAD_WARPS * 32, 2) head_block_kernel(const HeadArgs a) {
   extern __shared__ __align__(16) float hsm[];  // pool [HEAD_PB][pitch]; reused as partial [HEAD_WARPS][HEAD_PB][64]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -266,22 +289,19 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, 2) head_block_kernel(const He
   const int pitch = E + 8;          // (E + 8) % 32 == 8 for E % 32 == 0: conflict-free 8-byte A-fragment loads
   const int ktiles = E >> 4, ntiles = (a.out_dim + 7) >> 3;
   const int64_t groups = (a.B + HEAD_PB - 1) / HEAD_PB;
-  // column of channel group i in the token row: 32-channel segments seg_stride apart (ray halves stripped, d = 32) or
-  // one contiguous row (seg_len == E, seg_stride == 32 passed by the launcher): one multiply, no division
-  int colv[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) colv[i] = i * a.seg_stride;
+  const int S = E >> 5;
+  const int ch0 = (lane >> 4) * 32 + (lane & 15) * 2;  // the lane's channel pair of slot 0 (head_pool_pose)
   for (int64_t gi = blockIdx.x; gi < groups; gi += gridDim.x) {
     const int64_t b0 = gi * HEAD_PB;
     // ---- phase 1 ----
 #pragma unroll 1
     for (int pi = 0; pi < 2; ++pi) {
       const int p0 = warp * 2 + pi;
-      float pp[NV];
-      head_pool_pose<NV, FULL>(a, min(b0 + p0, a.B - 1), lane, colv, pp);
+      float2 pp[NK];
+      head_pool_pose<NK, SS, ST>(a, min(b0 + p0, a.B - 1), lane, pp);
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (FULL || 32 * i + lane < E) hsm[p0 * pitch + 32 * i + lane] = pp[i];
+      for (int k = 0; k < NK; ++k)
+        if (2 * k + (lane >> 4) < S) *reinterpret_cast<float2*>(hsm + p0 * pitch + ch0 + 64 * k) = pp[k];
     }
     __syncthreads();
     // ---- phase 2 ----
@@ -386,21 +406,30 @@ int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s) {
 }
 
 int try_launch_head_warp(const HeadArgs& a, cudaStream_t s) {
-  if (a.E > 32 * 17 || a.E % 32 != 0 || a.out_dim > 64 || a.hwT == nullptr || !(a.seg_len == 32 || a.seg_len == a.E)) return 1;
+  if (a.E > 32 * 18 || a.E % 32 != 0 || a.out_dim > 64 || a.hwT == nullptr || !(a.seg_len == 32 || a.seg_len == a.E)) return 1;
+  const int stride = a.seg_len == a.E ? 32 : a.seg_stride;  // contiguous row: segment i starts at column 32 i
+  auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+  if (!aligned8(a.tok) || a.tok_w % 2 != 0 || stride % 2 != 0 || !aligned8(a.vn_w) || !aligned8(a.vn_b) || !aligned8(a.hn_w) ||
+      !aligned8(a.hn_b))
+    return 1;
   if (a.B == 0) return MPL_OK;
   const int64_t blocks = std::min<int64_t>(ceil_div(a.B, HEAD_PB), (int64_t)kNumSMs * 2);
   const size_t smem = std::max((size_t)(a.E + 8) * HEAD_PB, (size_t)HEAD_WARPS * HEAD_PB * 64) * sizeof(float);
-  static bool attr_set[64][3] = {};
+  static bool attr_set[64][4] = {};
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
-  const int which = (a.E == 32 * 17) ? 2 : (a.E > 32 * 9 ? 1 : 0);
-  auto kern = which == 2 ? head_block_kernel<17, true> : (which == 1 ? head_block_kernel<17, false> : head_block_kernel<9, false>);
+  // the shipped width (17 segments; ray-stripped or contiguous rows) with everything compiled in, else runtime
+  // stride / segment count with 9 slots (up to 18 segments) or 5 (up to 10)
+  const int which = a.E == 32 * 17 && stride == 64 ? 0 : (a.E == 32 * 17 && stride == 32 ? 1 : (a.E > 32 * 10 ? 2 : 3));
+  void (*const kerns[4])(const HeadArgs) = {head_block_kernel<9, 64, 17>, head_block_kernel<9, 32, 17>, head_block_kernel<9, 0, 0>,
+                                            head_block_kernel<5, 0, 0>};
+  auto kern = kerns[which];
   if (dev < 0 || dev >= 64 || !attr_set[dev][which]) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) attr_set[dev][which] = true;
   }
   HeadArgs b = a;
-  if (a.seg_len == a.E) b.seg_stride = 32;  // contiguous row: channel group i starts at column 32 i
+  b.seg_stride = stride;
   kern<<<(unsigned)blocks, HEAD_WARPS * 32, smem, s>>>(b);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
