@@ -670,6 +670,11 @@ template <> struct ChunkIO<__nv_bfloat16, 8> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
   }
+  static __device__ __forceinline__ void unpack2(const uint4& u, float2 (&f)[4]) {  // element pairs for f32x2 arithmetic
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
     unpack(*reinterpret_cast<const uint4*>(p), f);
   }
@@ -687,6 +692,10 @@ template <> struct ChunkIO<__nv_bfloat16, 4> {
     f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
     f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
   }
+  static __device__ __forceinline__ void unpack2(const uint2& u, float2 (&f)[2]) {
+    f[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+    f[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[4]) {
     unpack(*reinterpret_cast<const uint2*>(p), f);
   }
@@ -701,6 +710,7 @@ template <> struct ChunkIO<__nv_bfloat16, 4> {
 template <> struct ChunkIO<float, 4> {
   using Pack = float4;
   static __device__ __forceinline__ void unpack(const float4& u, float (&f)[4]) { f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; }
+  static __device__ __forceinline__ void unpack2(const float4& u, float2 (&f)[2]) { f[0] = make_float2(u.x, u.y); f[1] = make_float2(u.z, u.w); }
   static __device__ __forceinline__ void load(const float* p, float (&f)[4]) { unpack(*reinterpret_cast<const float4*>(p), f); }
   static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
@@ -730,21 +740,44 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
       k[v] = *reinterpret_cast<const Pack*>(row0 + (int64_t)v * 3 * D + D + c * CE);
       vv[v] = *reinterpret_cast<const Pack*>(row0 + (int64_t)v * 3 * D + 2 * D + c * CE);
     }
+    // the dot products and the probability-weighted sums below run on packed f32x2 FMAs (element pairs of the chunk)
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float qi[CE];
-      ChunkIO<T, CE>::unpack(q[i], qi);
+      float2 qi[CE / 2];
+      ChunkIO<T, CE>::unpack2(q[i], qi);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        float kj[CE];
-        ChunkIO<T, CE>::unpack(k[j], kj);
-        float a = 0.f;
+        float2 kj[CE / 2];
+        ChunkIO<T, CE>::unpack2(k[j], kj);
+        float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < CE; ++e) a = fmaf(qi[e], kj[e], a);
-        part[c * (V * V) + i * V + j] = a;
+        for (int e = 0; e < CE / 2; ++e) a = __ffma2_rn(qi[e], kj[e], a);
+        part[c * (V * V) + i * V + j] = a.x + a.y;
       }
     }
     __syncthreads();
+    if ((V & (V - 1)) == 0 && blockDim.x % V == 0) {
+      // one thread per (head, query, key): sum the head's chunk partials (17 conflict-free loads instead of a 68-long
+      // chain on one warp), softmax across the V lanes of the row with shuffles
+      const unsigned mask = __activemask();
+      const int total = H * V * V;
+      for (int base = 0; base < total; base += blockDim.x) {
+        const int idx = base + threadIdx.x;
+        const bool live = idx < total;
+        const int h = (live ? idx : 0) / (V * V), ij = (live ? idx : 0) % (V * V);
+        float a = 0.f;
+        for (int cc = 0; cc < cph; ++cc) a += part[(h * cph + cc) * (V * V) + ij];
+        a *= scale;
+        float mx = a;
+#pragma unroll
+        for (int o = V / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(mask, mx, o));
+        const float e = expf(a - mx);
+        float sum = e;
+#pragma unroll
+        for (int o = V / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(mask, sum, o);
+        if (live) prob[idx] = e / sum;
+      }
+    } else
     // H * V query rows: sum the head's chunk partials, softmax over the V keys
     for (int r = threadIdx.x; r < H * V; r += blockDim.x) {
       const int h = r / V, i = r % V;
@@ -766,29 +799,32 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
     }
     __syncthreads();
     const int h = c / cph;
-    float o[V][CE];
+    float2 o2[V][CE / 2];
 #pragma unroll
     for (int i = 0; i < V; ++i)
 #pragma unroll
-      for (int e = 0; e < CE; ++e) o[i][e] = 0.f;
+      for (int e = 0; e < CE / 2; ++e) o2[i][e] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float vj[CE];
-      ChunkIO<T, CE>::unpack(vv[j], vj);
+      float2 vj[CE / 2];
+      ChunkIO<T, CE>::unpack2(vv[j], vj);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const float pj = prob[h * (V * V) + i * V + j];
+        const float2 pj2 = make_float2(pj, pj);
 #pragma unroll
-        for (int e = 0; e < CE; ++e) o[i][e] = fmaf(pj, vj[e], o[i][e]);
+        for (int e = 0; e < CE / 2; ++e) o2[i][e] = __ffma2_rn(pj2, vj[e], o2[i][e]);
       }
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      if (TF32_OUT) {
+      float o[CE];
 #pragma unroll
-        for (int e = 0; e < CE; ++e) o[i][e] = round_tf32(o[i][e]);
+      for (int e = 0; e < CE / 2; ++e) {
+        o[2 * e] = TF32_OUT ? round_tf32(o2[i][e].x) : o2[i][e].x;
+        o[2 * e + 1] = TF32_OUT ? round_tf32(o2[i][e].y) : o2[i][e].y;
       }
-      ChunkIO<T, CE>::store(out + (pose * V + i) * (int64_t)D + c * CE, o[i]);
+      ChunkIO<T, CE>::store(out + (pose * V + i) * (int64_t)D + c * CE, o);
     }
     __syncthreads();  // prob / part are reused by the next pose
   }
