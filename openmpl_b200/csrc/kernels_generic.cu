@@ -717,12 +717,12 @@ template <> struct ChunkIO<float, 4> {
   }
 };
 
-template <typename T, int V, int CE, bool TF32_OUT>
+template <typename T, int V, int CE, bool TF32_OUT, int CPH>  // CPH: chunks per head compiled in (17 for the shipped widths), 0 = hd / CE
 __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restrict__ qkv, T* __restrict__ out, int64_t poses,
                                                               int D, int hd, float scale) {
   extern __shared__ float sm[];       // partial [nchunks][V*V] then probs [H][V*V]
   const int nchunks = D / CE;         // == blockDim.x
-  const int cph = hd / CE;            // chunks per head
+  const int cph = CPH ? CPH : hd / CE;  // chunks per head
   const int H = D / hd;
   const int c = threadIdx.x;
   float* part = sm;
@@ -766,7 +766,13 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
         const bool live = idx < total;
         const int h = (live ? idx : 0) / (V * V), ij = (live ? idx : 0) % (V * V);
         float a = 0.f;
-        for (int cc = 0; cc < cph; ++cc) a += part[(h * cph + cc) * (V * V) + ij];
+        const float* pp = part + h * cph * (V * V) + ij;
+        if (CPH) {
+#pragma unroll
+          for (int cc = 0; cc < CPH; ++cc) a += pp[cc * (V * V)];
+        } else {
+          for (int cc = 0; cc < cph; ++cc) a += pp[cc * (V * V)];
+        }
         a *= scale;
         float mx = a;
 #pragma unroll
@@ -838,7 +844,7 @@ static int launch_attention_views(const T* qkv, T* out, int64_t poses, int V, in
   const unsigned grid = (unsigned)std::min<int64_t>(poses, (int64_t)kNumSMs * 32);
 #define MPL_AV(VV)                                                                                                      \
   case VV: {                                                                                                            \
-    auto kern = attention_views_kernel<T, VV, CE, TF32_OUT>;                                                            \
+    auto kern = hd / CE == 17 ? attention_views_kernel<T, VV, CE, TF32_OUT, 17> : attention_views_kernel<T, VV, CE, TF32_OUT, 0>; \
     if (smem > 48 * 1024) MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, threads, smem, s>>>(qkv, out, poses, D, hd, scale);                                                    \
   } break;
