@@ -717,9 +717,11 @@ template <> struct ChunkIO<float, 4> {
   }
 };
 
-template <typename T, int V, int CE, bool TF32_OUT, int CPH>  // CPH: chunks per head compiled in (17 for the shipped widths), 0 = hd / CE
+// DT / CPH: row width and chunks per head compiled in for the shipped widths (1088 / 544, 17), 0 = the runtime arguments
+template <typename T, int V, int CE, bool TF32_OUT, int DT, int CPH>
 __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restrict__ qkv, T* __restrict__ out, int64_t poses,
-                                                              int D, int hd, float scale) {
+                                                              int D_arg, int hd, float scale) {
+  const int D = DT ? DT : D_arg;
   extern __shared__ float sm[];       // partial [nchunks][V*V] then probs [H][V*V]
   const int nchunks = D / CE;         // == blockDim.x
   const int cph = CPH ? CPH : hd / CE;  // chunks per head
@@ -741,18 +743,21 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
       vv[v] = *reinterpret_cast<const Pack*>(row0 + (int64_t)v * 3 * D + 2 * D + c * CE);
     }
     // the dot products and the probability-weighted sums below run on packed f32x2 FMAs (element pairs of the chunk)
+    {
+      float2 k2[V][CE / 2];  // the keys are widened once, the queries one at a time
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float2 qi[CE / 2];
-      ChunkIO<T, CE>::unpack2(q[i], qi);
+      for (int j = 0; j < V; ++j) ChunkIO<T, CE>::unpack2(k[j], k2[j]);
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        float2 kj[CE / 2];
-        ChunkIO<T, CE>::unpack2(k[j], kj);
-        float2 a = make_float2(0.f, 0.f);
+      for (int i = 0; i < V; ++i) {
+        float2 qi[CE / 2];
+        ChunkIO<T, CE>::unpack2(q[i], qi);
 #pragma unroll
-        for (int e = 0; e < CE / 2; ++e) a = __ffma2_rn(qi[e], kj[e], a);
-        part[c * (V * V) + i * V + j] = a.x + a.y;
+        for (int j = 0; j < V; ++j) {
+          float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < CE / 2; ++e) a = __ffma2_rn(qi[e], k2[j][e], a);
+          part[c * (V * V) + i * V + j] = a.x + a.y;
+        }
       }
     }
     __syncthreads();
@@ -844,7 +849,8 @@ static int launch_attention_views(const T* qkv, T* out, int64_t poses, int V, in
   const unsigned grid = (unsigned)std::min<int64_t>(poses, (int64_t)kNumSMs * 32);
 #define MPL_AV(VV)                                                                                                      \
   case VV: {                                                                                                            \
-    auto kern = hd / CE == 17 ? attention_views_kernel<T, VV, CE, TF32_OUT, 17> : attention_views_kernel<T, VV, CE, TF32_OUT, 0>; \
+    auto kern = (D == 136 * CE && hd == 17 * CE) ? attention_views_kernel<T, VV, CE, TF32_OUT, 136 * CE, 17>                    \
+                                                 : attention_views_kernel<T, VV, CE, TF32_OUT, 0, 0>;                            \
     if (smem > 48 * 1024) MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, threads, smem, s>>>(qkv, out, poses, D, hd, scale);                                                    \
   } break;
