@@ -35,10 +35,13 @@ constexpr int QP = 104;     // fp16 row pitch of the q|k|v staging buffer (96 + 
                             // {0,20,8,28,16,4,24,12}: conflict-free half2 C-fragment stores, A-fragment loads and 16 B row loads
 constexpr int QPW = QP / 2;
 
-// fragment-packed layer blob (32-bit words): B fragments of the four weight matrices, then the fp32 vectors
+// fragment-packed layer blob (32-bit words): B fragments of the four weight matrices, then the four bias vectors as C
+// operands: per output tile column nt and quad lane t the 16-byte group (b[8nt+2t], b[8nt+2t+1], same, same) -- one
+// LDS.128 lands in an aligned register quad that the first MMA of the tile takes as its C operand as is.  The LayerNorm
+// weights are not stored: gamma / beta are folded into the QKV / fc1 weights and biases (spt_pack_kernel).
 constexpr int OFF_QKV = 0, OFF_PROJ = 1536, OFF_FC1 = 2048, OFF_FC2 = 3072, FRAG_WORDS = 4096;
-constexpr int F_N1W = 0, F_N1B = 32, F_QKVB = 64, F_PROJB = 160, F_N2W = 192, F_N2B = 224, F_FC1B = 256, F_FC2B = 320;
-constexpr int VEC_WORDS = 352, LAYER_WORDS = FRAG_WORDS + VEC_WORDS;  // 4448 words = 17792 bytes
+constexpr int F_QKVB = 0, F_PROJB = 192, F_FC1B = 256, F_FC2B = 384;
+constexpr int VEC_WORDS = 448, LAYER_WORDS = FRAG_WORDS + VEC_WORDS;  // 4544 words = 18176 bytes
 
 constexpr int SMEM_W = 2 * LAYER_WORDS * 4;
 constexpr int SMEM_QKV = SROWS * QP * 2;
@@ -59,11 +62,11 @@ __device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// first k-step of a tile: D = A.B + (bx, by, bx, by) -- the bias enters as the C operand, no accumulator initialisation
-__device__ __forceinline__ void mma_f16_16816_bias(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float bx, float by) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+// first k-step of a tile: D = A.B + (bx, by, bx, by) -- the bias quad enters as the C operand, no accumulator initialisation
+__device__ __forceinline__ void mma_f16_16816_bias(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const float4& c) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
                : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(bx), "f"(by));
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c.x), "f"(c.y), "f"(c.z), "f"(c.w));
 }
 
 __device__ __forceinline__ float quad_sum(float v) {
@@ -72,29 +75,29 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v;
 }
 
-// LayerNorm (eps 1e-6, biased variance) of the two rows a lane co-owns, straight to fp16 A fragments (2 k-tiles of 16)
-__device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], const float* __restrict__ gw, const float* __restrict__ gb,
-                                            int t, uint32_t (&a)[2][4]) {
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt) { s0 += x[nt][0] + x[nt][1]; s1 += x[nt][2] + x[nt][3]; }
-  const float m0 = quad_sum(s0) * (1.0f / D), m1 = quad_sum(s1) * (1.0f / D);
-  float q0 = 0.f, q1 = 0.f;
+// LayerNorm (eps 1e-6, biased variance) of the two rows a lane co-owns, straight to fp16 A fragments (2 k-tiles of 16).
+// Only the normalisation happens here: gamma is folded into the columns of the following weight matrix and beta into its
+// bias when the layer is packed (spt_pack_kernel), so a row costs one FMA per element: y = x * rstd - mean * rstd.
+__device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], uint32_t (&a)[2][4]) {
+  // one pass: sum and sum of squares together (32 values of O(1): E[x^2] - mean^2 in fp32 is far inside the fp16 operand
+  // rounding that follows), the four quad reductions issued back to back
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    const float d0 = x[nt][0] - m0, d1 = x[nt][1] - m0, d2 = x[nt][2] - m1, d3 = x[nt][3] - m1;
-    q0 += d0 * d0 + d1 * d1;
-    q1 += d2 * d2 + d3 * d3;
+    s0 += x[nt][0] + x[nt][1];
+    s1 += x[nt][2] + x[nt][3];
+    q0 = fmaf(x[nt][0], x[nt][0], fmaf(x[nt][1], x[nt][1], q0));
+    q1 = fmaf(x[nt][2], x[nt][2], fmaf(x[nt][3], x[nt][3], q1));
   }
-  const float r0 = rsqrtf(quad_sum(q0) * (1.0f / D) + 1e-6f), r1 = rsqrtf(quad_sum(q1) * (1.0f / D) + 1e-6f);
+  s0 = quad_sum(s0); s1 = quad_sum(s1); q0 = quad_sum(q0); q1 = quad_sum(q1);
+  const float m0 = s0 * (1.0f / D), m1 = s1 * (1.0f / D);
+  const float r0 = rsqrtf(fmaxf(fmaf(-m0, m0, q0 * (1.0f / D)), 0.f) + 1e-6f);
+  const float r1 = rsqrtf(fmaxf(fmaf(-m1, m1, q1 * (1.0f / D)), 0.f) + 1e-6f);
+  const float n0 = -m0 * r0, n1 = -m1 * r1;
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    const float2 w = *reinterpret_cast<const float2*>(gw + 8 * nt + 2 * t);
-    const float2 b = *reinterpret_cast<const float2*>(gb + 8 * nt + 2 * t);
-    const float y0 = (x[nt][0] - m0) * r0 * w.x + b.x, y1 = (x[nt][1] - m0) * r0 * w.y + b.y;
-    const float y2 = (x[nt][2] - m1) * r1 * w.x + b.x, y3 = (x[nt][3] - m1) * r1 * w.y + b.y;
-    a[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(y0, y1);
-    a[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(y2, y3);
+    a[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(fmaf(x[nt][0], r0, n0), fmaf(x[nt][1], r0, n0));
+    a[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(fmaf(x[nt][2], r1, n1), fmaf(x[nt][3], r1, n1));
   }
 }
 
@@ -104,11 +107,11 @@ template <int KT>
 __device__ __forceinline__ void gemm_tile2(float (&c0)[4], float (&c1)[4], const uint32_t (&a0)[KT][4], const uint32_t (&a1)[KT][4],
                                            const uint32_t* __restrict__ wfrag, int nt, const float* __restrict__ bias, int lane,
                                            int t) {
-  const float2 b2 = *reinterpret_cast<const float2*>(bias + 8 * nt + 2 * t);
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + 16 * nt + 4 * t);
   {
     const uint2 b = *reinterpret_cast<const uint2*>(wfrag + ((nt * KT) * 32 + lane) * 2);
-    mma_f16_16816_bias(c0, a0[0], b.x, b.y, b2.x, b2.y);
-    mma_f16_16816_bias(c1, a1[0], b.x, b.y, b2.x, b2.y);
+    mma_f16_16816_bias(c0, a0[0], b.x, b.y, b4);
+    mma_f16_16816_bias(c1, a1[0], b.x, b.y, b4);
   }
 #pragma unroll
   for (int kt = 1; kt < KT; ++kt) {
@@ -266,8 +269,8 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
       // ---- LN1 + QKV -> fp16 staging (q pre-scaled by scale * log2 e through the packed weights) ----
       {
         uint32_t a0[2][4], a1[2][4];
-        ln_to_afrag(x[0], wv + F_N1W, wv + F_N1B, t, a0);
-        ln_to_afrag(x[1], wv + F_N1W, wv + F_N1B, t, a1);
+        ln_to_afrag(x[0], a0);
+        ln_to_afrag(x[1], a1);
 #pragma unroll
         for (int nt = 0; nt < 12; ++nt) {
           float c0[4], c1[4];
@@ -472,8 +475,8 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
       // ---- LN2 + fc1 + GELU + fc2 + residual ----
       {
         uint32_t a0[2][4], a1[2][4];
-        ln_to_afrag(x[0], wv + F_N2W, wv + F_N2B, t, a0);
-        ln_to_afrag(x[1], wv + F_N2W, wv + F_N2B, t, a1);
+        ln_to_afrag(x[0], a0);
+        ln_to_afrag(x[1], a1);
         uint32_t h0[4][4], h1[4][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -627,21 +630,30 @@ __global__ void spt_pack_kernel(const SptPackArgs a) {
       if (third == 0) sc = a.q_scale;
     }
     const int k0 = (kind == 1) ? chan_of_pos(k) : k, k1 = (kind == 1) ? chan_of_pos(k + 1) : k + 1;
-    a.dst[i] = pack_f16_rn(W[n * K + k0] * sc, W[n * K + k1] * sc);
+    // the LayerNorm in front of QKV / fc1 leaves its gamma here (W' = W diag(gamma)) and its beta in the bias below
+    const float* gam = (i < OFF_PROJ) ? a.n1w : ((i >= OFF_FC1 && i < OFF_FC2) ? a.n2w : nullptr);
+    const float g0 = gam ? gam[k0] : 1.0f, g1 = gam ? gam[k1] : 1.0f;
+    a.dst[i] = pack_f16_rn(W[n * K + k0] * sc * g0, W[n * K + k1] * sc * g1);
   } else {
     const int f = i - FRAG_WORDS;
+    // bias quads: word (16 nt + 4 t + comp) of a section = bias of output column 8 nt + 2 t + (comp & 1)
+    const int sec = f < F_PROJB ? 0 : (f < F_FC1B ? 1 : (f < F_FC2B ? 2 : 3));
+    const int idx = f - (sec == 0 ? F_QKVB : (sec == 1 ? F_PROJB : (sec == 2 ? F_FC1B : F_FC2B)));
+    const int col = 8 * (idx / 16) + 2 * ((idx % 16) / 4) + (idx & 1);
     float v;
-    if (f < F_N1B) v = a.n1w[f - F_N1W];
-    else if (f < F_QKVB) v = a.n1b[f - F_N1B];
-    else if (f < F_PROJB) {
-      const int pos = f - F_QKVB, third = pos / 32;
-      v = a.qkvb ? a.qkvb[third * 32 + chan_of_pos(pos % 32)] * (third == 0 ? a.q_scale : 1.0f) : 0.f;
+    if (sec == 0) {
+      const int third = col / 32, n = third * 32 + chan_of_pos(col % 32);
+      v = a.qkvb ? a.qkvb[n] : 0.f;
+      for (int k = 0; k < 32; ++k) v = fmaf(a.qkvw[n * 32 + k], a.n1b[k], v);  // b' = b + W beta
+      v *= (third == 0 ? a.q_scale : 1.0f);
+    } else if (sec == 1) {
+      v = a.projb[col];
+    } else if (sec == 2) {
+      v = a.fc1b[col];
+      for (int k = 0; k < 32; ++k) v = fmaf(a.fc1w[col * 32 + k], a.n2b[k], v);
+    } else {
+      v = a.fc2b[col];
     }
-    else if (f < F_N2W) v = a.projb[f - F_PROJB];
-    else if (f < F_N2B) v = a.n2w[f - F_N2W];
-    else if (f < F_FC1B) v = a.n2b[f - F_N2B];
-    else if (f < F_FC2B) v = a.fc1b[f - F_FC1B];
-    else v = a.fc2b[f - F_FC2B];
     a.dst[i] = __float_as_uint(v);
   }
 }
