@@ -8,7 +8,8 @@
 //     was bound by the LSU pipe); the two resident CTAs run out of phase, so the attention phase of one (LSU + MUFU)
 //     overlaps the MMA / GELU phases of the other (one 544-thread CTA per SM issued only 48 % of the cycles);
 //   * the residual stream lives in registers as mma.sync C fragments (32 fp32 per lane) across all applications;
-//   * LayerNorm is computed on the fragments (quad shuffles); the four Linears are fp16 mma.sync m16n8k16 with fp32
+//   * LayerNorm is computed on the fragments (quad shuffles, one pass, gamma / beta folded into the following weights
+//     and biases at pack time); the four Linears are fp16 mma.sync m16n8k16 with fp32
 //     accumulation (fp16 rather than bf16 operands: 3 more mantissa bits, and every operand here is O(1) after
 //     LayerNorm; conversions saturate), weights pre-packed in fragment order, double-buffered via cp.async;
 //   * q|k|v of the 32 sets are staged once in shared memory as fp16 with the channels of each head PAIR interleaved
