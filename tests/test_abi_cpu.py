@@ -269,3 +269,17 @@ def test_product_path_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(dirpath, f)
                 assert "mpl_oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_missing_library_fails_loudly_without_fallback(tmp_path):
+    """No CPU / eager fallback: with the shared library absent (MPL_B200_LIB pointing nowhere) the first use raises."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); "
+            "from openmpl_b200.models import multiview_mpl_b200 as mb; "
+            "m = mb.MultiView_MPL(depth=1, num_views=2); "
+            "from openmpl_b200 import _lib; _lib.lib()") % ROOT
+    env = dict(os.environ, MPL_B200_LIB=str(tmp_path / "nowhere" / "libmpl_b200.so"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "is missing" in r.stderr and "no fallback" in r.stderr
