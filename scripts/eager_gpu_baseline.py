@@ -21,7 +21,7 @@ cfg = spec.make_config(**kw)
 dev = torch.device("cuda", 0)
 weights = {k: torch.from_numpy(v).to(dev) for k, v in synth.named_weights(spec.param_spec(cfg), seed=0).items()}
 rig = synth.make_rig(4)
-for B in (256, 16384):
+for B in [int(a) for a in sys.argv[1:]] or (256, 16384, 65536):
     batch = synth.make_batch(B, rig, seed=1)
     x = [torch.from_numpy(batch[k]).to(dev) for k in ("poses", "rays", "centers")]
     for mode in ("fp32", "tf32", "bf16-autocast"):
