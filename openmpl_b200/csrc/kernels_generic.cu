@@ -761,7 +761,6 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
       }
     }
     __syncthreads();
-    const float* pfin = prob;  // where the PV stage finds the probabilities
     if ((V & (V - 1)) == 0 && blockDim.x % V == 0) {
       // one thread per (head, query, key): sum the head's chunk partials (17 conflict-free loads instead of a 68-long
       // chain on one warp), softmax across the V lanes of the row with shuffles
@@ -789,35 +788,25 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
         for (int o = V / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(mask, sum, o);
         if (live) prob[idx] = e / sum;
       }
-    } else {
-      // any V: one thread per (head, query, key) sums the head's chunk partials into the scaled score, then (after a
-      // barrier) normalises its own entry against the V scores of its row -- V redundant exps per thread instead of a
-      // cph * V-long load chain on H * V threads
-      const int total = H * V * V;
-      for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int h = idx / (V * V), ij = idx % (V * V);
-        const float* pp = part + h * cph * (V * V) + ij;
+    } else
+    // H * V query rows: sum the head's chunk partials, softmax over the V keys
+    for (int r = threadIdx.x; r < H * V; r += blockDim.x) {
+      const int h = r / V, i = r % V;
+      float sc[V];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
         float a = 0.f;
-        if (CPH) {
-#pragma unroll
-          for (int cc = 0; cc < CPH; ++cc) a += pp[cc * (V * V)];
-        } else {
-          for (int cc = 0; cc < cph; ++cc) a += pp[cc * (V * V)];
-        }
-        prob[idx] = a * scale;
+        for (int cc = 0; cc < cph; ++cc) a += part[(h * cph + cc) * (V * V) + i * V + j];
+        sc[j] = a * scale;
+        mx = fmaxf(mx, sc[j]);
       }
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const float* row = prob + idx - idx % V;
-        float mx = row[0];
+      float sum = 0.f;
 #pragma unroll
-        for (int j = 1; j < V; ++j) mx = fmaxf(mx, row[j]);
-        float sum = 0.f;
+      for (int j = 0; j < V; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+      const float inv = 1.0f / sum;
 #pragma unroll
-        for (int j = 0; j < V; ++j) sum += expf(row[j] - mx);
-        part[idx] = expf(prob[idx] - mx) / sum;  // the partials are consumed: their buffer takes the probabilities
-      }
-      pfin = part;
+      for (int j = 0; j < V; ++j) prob[h * (V * V) + i * V + j] = sc[j] * inv;
     }
     __syncthreads();
     const int h = c / cph;
@@ -832,7 +821,7 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
       ChunkIO<T, CE>::unpack2(vv[j], vj);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float pj = pfin[h * (V * V) + i * V + j];
+        const float pj = prob[h * (V * V) + i * V + j];
         const float2 pj2 = make_float2(pj, pj);
 #pragma unroll
         for (int e = 0; e < CE / 2; ++e) o2[i][e] = __ffma2_rn(pj2, vj[e], o2[i][e]);
