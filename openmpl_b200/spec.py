@@ -7,7 +7,7 @@ host module, the oracle, the golden generator and the C-ABI all agree on one par
 from __future__ import annotations
 
 from collections import OrderedDict
-from dataclasses import dataclass, field, asdict
+from dataclasses import dataclass
 
 # Keyword arguments of MultiView_MPL.__init__, in order, with the reference defaults (multiview_mpl.py:95-117).
 CTOR_DEFAULTS = OrderedDict([

@@ -13,7 +13,7 @@ import torch
 from conftest import ROOT, load_golden
 from oracle import ref_loader
 from oracle.cases import CASES, GRID_BASE, GRID_FLAGS
-from openmpl_b200 import _lib, spec, synth
+from openmpl_b200 import _lib, spec
 from openmpl_b200.models import multiview_mpl_b200 as mb
 
 

@@ -1,6 +1,5 @@
 """The tcgen05 projection kernel in isolation (through the C-ABI test hook) against a plain fp32 matmul of the same
 rounded operands.  Covers both CTA-group modes, both operand kinds, every epilogue, ragged M / N / K tiles."""
-import ctypes
 
 import numpy as np
 import pytest
