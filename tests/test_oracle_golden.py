@@ -189,3 +189,24 @@ def test_torch_cpu_port_matches_golden(name):
     out = torch_port.forward(p, cfg, *(torch.from_numpy(batch[k]) for k in ("poses", "rays", "centers"))).numpy()
     assert np.abs(out - g["out64_0"]).max() <= 2e-5 * max(np.abs(g["out64_0"]).max(), 1.0)
     assert np.abs(out - g["out32_0"]).max() <= 2e-5 * max(np.abs(g["out64_0"]).max(), 1.0)
+
+
+def test_procrustes_invariances_random():
+    """Properties PoseUtils.procrustes guarantees for any non-degenerate pair: orthogonal rotation, 0 <= d <= 1 with scaling,
+    the aligned error is invariant under a similarity transform of the prediction, Z = scale * B R + t."""
+    rng = np.random.default_rng(21)
+    for _ in range(40):
+        J = int(rng.integers(4, 25))
+        A = rng.normal(size=(J, 3)) + rng.uniform(-3, 3, size=3)
+        B = rng.normal(size=(J, 3))
+        d, Z, tf = mpl_oracle.procrustes(A, B)
+        R = tf["rotation"]
+        np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-12)
+        assert -1e-12 <= d <= 1 + 1e-12
+        np.testing.assert_allclose(Z, tf["scale"] * B @ R + tf["translation"], atol=1e-10)
+        Q = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        d2, Z2, _ = mpl_oracle.procrustes(A, 2.5 * B @ Q - 4.0)
+        assert abs(d - d2) < 1e-10
+        np.testing.assert_allclose(Z, Z2, atol=1e-9)
+        dr, Zr, tr = mpl_oracle.procrustes(A, B, scaling=False)          # rigid: scale reported as 1, residual larger
+        assert tr["scale"] == 1 and ((Zr - A) ** 2).sum() >= ((Z - A) ** 2).sum() - 1e-10
