@@ -83,7 +83,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, min(args.steps, 100)), max(1, min(args.warmup, 5))   # K timed forwards, W untimed
     times = cpu_forward_timer(args, steps, warmup)
     total = sum(times)
     value = args.cpu_batch * len(times) / total
@@ -92,8 +92,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": len(times),
         "warmup": warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"H36M 4-view 17-joint hm_0 lifter forward, depth {cfg.depth}, D={cfg.fpt_dim}",
-                   "batch_per_step": args.cpu_batch, "note": "torch-CPU fp32 restatement of MultiView_MPL.forward (same ATen calls as the reference) on all host cores"},
+        "config": {"workload": f"H36M 4-view 17-joint hm_0 lifter forward (MultiSPT, Conf3rd, Raytoken, Add3dEncRays), depth {cfg.depth}, "
+                               f"D={cfg.fpt_dim}, bounded sample of {args.cpu_batch} poses per step",
+                   "batch_per_step": args.cpu_batch, "views": cfg.V, "joints": cfg.J, "note": "torch-CPU fp32 restatement of MultiView_MPL.forward (same ATen calls as the reference) on all host cores"},
         "cpu_baseline": {"value": value, "unit": "poses/s", "cores": cores, "kind": "port",
                          "sample": f"{len(times)} forwards of {args.cpu_batch} poses"},
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
