@@ -11,6 +11,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPL_B200_LIB") or os.path.join(HERE, "libmpl_b200.so")   # override: another build of the same ABI
 
+ABI_VERSION = 2
 MPL_OK = 0
 MPL_ERR_INVALID_ARGUMENT = -1
 MPL_ERR_CONFIG_RUNTIME = -2
@@ -26,8 +27,7 @@ EXPORTS = [
     "mpl_last_error", "mpl_abi_version", "mpl_create", "mpl_destroy", "mpl_num_params", "mpl_param_info", "mpl_dim",
     "mpl_packed_bytes", "mpl_pack_weights", "mpl_workspace_bytes", "mpl_chunk_poses", "mpl_set_chunk_poses",
     "mpl_forward", "mpl_last_launch_count", "mpl_mpjpe_accumulate", "mpl_build_inputs", "mpl_test_gemm",
-    "mpl_set_gemm_cta_group", "mpl_get_gemm_cta_group", "mpl_set_profile", "mpl_profile_categories",
-    "mpl_profile_category_name", "mpl_profile_collect", "mpl_set_ln_fusion", "mpl_get_ln_fusion", "mpl_synth_project",
+    "mpl_set_profile", "mpl_profile_categories", "mpl_profile_category_name", "mpl_profile_collect", "mpl_synth_project",
     "mpl_pmpjpe_accumulate",
 ]
 
@@ -45,10 +45,11 @@ class MplDesc(ctypes.Structure):
     _fields_ = ([("struct_size", c_int32), ("num_joints", c_int32), ("in_chans", c_int32), ("embed_dim_ratio", c_int32),
                  ("depth", c_int32), ("num_heads", c_int32), ("num_views", c_int32), ("hidden_dim", c_int32),
                  ("mlp_ratio", c_float), ("qk_scale", c_float)]
-                + [(f, c_int32) for f in _DESC_FLAGS] + [("precision", c_int32)])
+                + [(f, c_int32) for f in _DESC_FLAGS] + [("precision", c_int32), ("ln_fusion", c_int32),
+                                                         ("gemm_cta_group", c_int32)])
 
 
-def make_desc(kw: dict, precision: str) -> MplDesc:
+def make_desc(kw: dict, precision: str, ln_fusion: bool = True, gemm_cta_group: int = 2) -> MplDesc:
     """Constructor kwargs of MultiView_MPL (multiview_mpl.py:95-117) -> MplDesc."""
     if precision not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
@@ -61,6 +62,8 @@ def make_desc(kw: dict, precision: str) -> MplDesc:
     for f in _DESC_FLAGS:
         setattr(d, f, int(bool(kw[f])))
     d.precision = PRECISIONS[precision]
+    d.ln_fusion = int(bool(ln_fusion))
+    d.gemm_cta_group = int(gemm_cta_group)
     return d
 
 
@@ -106,18 +109,14 @@ def lib():
         L.mpl_pmpjpe_accumulate.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p]
         L.mpl_build_inputs.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         L.mpl_test_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
-                                    c_void_p]
+                                    c_int, c_void_p]
         L.mpl_set_profile.argtypes = [c_void_p, c_int]
         L.mpl_profile_category_name.argtypes = [c_int]
         L.mpl_profile_category_name.restype = c_char_p
         L.mpl_profile_collect.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]
-        L.mpl_set_gemm_cta_group.argtypes = [c_int]
-        L.mpl_get_gemm_cta_group.restype = c_int
         L.mpl_synth_project.argtypes = [ctypes.c_uint64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                         c_void_p, c_void_p]
-        L.mpl_set_ln_fusion.argtypes = [c_int]
-        L.mpl_get_ln_fusion.restype = c_int
-        if L.mpl_abi_version() != 1:
+        if L.mpl_abi_version() != ABI_VERSION:
             raise RuntimeError("libmpl_b200.so ABI version mismatch")
         _lib = L
     return _lib

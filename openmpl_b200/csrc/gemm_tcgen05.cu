@@ -3,7 +3,10 @@
 //
 // Persistent, warp-specialised, hand-written tcgen05 kernel:
 //   warp 0     TMA producer   cp.async.bulk.tensor 2D tiles (128B swizzle) into a ring of shared-memory stages
-//   warp 1     MMA issuer     one thread issues tcgen05.mma (kind::f16 bf16 or kind::tf32), accumulators in TMEM
+//   warp 1     MMA issuer     one thread issues tcgen05.mma (kind::f16, bf16 / fp16 operands), accumulators in TMEM.
+//                             KIND 1 ("split", the fp32-grade mode): both operands arrive as two bf16 planes, hi = bf16(x)
+//                             and lo = bf16(x - hi), and every k-step issues hi.hi + hi.lo + lo.hi into the same
+//                             accumulator (2^-16 relative operand error instead of 2^-9, at a third of the bf16 rate)
 //   warp 2     TMEM allocator 512 columns = two 256-column accumulator stages (MMA of tile i+1 overlaps epilogue of i)
 //   warps 4-11 epilogue       tcgen05.ld -> registers -> bias / GELU -> 128B-swizzled staging tile in shared memory ->
 //                             TMA store (bf16 / fp32) or TMA reduce-add (the fp32 residual stream is updated in L2,
@@ -16,6 +19,7 @@
 // the K tail is zero-filled by TMA, so no padding copies are needed.
 #include <cuda.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -34,16 +38,17 @@ constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter: even / odd 32-c
 constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
 
-template <int CG, int EPI = 0>
+template <int CG, int EPI = 0, int KIND = 0>
 struct Cfg {
+  static constexpr int OPS = (KIND == 1) ? 2 : 1;           // operand planes per matrix (split mode: hi + lo)
   static constexpr int A_BYTES = BM * KB_BYTES;             // 16 KB
   static constexpr int B_ROWS = BN / CG;                    // W rows staged per CTA
   static constexpr int B_BYTES = B_ROWS * KB_BYTES;         // 32 KB / 16 KB
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // 48 KB / 32 KB
+  static constexpr int STAGE_BYTES = OPS * (A_BYTES + B_BYTES);  // 48 KB / 32 KB (split: 96 KB / 64 KB)
   // 192 KB of operand ring.  The residual-emit epilogue (EPI 6) trades two stages for a shared-memory prefetch ring of
   // old residual values (measured: the ring depth does not matter for K = 1088 and costs K = 2176 little)
   static constexpr int XRING_BYTES = (EPI == 6) ? NUM_EPI_WARPS * 2 * 4096 : 0;  // two 4 KB chunks per epilogue warp
-  static constexpr int STAGES = (EPI == 6) ? ((CG == 1) ? 2 : 4) : ((CG == 1) ? 4 : 6);
+  static constexpr int STAGES = (KIND == 1) ? ((CG == 1) ? 2 : 3) : (EPI == 6) ? ((CG == 1) ? 2 : 4) : ((CG == 1) ? 4 : 6);
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096; // per epilogue warp: one 32-row x 128-byte output box
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + XRING_BYTES + BAR_BYTES;
@@ -60,19 +65,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16 / kind::tf32 instruction descriptor: fp32 accumulate, K-major A and B
-__device__ __forceinline__ uint32_t make_idesc(int kind, int m, int n, bool fp16 = false) {
-  const uint32_t fmt = (kind == 0) ? (fp16 ? 0u : 1u) : 2u;  // kind::f16: F16 = 0, BF16 = 1; kind::tf32: TF32 = 2
+// kind::f16 instruction descriptor: fp32 accumulate, K-major A and B
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, bool fp16 = false) {
+  const uint32_t fmt = fp16 ? 0u : 1u;  // kind::f16: F16 = 0, BF16 = 1
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float round_tf32_dev(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// EPI: 0 bias -> operand dtype, 1 bias + GELU -> operand dtype, 2 Y(fp32) += acc + bias, 3 bias -> fp32,
+// EPI: 0 bias -> operand dtype (split mode: two bf16 planes), 1 bias + GELU -> operand dtype, 2 Y(fp32) += acc + bias, 3 bias -> fp32,
 //      4 / 5 = 0 / 1 with LayerNorm folded in (see GemmLn), 6 / 7 residual update that also emits the next LayerNorm's inputs
 //      (6: shared-memory prefetch ring of the old residual, 7: register prefetch).
 //
@@ -118,7 +117,7 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[32], const flo
   }
   if constexpr (EPI == 1 || EPI == 5) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = (KIND == 0) ? gelu_tanh_fit(f[i]) : round_tf32_dev(gelu_erf(f[i]));
+    for (int i = 0; i < 32; ++i) f[i] = (KIND == 0) ? gelu_tanh_fit(f[i]) : gelu_erf(f[i]);  // split mode: exact erf form
   }
 }
 
@@ -144,6 +143,24 @@ __device__ __forceinline__ void stage_row_bf16(uint32_t box, int lane, int j0, c
   }
 }
 
+// split-plane output: stores bf16(f) like stage_row_bf16 and leaves the rounding remainder f - bf16(f) in f, so a second
+// call stages the lo plane
+__device__ __forceinline__ void stage_row_bf16_rem(uint32_t box, int lane, int j0, float (&f)[32]) {
+  const uint32_t rowaddr = box + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * j + 2 * i], f[8 * j + 2 * i + 1]);
+      p[i] = *reinterpret_cast<const uint32_t*>(&h);
+      f[8 * j + 2 * i] -= __uint_as_float(p[i] << 16);
+      f[8 * j + 2 * i + 1] -= __uint_as_float(p[i] & 0xffff0000u);
+    }
+    ptx::st_shared_v4(rowaddr + (((j0 + j) ^ (lane & 7)) << 4), p[0], p[1], p[2], p[3]);
+  }
+}
+
 // fp16 output path (fc1 -> fc2 hidden activations kept in fp16: 3 more mantissa bits than bf16, and the GELU runs as packed
 // half2 arithmetic): 32 fp32 values -> half2 pairs (saturating) -> optional tanh-fit erf-GELU -> chunks j0 .. j0+3 of the row
 template <bool GELU>
@@ -164,10 +181,14 @@ __device__ __forceinline__ void stage_row_f16(uint32_t box, int lane, int j0, co
 template <int CG, int KIND, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, int64_t M, int N, int K,
+                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmY2,
+                    const float* __restrict__ bias, int64_t M, int N, int K,
                     int bn, const GemmLn ln) {  // bn: output-tile width (256 / 192 / 128), chosen so that no interior tile is narrow
-  using C = Cfg<CG, EPI>;
-  constexpr int ESZ = (KIND == 0) ? 2 : 4;
+  // tmA2 / tmB2 / tmY2: the lo planes of the split mode (KIND 1); copies of tmA / tmB / tmY otherwise
+  using C = Cfg<CG, EPI, KIND>;
+  constexpr bool SPLIT = (KIND == 1);
+  constexpr int ESZ = 2;
   constexpr int BK = KB_BYTES / ESZ;  // K elements per stage
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte aligned bases
@@ -192,6 +213,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     ptx::prefetch_tensormap(&tmY);
+    if constexpr (SPLIT) {
+      ptx::prefetch_tensormap(&tmA2);
+      ptx::prefetch_tensormap(&tmB2);
+      ptx::prefetch_tensormap(&tmY2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -214,7 +240,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_tiles = (N + bn - 1) / bn;
-  const uint32_t stage_tx = (uint32_t)(C::A_BYTES + (bn / CG) * KB_BYTES);  // bytes one CTA's two TMA boxes deliver per stage
+  const uint32_t stage_tx = (uint32_t)(C::OPS * (C::A_BYTES + (bn / CG) * KB_BYTES));  // bytes one CTA's TMA boxes deliver per stage
   const int64_t m_tiles = (M + (int64_t)BM * CG - 1) / ((int64_t)BM * CG);
   const int64_t total_tiles = m_tiles * n_tiles;
   const int64_t first_tile = blockIdx.x / CG;
@@ -240,20 +266,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool prefetch_next = next_tile < total_tiles && (next_tile % n_tiles) == 0;
         const int32_t next_m0 = (int32_t)((next_tile / n_tiles) * BM * CG + cta_rank * BM);
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (prefetch_next) ptx::tma_prefetch_l2_2d(&tmA, kb * BK, next_m0);
+          if (prefetch_next) {
+            ptx::tma_prefetch_l2_2d(&tmA, kb * BK, next_m0);
+            if constexpr (SPLIT) ptx::tma_prefetch_l2_2d(&tmA2, kb * BK, next_m0);
+          }
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + C::A_BYTES;
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;  // [A hi][A lo][W hi][W lo] in split mode
+          const uint32_t b_dst = a_dst + C::OPS * C::A_BYTES;
           if constexpr (CG == 1) {
             ptx::mbar_arrive_expect_tx(full_bar(stage), stage_tx);
             ptx::tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, m0);
             ptx::tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
+            if constexpr (SPLIT) {
+              ptx::tma_load_2d(a_dst + C::A_BYTES, &tmA2, full_bar(stage), kb * BK, m0);
+              ptx::tma_load_2d(b_dst + C::B_BYTES, &tmB2, full_bar(stage), kb * BK, n0);
+            }
           } else {
             const uint32_t lbar = leader_full0 + 8u * stage;
             // the peer's bytes may land before this expect_tx: the phase still cannot complete without this arrive
             if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
             ptx::tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
             ptx::tma_load_2d_pair(b_dst, &tmB, lbar, kb * BK, n0);
+            if constexpr (SPLIT) {
+              ptx::tma_load_2d_pair(a_dst + C::A_BYTES, &tmA2, lbar, kb * BK, m0);
+              ptx::tma_load_2d_pair(b_dst + C::B_BYTES, &tmB2, lbar, kb * BK, n0);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -270,7 +307,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int n_blk = (int)(tile % n_tiles);
         const int n_size = min(bn, N - n_blk * bn);
-        const uint32_t idesc = make_idesc(KIND, BM * CG, n_size, (ln.flags & 2) != 0);
+        const uint32_t idesc = make_idesc(BM * CG, n_size, (ln.flags & 2) != 0);
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -278,12 +315,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t b_src = a_src + C::A_BYTES;
+          const uint32_t b_src = a_src + C::OPS * C::A_BYTES;
 #pragma unroll
           for (int k = 0; k < KB_BYTES / UMMA_K_BYTES; ++k) {
             const uint64_t adesc = make_smem_desc(a_src + k * UMMA_K_BYTES);
             const uint64_t bdesc = make_smem_desc(b_src + k * UMMA_K_BYTES);
-            ptx::umma<CG, KIND>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (SPLIT) {
+              // small cross terms first, the hi.hi product last (the lo.lo term, 2^-18 relative, is dropped)
+              const uint64_t adesc2 = make_smem_desc(a_src + C::A_BYTES + k * UMMA_K_BYTES);
+              const uint64_t bdesc2 = make_smem_desc(b_src + C::B_BYTES + k * UMMA_K_BYTES);
+              ptx::umma<CG, 0>(d_tmem, adesc, bdesc2, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::umma<CG, 0>(d_tmem, adesc2, bdesc, idesc, 1u);
+              ptx::umma<CG, 0>(d_tmem, adesc, bdesc, idesc, 1u);
+            } else {
+              ptx::umma<CG, 0>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
           else ptx::umma_commit_pair(empty_bar(stage), 0x3);
@@ -300,6 +346,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;            // TMEM lane quarter this warp may read (warp id % 4)
     const int half = (warp - 4) >> 2;  // 0: even 64-column groups, 1: odd groups
     constexpr bool OUT_BF16 = (KIND == 0) && (EPI == 0 || EPI == 1 || EPI == 4 || EPI == 5);
+    constexpr bool OUT_SPLIT = SPLIT && (EPI == 0 || EPI == 1);  // two bf16 planes (hi through tmY, lo through tmY2)
     constexpr bool LNF = (EPI == 4 || EPI == 5);
     const uint32_t box = staging_base + (uint32_t)(warp - 4) * 4096u;
     int acc = 0;
@@ -524,7 +571,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ptx::tmem_ld_32x32(taddr + c, va);
         ptx::tmem_ld_32x32(taddr + c + 32, vb);
         ptx::tmem_ld_wait();
-        if constexpr (OUT_BF16) {
+        if constexpr (OUT_SPLIT) {
+          // one 64-column group per step, as two bf16 boxes: hi plane, then the rounding remainder as the lo plane
+          float fa[32], fb[32];
+          epilogue_math<KIND, EPI>(va, bias, ncol0 + c, N, fa);
+          epilogue_math<KIND, EPI>(vb, bias, ncol0 + c + 32, N, fb);
+#pragma unroll
+          for (int plane = 0; plane < 2; ++plane) {
+            if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has finished reading the box
+            __syncwarp();
+            stage_row_bf16_rem(box, lane, 0, fa);
+            stage_row_bf16_rem(box, lane, 4, fb);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(plane ? &tmY2 : &tmY, box, ncol0 + c, row0);
+              ptx::bulk_commit();
+            }
+          }
+        } else if constexpr (OUT_BF16) {
           // one 64-column bf16 box per step
           float fa[32], fb[32];
           constexpr bool GELU = (EPI == 1 || EPI == 5);
@@ -632,19 +697,21 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, i
   return MPL_OK;
 }
 
-int g_gemm_cta_group = 2;  // CTA pairs by default: half the operand traffic per SM (measured faster on every FPT shape)
+struct GemmMaps {
+  CUtensorMap a, b, y, a2, b2, y2;
+};
 
 template <int CG, int KIND, int EPI>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const float* bias, int64_t M, int N,
-               int K, int bn, const GemmLn& ln, cudaStream_t s) {
-  using C = Cfg<CG, EPI>;
+int launch_one(const GemmMaps& tm, const float* bias, int64_t M, int N, int K, int bn, const GemmLn& ln, cudaStream_t s) {
+  using C = Cfg<CG, EPI, KIND>;
   auto kern = gemm_tcgen05_kernel<CG, KIND, EPI>;
-  static bool attr_set[64] = {};  // per instantiation and device (function attributes live in the device's context)
+  // per instantiation and device (function attributes live in the device's context); a benign race: two threads may both set it
+  static std::atomic<unsigned char> attr_set[64];
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
   }
   const int n_tiles = (N + bn - 1) / bn;
   const int64_t m_tiles = ceil_div(M, (int64_t)BM * CG);
@@ -663,26 +730,26 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmY, bias, M, N, K, bn, ln));
+  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.y, tm.a2, tm.b2, tm.y2, bias, M, N, K, bn, ln));
   return MPL_OK;
 }
 
 template <int CG, int KIND>
-int launch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const float* bias, int64_t M,
-               int N, int K, int bn, const GemmLn& ln, cudaStream_t s) {
+int launch_epi(int epi, const GemmMaps& tm, const float* bias, int64_t M, int N, int K, int bn, const GemmLn& ln,
+               cudaStream_t s) {
   switch (epi) {
-    case 0: return launch_one<CG, KIND, 0>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
-    case 1: return launch_one<CG, KIND, 1>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
-    case 2: return launch_one<CG, KIND, 2>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
-    case 3: return launch_one<CG, KIND, 3>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+    case 0: return launch_one<CG, KIND, 0>(tm, bias, M, N, K, bn, ln, s);
+    case 1: return launch_one<CG, KIND, 1>(tm, bias, M, N, K, bn, ln, s);
+    case 2: return launch_one<CG, KIND, 2>(tm, bias, M, N, K, bn, ln, s);
+    case 3: return launch_one<CG, KIND, 3>(tm, bias, M, N, K, bn, ln, s);
     default: break;
   }
-  if constexpr (KIND == 0) {  // the LayerNorm-fused epilogues exist for bf16 operands only
+  if constexpr (KIND == 0) {  // the LayerNorm-fused epilogues exist for single-plane bf16 / fp16 operands only
     switch (epi) {
-      case 4: return launch_one<CG, KIND, 4>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
-      case 5: return launch_one<CG, KIND, 5>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
-      case 6: return launch_one<CG, KIND, 6>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
-      case 7: return launch_one<CG, KIND, 7>(tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+      case 4: return launch_one<CG, KIND, 4>(tm, bias, M, N, K, bn, ln, s);
+      case 5: return launch_one<CG, KIND, 5>(tm, bias, M, N, K, bn, ln, s);
+      case 6: return launch_one<CG, KIND, 6>(tm, bias, M, N, K, bn, ln, s);
+      case 7: return launch_one<CG, KIND, 7>(tm, bias, M, N, K, bn, ln, s);
       default: break;
     }
   }
@@ -712,18 +779,15 @@ int pick_tile_n(int N, bool out32 = false) {
 
 }  // namespace
 
-void set_gemm_cta_group(int cg) { g_gemm_cta_group = (cg == 2) ? 2 : 1; }
-int get_gemm_cta_group() { return g_gemm_cta_group; }
-
 bool gemm_tcgen05_supports(int N, int K, int dtype) {
-  const int esz = (dtype == MPL_PREC_BF16) ? 2 : 4;
-  return N >= 16 && N % 16 == 0 && K >= 1 && ((int64_t)K * esz) % 16 == 0;
+  (void)dtype;  // both tensor-core modes stage bf16 planes
+  return N >= 16 && N % 16 == 0 && K >= 1 && ((int64_t)K * 2) % 16 == 0;
 }
 
 int gemm_ln_slots(int N) { return 2 * ((N + pick_tile_n(N, true) - 1) / pick_tile_n(N, true)); }
 
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
-                        int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* lnargs) {
+                        int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* lnargs, int cta_group) {
   if (M == 0) return MPL_OK;
   GemmLn ln{};
   if (epilogue >= EPI_LN_BIAS) {
@@ -763,25 +827,32 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
     set_error("launch_gemm_tcgen05: bias must not be null");
     return MPL_ERR_INVALID_ARGUMENT;
   }
-  const int esz = (dtype == MPL_PREC_BF16) ? 2 : 4;
-  const int cg = g_gemm_cta_group;
-  CUtensorMap tmA, tmB, tmY;
-  MPL_TRY(make_tmap(&tmA, A, M, K, esz, BM));
+  const int cg = (cta_group == 1) ? 1 : 2;  // CTA pairs by default: half the operand traffic per SM (measured faster on every FPT shape)
+  const bool split = dtype == MPL_PREC_TF32;  // the fp32-grade mode: operands are two bf16 planes (hi, lo), [2][rows][K]
   int epi = epilogue;
   if (epilogue == EPI_BIAS && out_fp32) epi = 3;
-  const int kind = (dtype == MPL_PREC_BF16) ? 0 : 1;
   // output boxes: 32 rows x 128 bytes (64 bf16 or 32 fp32 columns), 128B swizzle like the staging writes
-  const bool out_bf16 = kind == 0 && (epi == 0 || epi == 1 || epi == 4 || epi == 5);
+  const bool out_bf16 = epi == 0 || epi == 1 || epi == 4 || epi == 5;
   // residual-emit: short K (proj) is epilogue-bound -> shared-memory prefetch ring on a 4-stage operand ring (EPI 6);
   // long K (fc2) hides the epilogue behind the main loop -> register prefetch, all 6 stages (EPI 7)
   if (epi == 6 && K > 1536) epi = 7;
-  const int bn = pick_tile_n(N, epi == 2 || epi == 6 || epi == 7);  // tf32 EPI 0 / 1 / 3 store through 64-column steps: keep 64-multiples
-  MPL_TRY(make_tmap(&tmB, W, N, K, esz, bn / cg));
-  MPL_TRY(make_tmap(&tmY, Y, M, N, out_bf16 ? 2 : 4, 32, out_bf16 ? 64 : 32));
-  if (cg == 1) {
-    return kind == 0 ? launch_epi<1, 0>(epi, tmA, tmB, tmY, bias, M, N, K, bn, ln, s) : launch_epi<1, 1>(epi, tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+  const int bn = pick_tile_n(N, epi == 2 || epi == 6 || epi == 7);  // EPI 0 / 1 / 3 store through 64-column steps: keep 64-multiples
+  GemmMaps tm;
+  MPL_TRY(make_tmap(&tm.a, A, M, K, 2, BM));
+  MPL_TRY(make_tmap(&tm.b, W, N, K, 2, bn / cg));
+  MPL_TRY(make_tmap(&tm.y, Y, M, N, out_bf16 ? 2 : 4, 32, out_bf16 ? 64 : 32));
+  if (split) {
+    MPL_TRY(make_tmap(&tm.a2, reinterpret_cast<const __nv_bfloat16*>(A) + M * (int64_t)K, M, K, 2, BM));
+    MPL_TRY(make_tmap(&tm.b2, reinterpret_cast<const __nv_bfloat16*>(W) + (int64_t)N * K, N, K, 2, bn / cg));
+    if (out_bf16) MPL_TRY(make_tmap(&tm.y2, reinterpret_cast<__nv_bfloat16*>(Y) + M * (int64_t)N, M, N, 2, 32, 64));
+    else tm.y2 = tm.y;
+  } else {
+    tm.a2 = tm.a; tm.b2 = tm.b; tm.y2 = tm.y;
   }
-  return kind == 0 ? launch_epi<2, 0>(epi, tmA, tmB, tmY, bias, M, N, K, bn, ln, s) : launch_epi<2, 1>(epi, tmA, tmB, tmY, bias, M, N, K, bn, ln, s);
+  if (cg == 1) {
+    return split ? launch_epi<1, 1>(epi, tm, bias, M, N, K, bn, ln, s) : launch_epi<1, 0>(epi, tm, bias, M, N, K, bn, ln, s);
+  }
+  return split ? launch_epi<2, 1>(epi, tm, bias, M, N, K, bn, ln, s) : launch_epi<2, 0>(epi, tm, bias, M, N, K, bn, ln, s);
 }
 
 }  // namespace mpl

@@ -57,9 +57,9 @@ int launch_layernorm(const float* x, int64_t ldx, int seg_len, int seg_stride, c
 // same, bf16 output (A operand of the tcgen05 projections)
 int launch_layernorm_bf16(const float* x, int64_t ldx, const float* w, const float* b, float eps, __nv_bfloat16* y,
                           int64_t ldy, int64_t rows, int C, cudaStream_t s);
-// same, fp32 output rounded to tf32 (A operand of the kind::tf32 projections)
-int launch_layernorm_tf32(const float* x, int64_t ldx, const float* w, const float* b, float eps, float* y, int64_t ldy,
-                          int64_t rows, int C, cudaStream_t s);
+// same, split bf16 planes out (A operand of the fp32-grade split-mode projections): hi at y, lo at y + plane
+int launch_layernorm_split(const float* x, int64_t ldx, const float* w, const float* b, float eps, __nv_bfloat16* y,
+                           int64_t ldy, int64_t plane, int64_t rows, int C, cudaStream_t s);
 
 // entry of the LayerNorm-fused FPT: raw bf16 copy of the rows + (sum, sum^2) in statistics slot 0 of `slots`
 int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, int64_t ldb, void* stats, int slots, int64_t rows, int C,
@@ -79,8 +79,10 @@ int launch_attention_f32(const float* qkv, float* out, int64_t sets, int N, int 
 // bf16 in / bf16 out variant used behind the tensor-core QKV projection
 int launch_attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t sets, int N, int H, int hd, float scale,
                           cudaStream_t s);
-// fp32 in / tf32-rounded fp32 out variant
-int launch_attention_tf32(const float* qkv, float* out, int64_t sets, int N, int H, int hd, float scale, cudaStream_t s);
+// fp32 in / split bf16 planes out (hi at out, lo at out + plane); scratch: [sets * N, H * hd] fp32 for the shapes the
+// view-token kernel does not serve
+int launch_attention_split(const float* qkv, __nv_bfloat16* out, int64_t plane, float* scratch, int64_t sets, int N, int H,
+                           int hd, float scale, cudaStream_t s);
 
 // ---- Conv1d(V -> 1, k = 1) over the view axis (multiview_mpl.py:281,445): y[b,e] = sum_v w[v] x[b,v,e] + bias -------
 int launch_view_mean(const float* x, const float* w, const float* bias, float* y, int64_t B, int V, int E, cudaStream_t s);
@@ -109,7 +111,7 @@ int launch_fold_bn(const float* W, const float* b, const float* g, const float* 
                    float eps, float* Wf, float* bf, int N, int K, cudaStream_t s);
 int launch_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);
 int launch_to_f16(const float* src, void* dst, int64_t n, cudaStream_t s);
-int launch_to_tf32(const float* src, float* dst, int64_t n, cudaStream_t s);
+int launch_to_split(const float* src, __nv_bfloat16* dst, int64_t n, int64_t plane, cudaStream_t s);  // hi at dst, lo at dst + plane
 
 // ---- tcgen05 projection GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
 enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_LN_BIAS = 4, EPI_LN_BIAS_GELU = 5, EPI_RESIDUAL_EMIT = 6 };
@@ -130,11 +132,13 @@ struct GemmLnArgs {
   int out_fp16;  // EPI_LN_BIAS(_GELU): write fp16 (not bf16); the GELU then runs in packed half2 arithmetic
 };
 int gemm_ln_slots(int N);
-// A [M,K] row-major (lda = K), W [N,K] row-major, both bf16 (dtype MPL_PREC_BF16) or tf32-rounded fp32 (MPL_PREC_TF32).
-// EPI_BIAS / EPI_BIAS_GELU write Y [M,N] in the operand dtype (or fp32 if out_fp32); EPI_BIAS_RESIDUAL does
-// Y(fp32) += A W^T + bias in place.
+// A [M,K] row-major (lda = K), W [N,K] row-major.  dtype MPL_PREC_BF16: bf16 matrices.  dtype MPL_PREC_TF32 (the fp32-grade
+// "split" mode): every matrix is TWO bf16 planes, [2][rows][K] = hi = bf16(x) then lo = bf16(x - hi), and the kernel
+// accumulates hi.hi + hi.lo + lo.hi.  EPI_BIAS / EPI_BIAS_GELU write Y [M,N] in the operand format (bf16, or two planes
+// [2][M][N]) or fp32 if out_fp32; EPI_BIAS_RESIDUAL does Y(fp32) += A W^T + bias in place.
+// cta_group: 1 = one CTA per 128 x 256 tile, anything else = CTA pairs per 256 x 256 tile (the default).
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
-                        int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* ln = nullptr);
+                        int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* ln = nullptr, int cta_group = 2);
 bool gemm_tcgen05_supports(int N, int K, int dtype);
 
 // ---- K2: fused Spatial Pose Transformer stack (spt_fused.cu) ---------------------------------------------------------

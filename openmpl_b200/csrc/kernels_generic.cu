@@ -15,10 +15,20 @@ __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat16
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-__device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// split-plane operand format of the fp32-grade tensor-core mode: x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi)
+// (16 significand bits; the planes are `plane` elements apart)
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, int64_t plane, float a, float b, float c, float d) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b), h1 = __floats2bfloat162_rn(c, d);
+  const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(a - __uint_as_float(u0 << 16), b - __uint_as_float(u0 & 0xffff0000u));
+  const __nv_bfloat162 l1 = __floats2bfloat162_rn(c - __uint_as_float(u1 << 16), d - __uint_as_float(u1 & 0xffff0000u));
+  *reinterpret_cast<uint2*>(hi) = make_uint2(u0, u1);
+  *reinterpret_cast<uint2*>(hi + plane) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+__device__ __forceinline__ void store_split1(__nv_bfloat16* hi, int64_t plane, float a) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(a);
+  *hi = h;
+  hi[plane] = __float2bfloat16_rn(a - __bfloat162float(h));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -156,12 +166,12 @@ int launch_token_build(const TokenArgs& a, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, two passes over the row (second one hits L1), biased variance like nn.LayerNorm.
-// MODE 0: fp32 out, 1: bf16 out, 2: tf32-rounded fp32 out.
+// MODE 0: fp32 out, 1: bf16 out, 2: split bf16 planes out (hi at y, lo at y + plane).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE, typename TO>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx, int seg_len, int seg_stride,
                                                         const float* __restrict__ w, const float* __restrict__ b, float eps,
-                                                        TO* __restrict__ y, int64_t ldy, int64_t rows, int C) {
+                                                        TO* __restrict__ y, int64_t ldy, int64_t rows, int C, int64_t plane) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -183,9 +193,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   TO* yr = y + row * ldy;
   for (int e = lane; e < C; e += 32) {
     const int col = plain ? e : (e / seg_len) * seg_stride + (e % seg_len);
-    float o = (xr[col] - mean) * rstd * __ldg(w + e) + __ldg(b + e);
-    if (MODE == 2) o = round_tf32(o);
-    stf(yr + e, o);
+    const float o = (xr[col] - mean) * rstd * __ldg(w + e) + __ldg(b + e);
+    if constexpr (MODE == 2) store_split1(yr + e, plane, o);
+    else stf(yr + e, o);
   }
 }
 
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <int MODE, typename TO, int MAXV4>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                             const float* __restrict__ b, float eps, TO* __restrict__ y,
-                                                            int64_t ldy, int64_t rows, int C) {
+                                                            int64_t ldy, int64_t rows, int C, int64_t plane) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -238,8 +248,9 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
         reinterpret_cast<uint2*>(y + row * ldy)[e4] = pk;
+      } else if constexpr (MODE == 2) {
+        store_split4(y + row * ldy + 4 * e4, plane, o0, o1, o2, o3);
       } else {
-        if (MODE == 2) { o0 = round_tf32(o0); o1 = round_tf32(o1); o2 = round_tf32(o2); o3 = round_tf32(o3); }
         reinterpret_cast<float4*>(y + row * ldy)[e4] = make_float4(o0, o1, o2, o3);
       }
     }
@@ -248,20 +259,20 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
 
 template <int MODE, typename TO>
 static int launch_ln_any(const float* x, int64_t ldx, int seg_len, int seg_stride, const float* w, const float* b, float eps,
-                         TO* y, int64_t ldy, int64_t rows, int C, cudaStream_t s) {
+                         TO* y, int64_t ldy, int64_t rows, int C, cudaStream_t s, int64_t plane = 0) {
   if (rows == 0) return MPL_OK;
   const unsigned grid = (unsigned)ceil_div(rows, 8);
-  const bool vec_ok = (seg_len == seg_stride) && (C % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
+  const bool vec_ok = (seg_len == seg_stride) && (C % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && (plane % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w) |
                         reinterpret_cast<uintptr_t>(b)) % 16 == 0);
   if (vec_ok && C <= 32 * 4 * 5) {
-    layernorm_vec_kernel<MODE, TO, 5><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C);
+    layernorm_vec_kernel<MODE, TO, 5><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C, plane);
   } else if (vec_ok && C <= 32 * 4 * 9) {
-    layernorm_vec_kernel<MODE, TO, 9><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C);
+    layernorm_vec_kernel<MODE, TO, 9><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C, plane);
   } else if (vec_ok && C <= 32 * 4 * 17) {
-    layernorm_vec_kernel<MODE, TO, 17><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C);
+    layernorm_vec_kernel<MODE, TO, 17><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, y, ldy, rows, C, plane);
   } else {
-    layernorm_kernel<MODE, TO><<<grid, 256, 0, s>>>(x, ldx, seg_len, seg_stride, w, b, eps, y, ldy, rows, C);
+    layernorm_kernel<MODE, TO><<<grid, 256, 0, s>>>(x, ldx, seg_len, seg_stride, w, b, eps, y, ldy, rows, C, plane);
   }
   MPL_LAUNCH_CHECK();
   return MPL_OK;
@@ -275,9 +286,9 @@ int launch_layernorm_bf16(const float* x, int64_t ldx, const float* w, const flo
                           int64_t ldy, int64_t rows, int C, cudaStream_t s) {
   return launch_ln_any<1, __nv_bfloat16>(x, ldx, C, C, w, b, eps, y, ldy, rows, C, s);
 }
-int launch_layernorm_tf32(const float* x, int64_t ldx, const float* w, const float* b, float eps, float* y, int64_t ldy,
-                          int64_t rows, int C, cudaStream_t s) {
-  return launch_ln_any<2, float>(x, ldx, C, C, w, b, eps, y, ldy, rows, C, s);
+int launch_layernorm_split(const float* x, int64_t ldx, const float* w, const float* b, float eps, __nv_bfloat16* y,
+                           int64_t ldy, int64_t plane, int64_t rows, int C, cudaStream_t s) {
+  return launch_ln_any<2, __nv_bfloat16>(x, ldx, C, C, w, b, eps, y, ldy, rows, C, s, plane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -439,7 +450,7 @@ int launch_linear_f32(const float* X, int64_t lda, const float* W, const float* 
 // Narrow heads (hd <= 16: the 17-token spatial sets and the V*J keypoint-token sets): lanes sweep the keys.
 // Wide heads (view tokens, hd = D/H): lanes sweep the head channels, scores by warp reduction.
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename TI, typename TO, bool TF32_OUT>
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(128) attention_kernel(const TI* __restrict__ qkv, TO* __restrict__ out, int64_t sets, int N,
                                                         int H, int hd, float scale, const float* __restrict__ conf) {
   extern __shared__ float psm[];  // [4 warps][N]
@@ -499,7 +510,6 @@ __global__ void __launch_bounds__(128) attention_kernel(const TI* __restrict__ q
     float acc = 0.f;
     for (int j = 0; j < N; ++j) acc = fmaf(p[j], ldf(vb + (int64_t)j * ld + t), acc);
     acc *= norm;
-    if (TF32_OUT) acc = round_tf32(acc);
     stf(o + t, acc);
   }
 }
@@ -509,7 +519,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const TI* __restrict__ q
 // whole sets in shared memory with coalesced 16-byte loads, then one thread per (set, head, query) runs the exact
 // two-pass softmax (max, then exp / sum) over the N keys reading k_j / v_j as broadcast shared-memory vectors.
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename TI, typename TO, bool TF32_OUT, int HD>
+template <typename TI, typename TO, int HD>
 __global__ void __launch_bounds__(256) attention_narrow_kernel(const TI* __restrict__ qkv, TO* __restrict__ out, int64_t sets,
                                                                int N, int H, int G, float scale, const float* __restrict__ conf) {
   extern __shared__ float sm[];  // [G][N][3C]
@@ -560,9 +570,7 @@ __global__ void __launch_bounds__(256) attention_narrow_kernel(const TI* __restr
     TO* o = out + ((set0 + g) * N + i) * (int64_t)C + h * HD;
 #pragma unroll
     for (int t = 0; t < HD; ++t) {
-      float r = acc[t] * norm;
-      if (TF32_OUT) r = round_tf32(r);
-      stf(o + t, r);
+      stf(o + t, acc[t] * norm);
     }
   }
 }
@@ -718,9 +726,10 @@ template <> struct ChunkIO<float, 4> {
 };
 
 // DT / CPH: row width and chunks per head compiled in for the shipped widths (1088 / 544, 17), 0 = the runtime arguments
-template <typename T, int V, int CE, bool TF32_OUT, int DT, int CPH>
+// SPLIT_OUT (fp32 q|k|v in, the fp32-grade tensor-core mode): `out` is the hi plane of a split bf16 pair, lo `plane` elements on
+template <typename T, int V, int CE, bool SPLIT_OUT, int DT, int CPH>
 __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restrict__ qkv, T* __restrict__ out, int64_t poses,
-                                                              int D_arg, int hd, float scale) {
+                                                              int D_arg, int hd, float scale, int64_t plane) {
   const int D = DT ? DT : D_arg;
   extern __shared__ float sm[];       // partial [nchunks][V*V] then probs [H][V*V]
   const int nchunks = D / CE;         // == blockDim.x
@@ -829,30 +838,37 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float o[CE];
+      if constexpr (SPLIT_OUT) {
+        static_assert(!SPLIT_OUT || CE == 4, "split output works on 4-element chunks");
+        store_split4(reinterpret_cast<__nv_bfloat16*>(out) + (pose * V + i) * (int64_t)D + c * CE, plane, o2[i][0].x, o2[i][0].y,
+                     o2[i][1].x, o2[i][1].y);
+      } else {
+        float o[CE];
 #pragma unroll
-      for (int e = 0; e < CE / 2; ++e) {
-        o[2 * e] = TF32_OUT ? round_tf32(o2[i][e].x) : o2[i][e].x;
-        o[2 * e + 1] = TF32_OUT ? round_tf32(o2[i][e].y) : o2[i][e].y;
+        for (int e = 0; e < CE / 2; ++e) {
+          o[2 * e] = o2[i][e].x;
+          o[2 * e + 1] = o2[i][e].y;
+        }
+        ChunkIO<T, CE>::store(out + (pose * V + i) * (int64_t)D + c * CE, o);
       }
-      ChunkIO<T, CE>::store(out + (pose * V + i) * (int64_t)D + c * CE, o);
     }
     __syncthreads();  // prob / part are reused by the next pose
   }
 }
 
-template <typename T, int CE, bool TF32_OUT>
-static int launch_attention_views(const T* qkv, T* out, int64_t poses, int V, int D, int hd, float scale, cudaStream_t s) {
+template <typename T, int CE, bool SPLIT_OUT>
+static int launch_attention_views(const T* qkv, T* out, int64_t poses, int V, int D, int hd, float scale, cudaStream_t s,
+                                  int64_t plane = 0) {
   const int threads = D / CE;
   const int H = D / hd;
   const size_t smem = ((size_t)threads + H) * V * V * sizeof(float);
   const unsigned grid = (unsigned)std::min<int64_t>(poses, (int64_t)kNumSMs * 32);
 #define MPL_AV(VV)                                                                                                      \
   case VV: {                                                                                                            \
-    auto kern = (D == 136 * CE && hd == 17 * CE) ? attention_views_kernel<T, VV, CE, TF32_OUT, 136 * CE, 17>                    \
-                                                 : attention_views_kernel<T, VV, CE, TF32_OUT, 0, 0>;                            \
+    auto kern = (D == 136 * CE && hd == 17 * CE) ? attention_views_kernel<T, VV, CE, SPLIT_OUT, 136 * CE, 17>                   \
+                                                 : attention_views_kernel<T, VV, CE, SPLIT_OUT, 0, 0>;                           \
     if (smem > 48 * 1024) MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, threads, smem, s>>>(qkv, out, poses, D, hd, scale);                                                    \
+    kern<<<grid, threads, smem, s>>>(qkv, out, poses, D, hd, scale, plane);                                                  \
   } break;
   switch (V) {
     MPL_AV(2) MPL_AV(3) MPL_AV(4) MPL_AV(5) MPL_AV(6) MPL_AV(7) MPL_AV(8)
@@ -863,7 +879,7 @@ static int launch_attention_views(const T* qkv, T* out, int64_t poses, int V, in
   return MPL_OK;
 }
 
-template <typename TI, typename TO, bool TF32_OUT>
+template <typename TI, typename TO>
 static int launch_attention_any(const TI* qkv, TO* out, int64_t sets, int N, int H, int hd, float scale, const float* conf,
                                 cudaStream_t s) {
   const int64_t total = sets * H * N;
@@ -876,12 +892,12 @@ static int launch_attention_any(const TI* qkv, TO* out, int64_t sets, int N, int
       const bool aligned = (reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
       if constexpr (is_bf16) {
         if (aligned && hd % 8 == 0 && N <= 4 && C / 8 <= 288 && C / 8 >= H * N)
-          return launch_attention_views<TI, 8, TF32_OUT>(qkv, out, sets, N, C, hd, scale, s);
+          return launch_attention_views<TI, 8, false>(qkv, out, sets, N, C, hd, scale, s);
         if (aligned && hd % 4 == 0 && C / 4 <= 288 && C / 4 >= H * N)
-          return launch_attention_views<TI, 4, TF32_OUT>(qkv, out, sets, N, C, hd, scale, s);
+          return launch_attention_views<TI, 4, false>(qkv, out, sets, N, C, hd, scale, s);
       } else {
         if (aligned && hd % 4 == 0 && C / 4 <= 288 && C / 4 >= H * N)
-          return launch_attention_views<TI, 4, TF32_OUT>(qkv, out, sets, N, C, hd, scale, s);
+          return launch_attention_views<TI, 4, false>(qkv, out, sets, N, C, hd, scale, s);
       }
     }
   }
@@ -913,7 +929,7 @@ static int launch_attention_any(const TI* qkv, TO* out, int64_t sets, int N, int
       const unsigned grid = (unsigned)ceil_div(sets, G);
 #define MPL_AN(HD)                                                                                                   \
   {                                                                                                                  \
-    auto kern = attention_narrow_kernel<TI, TO, TF32_OUT, HD>;                                                       \
+    auto kern = attention_narrow_kernel<TI, TO, HD>;                                                       \
     if (smem > 48 * 1024) MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
     kern<<<grid, 256, smem, s>>>(qkv, out, sets, N, H, G, scale, conf);                                              \
   }
@@ -925,21 +941,30 @@ static int launch_attention_any(const TI* qkv, TO* out, int64_t sets, int N, int
   }
   // (3) anything else: one warp per (set, head, query)
   const size_t smem = 4 * (size_t)N * sizeof(float);
-  attention_kernel<TI, TO, TF32_OUT><<<(unsigned)ceil_div(total, 4), 128, smem, s>>>(qkv, out, sets, N, H, hd, scale, conf);
+  attention_kernel<TI, TO><<<(unsigned)ceil_div(total, 4), 128, smem, s>>>(qkv, out, sets, N, H, hd, scale, conf);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
 
 int launch_attention_f32(const float* qkv, float* out, int64_t sets, int N, int H, int hd, float scale, const float* conf,
                          cudaStream_t s) {
-  return launch_attention_any<float, float, false>(qkv, out, sets, N, H, hd, scale, conf, s);
+  return launch_attention_any<float, float>(qkv, out, sets, N, H, hd, scale, conf, s);
 }
 int launch_attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int64_t sets, int N, int H, int hd, float scale,
                           cudaStream_t s) {
-  return launch_attention_any<__nv_bfloat16, __nv_bfloat16, false>(qkv, out, sets, N, H, hd, scale, nullptr, s);
+  return launch_attention_any<__nv_bfloat16, __nv_bfloat16>(qkv, out, sets, N, H, hd, scale, nullptr, s);
 }
-int launch_attention_tf32(const float* qkv, float* out, int64_t sets, int N, int H, int hd, float scale, cudaStream_t s) {
-  return launch_attention_any<float, float, true>(qkv, out, sets, N, H, hd, scale, nullptr, s);
+// fp32 q|k|v in, split bf16 planes out (A operand of the split-mode proj GEMM).  View tokens with wide heads write the
+// planes directly; every other shape runs the fp32 kernel into `scratch` ([sets * N, C] fp32) and splits it afterwards.
+int launch_attention_split(const float* qkv, __nv_bfloat16* out, int64_t plane, float* scratch, int64_t sets, int N, int H,
+                           int hd, float scale, cudaStream_t s) {
+  if (sets == 0) return MPL_OK;
+  const int C = H * hd;
+  const bool aligned = (reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) % 16 == 0 && plane % 4 == 0;
+  if (N >= 2 && N <= 8 && hd >= 16 && aligned && hd % 4 == 0 && C / 4 <= 288 && C / 4 >= H * N)
+    return launch_attention_views<float, 4, true>(qkv, reinterpret_cast<float*>(out), sets, N, C, hd, scale, s, plane);
+  MPL_TRY((launch_attention_any<float, float>(qkv, scratch, sets, N, H, hd, scale, nullptr, s)));
+  return launch_to_split(scratch, out, sets * N * (int64_t)C, plane, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1074,13 +1099,13 @@ int launch_to_f16(const float* src, void* dst, int64_t n, cudaStream_t s) {
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
-__global__ void to_tf32_kernel(const float* src, float* dst, int64_t n) {
+__global__ void to_split_kernel(const float* src, __nv_bfloat16* dst, int64_t n, int64_t plane) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = round_tf32(src[i]);
+  if (i < n) store_split1(dst + i, plane, src[i]);
 }
-int launch_to_tf32(const float* src, float* dst, int64_t n, cudaStream_t s) {
+int launch_to_split(const float* src, __nv_bfloat16* dst, int64_t n, int64_t plane, cudaStream_t s) {
   if (n == 0) return MPL_OK;
-  to_tf32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, dst, n);
+  to_split_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, dst, n, plane);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

@@ -23,10 +23,6 @@ void set_error(const char* fmt, ...) {
   g_last_error = buf;
 }
 
-void set_gemm_cta_group(int cg);
-int get_gemm_cta_group();
-static int g_ln_fusion = 1;  // bf16 mode: LayerNorm fused into the FPT projection epilogues (handles created afterwards)
-
 struct ParamInfo {
   std::string name;
   int64_t numel;
@@ -62,6 +58,7 @@ struct MplModel {
   bool ln_fused;   // bf16 mode: the FPT LayerNorms are folded into the projection GEMMs (no LayerNorm kernel)
   bool fpt_kp_fused;  // bf16 mode, keypoint-token FPT (width 32, 8 heads, J = 17): the whole FPT stack is one kernel launch
   int ln_slots;    // statistics slots per row written by the residual-emit GEMMs
+  int cta_group;   // 1: one CTA per 128 x 256 GEMM tile, 2: CTA pairs per 256 x 256 tile (default)
   std::vector<ParamInfo> params;
   std::unordered_map<std::string, int> index;
   std::vector<Derived> derived;
@@ -237,8 +234,9 @@ static void build_tables(MplModel* m) {
   }
   if (m->fpt_kp_fused) add_derived(m, "fptpack", (int64_t)m->depth * spt_fused_layer_bytes(), 1);
   if (m->fpt_tc) {
+    // bf16 mode: one bf16 (fp16 for fc2 under LayerNorm fusion) copy; split mode: two bf16 planes (hi, lo) per matrix
     const int esz = (d.precision == MPL_PREC_BF16) ? 2 : 4;
-    const char* tag = (d.precision == MPL_PREC_BF16) ? "bf16:" : "tf32:";
+    const char* tag = (d.precision == MPL_PREC_BF16) ? "bf16:" : "split:";
     for (int l = 0; l < m->depth; ++l) {
       const std::string p = "blocks." + std::to_string(l) + ".";
       const int64_t D = m->fpt_dim, Hf = m->fpt_hidden;
@@ -395,7 +393,7 @@ static BlockW block_weights(const MplModel* m, const Packed& P, const std::strin
   b.fc2w = P.f(p + "mlp.fc2.weight");
   b.fc2b = P.f(p + "mlp.fc2.bias");
   if (tc) {
-    const std::string tag = (m->d.precision == MPL_PREC_BF16) ? "bf16:" : "tf32:";
+    const std::string tag = (m->d.precision == MPL_PREC_BF16) ? "bf16:" : "split:";
     if (m->ln_fused) {
       b.qkvw_tc = P.dv("lnw:" + p + "attn.qkv");
       b.qkv_cs = P.df("lncs:" + p + "attn.qkv");
@@ -429,11 +427,14 @@ static int block_f32(MplModel* m, bool fpt, const BlockW& w, float* x, int64_t r
   return MPL_OK;
 }
 
-// Same block with the four projections on tcgen05 (bf16 or tf32 operands); LayerNorm / softmax / residual stay fp32.
+// Same block with the four projections on tcgen05; LayerNorm / softmax / residual stay fp32.  bf16 mode: bf16 operands (one
+// MMA per k-step).  tf32-named mode = fp32-grade "split" arithmetic: every GEMM operand is a pair of bf16 planes (hi, lo) and
+// the tensor cores accumulate hi.hi + hi.lo + lo.hi (the producers -- LayerNorm, attention, the fc1 epilogue -- write planes).
 static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_t sets, int N, int C, int hidden, float scale,
                     void* xn, void* qkv, void* att, void* hid, void* stats, cudaStream_t s) {
   const int prec = m->d.precision;
   const int hd = C / m->H;
+  const int cg = m->cta_group;
   if (m->ln_fused) {
     // xn holds the raw bf16 copy of x and `stats` its per-row (sum, sum^2) partials, both written by the previous
     // residual-emit epilogue (or by launch_ln_prep before the first block): 5 launches per block, no LayerNorm kernel
@@ -445,32 +446,36 @@ static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_
     emit.stats_out = stats;
     emit.xb = xn;
     app.colsum = w.qkv_cs;
-    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkv_bf, qkv, rows, 3 * C, C, prec, EPI_LN_BIAS, 0, s, &app));
+    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkv_bf, qkv, rows, 3 * C, C, prec, EPI_LN_BIAS, 0, s, &app, cg));
     LC(CAT_FPT_ATTN, launch_attention_bf16((const __nv_bfloat16*)qkv, (__nv_bfloat16*)att, sets, N, m->H, hd, scale, s));
-    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_RESIDUAL_EMIT, 1, s, &emit));
+    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_RESIDUAL_EMIT, 1, s, &emit, cg));
     app.colsum = w.fc1_cs;
     app.out_fp16 = 1;   // hidden activations in fp16 (GELU in packed half2), fc2 runs kind::f16 on fp16 operands
-    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1_bf, hid, rows, hidden, C, prec, EPI_LN_BIAS_GELU, 0, s, &app));
+    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1_bf, hid, rows, hidden, C, prec, EPI_LN_BIAS_GELU, 0, s, &app, cg));
     emit.ab_fp16 = 1;
-    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_RESIDUAL_EMIT, 1, s, &emit));
+    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_RESIDUAL_EMIT, 1, s, &emit, cg));
     return MPL_OK;
   }
   if (prec == MPL_PREC_BF16) {
     LC(CAT_FPT_LN, launch_layernorm_bf16(x, C, w.n1w, w.n1b, 1e-6f, (__nv_bfloat16*)xn, C, rows, C, s));
-    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkvb, qkv, rows, 3 * C, C, prec, EPI_BIAS, 0, s));
+    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkvb, qkv, rows, 3 * C, C, prec, EPI_BIAS, 0, s, nullptr, cg));
     LC(CAT_FPT_ATTN, launch_attention_bf16((const __nv_bfloat16*)qkv, (__nv_bfloat16*)att, sets, N, m->H, hd, scale, s));
-    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_BIAS_RESIDUAL, 1, s));
+    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_BIAS_RESIDUAL, 1, s, nullptr, cg));
     LC(CAT_FPT_LN, launch_layernorm_bf16(x, C, w.n2w, w.n2b, 1e-6f, (__nv_bfloat16*)xn, C, rows, C, s));
-    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1b, hid, rows, hidden, C, prec, EPI_BIAS_GELU, 0, s));
-    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_BIAS_RESIDUAL, 1, s));
+    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1b, hid, rows, hidden, C, prec, EPI_BIAS_GELU, 0, s, nullptr, cg));
+    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_BIAS_RESIDUAL, 1, s, nullptr, cg));
   } else {
-    LC(CAT_FPT_LN, launch_layernorm_tf32(x, C, w.n1w, w.n1b, 1e-6f, (float*)xn, C, rows, C, s));
-    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkvb, qkv, rows, 3 * C, C, prec, EPI_BIAS, 1, s));
-    LC(CAT_FPT_ATTN, launch_attention_tf32((const float*)qkv, (float*)att, sets, N, m->H, hd, scale, s));
-    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_BIAS_RESIDUAL, 1, s));
-    LC(CAT_FPT_LN, launch_layernorm_tf32(x, C, w.n2w, w.n2b, 1e-6f, (float*)xn, C, rows, C, s));
-    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1b, hid, rows, hidden, C, prec, EPI_BIAS_GELU, 1, s));
-    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_BIAS_RESIDUAL, 1, s));
+    // split planes: xn / att [2][rows][C], hid [2][rows][hidden] bf16; qkv [rows][3C] fp32 (the attention arithmetic is fp32).
+    // xn is free between the QKV GEMM and the second LayerNorm: it doubles as the fp32 scratch of the attention fallback.
+    __nv_bfloat16* xnp = (__nv_bfloat16*)xn;
+    __nv_bfloat16* attp = (__nv_bfloat16*)att;
+    LC(CAT_FPT_LN, launch_layernorm_split(x, C, w.n1w, w.n1b, 1e-6f, xnp, C, rows * C, rows, C, s));
+    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkvb, qkv, rows, 3 * C, C, prec, EPI_BIAS, 1, s, nullptr, cg));
+    LC(CAT_FPT_ATTN, launch_attention_split((const float*)qkv, attp, rows * C, (float*)xn, sets, N, m->H, hd, scale, s));
+    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_BIAS_RESIDUAL, 1, s, nullptr, cg));
+    LC(CAT_FPT_LN, launch_layernorm_split(x, C, w.n2w, w.n2b, 1e-6f, xnp, C, rows * C, rows, C, s));
+    LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1b, hid, rows, hidden, C, prec, EPI_BIAS_GELU, 0, s, nullptr, cg));
+    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_BIAS_RESIDUAL, 1, s, nullptr, cg));
   }
   return MPL_OK;
 }
@@ -704,6 +709,10 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
     set_error("mpl_create: unknown precision %d", desc->precision);
     return MPL_ERR_INVALID_ARGUMENT;
   }
+  if (desc->gemm_cta_group < 0 || desc->gemm_cta_group > 2) {
+    set_error("mpl_create: gemm_cta_group must be 0 (default), 1 or 2");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
   *out = nullptr;
   MplModel* m = new MplModel();
   m->d = *desc;
@@ -749,7 +758,8 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
     m->fpt_tc = true;
   }
   // LayerNorm fusion: the residual-emit epilogue works on whole 32-column chunks, launch_ln_prep on float4 rows
-  m->ln_fused = m->fpt_tc && d.precision == MPL_PREC_BF16 && g_ln_fusion != 0 && m->fpt_dim % 32 == 0 && m->fpt_dim <= 32 * 4 * 17;
+  m->ln_fused = m->fpt_tc && d.precision == MPL_PREC_BF16 && d.ln_fusion != 0 && m->fpt_dim % 32 == 0 && m->fpt_dim <= 32 * 4 * 17;
+  m->cta_group = (d.gemm_cta_group == 1) ? 1 : 2;
   m->ln_slots = m->ln_fused ? gemm_ln_slots(m->fpt_dim) : 0;
   build_tables(m);
   *out = m;
@@ -900,7 +910,7 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
   }
   if (m->fpt_tc) {
     const bool bf = m->d.precision == MPL_PREC_BF16;
-    const std::string tag = bf ? "bf16:" : "tf32:";
+    const std::string tag = bf ? "bf16:" : "split:";
     for (int l = 0; l < m->depth; ++l) {
       const std::string p = "blocks." + std::to_string(l) + ".";
       if (m->ln_fused) {
@@ -921,7 +931,7 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
         const Derived& dd = m->derived[m->dindex.at(tag + p + wn)];
         if (bf && m->ln_fused && std::string(wn) == "mlp.fc2.weight") MPL_TRY(launch_to_f16(src, base + dd.offset, dd.numel, s));
         else if (bf) MPL_TRY(launch_to_bf16(src, reinterpret_cast<__nv_bfloat16*>(base + dd.offset), dd.numel, s));
-        else MPL_TRY(launch_to_tf32(src, reinterpret_cast<float*>(base + dd.offset), dd.numel, s));
+        else MPL_TRY(launch_to_split(src, reinterpret_cast<__nv_bfloat16*>(base + dd.offset), dd.numel, dd.numel, s));
       }
     }
   }
@@ -1054,24 +1064,11 @@ int mpl_synth_project(uint64_t seed, int64_t start, int64_t batch, int num_views
 }
 
 int mpl_test_gemm(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype, int epilogue,
-                  int out_fp32, mpl_stream_t stream) {
-  return launch_gemm_tcgen05(A, W, bias, Y, M, N, K, dtype, epilogue, out_fp32, reinterpret_cast<cudaStream_t>(stream));
+                  int out_fp32, int cta_group, mpl_stream_t stream) {
+  MPL_API_BEGIN
+  return launch_gemm_tcgen05(A, W, bias, Y, M, N, K, dtype, epilogue, out_fp32, reinterpret_cast<cudaStream_t>(stream), nullptr,
+                             cta_group);
+  MPL_API_END
 }
-
-int mpl_set_gemm_cta_group(int cta_group) {
-  if (cta_group != 1 && cta_group != 2) {
-    set_error("mpl_set_gemm_cta_group: cta_group must be 1 or 2");
-    return MPL_ERR_INVALID_ARGUMENT;
-  }
-  set_gemm_cta_group(cta_group);
-  return MPL_OK;
-}
-int mpl_get_gemm_cta_group(void) { return get_gemm_cta_group(); }
-
-int mpl_set_ln_fusion(int enabled) {
-  g_ln_fusion = enabled != 0;
-  return MPL_OK;
-}
-int mpl_get_ln_fusion(void) { return g_ln_fusion; }
 
 }  // extern "C"

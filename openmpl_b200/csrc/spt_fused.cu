@@ -21,6 +21,8 @@
 //   * the attention output overwrites the (already consumed) q slot of its own row and is the A operand of proj;
 //   * erf-GELU via a tanh-form fit (see gelu_tanh_fit), residual adds and the final Spatial_norm stay in fp32.
 // HBM traffic per set: 17*32*4 B in + out, nothing in between.
+#include <atomic>
+
 #include <cuda_fp16.h>
 
 #include "kernels.cuh"
@@ -43,10 +45,19 @@ constexpr int QPW = QP / 2;
 constexpr int OFF_QKV = 0, OFF_PROJ = 1536, OFF_FC1 = 2048, OFF_FC2 = 3072, FRAG_WORDS = 4096;
 constexpr int F_QKVB = 0, F_PROJB = 192, F_FC1B = 256, F_FC2B = 384;
 constexpr int VEC_WORDS = 448, LAYER_WORDS = FRAG_WORDS + VEC_WORDS;  // 4544 words = 18176 bytes
+// The packed blob of a layer continues with the LO fragments: fp16(w - fp16(w)) of the same four matrices in the same order.
+// Only the PRECISE kernel (the fp32-grade tensor-core mode) loads them: it splits every MMA operand into fp16 hi + lo and
+// accumulates hi.hi + lo.hi + hi.lo (22 significand bits per operand instead of 11).
+constexpr int LAYER_WORDS_FULL = LAYER_WORDS + FRAG_WORDS;  // 8640 words = 34560 bytes: stride of a layer in the blob
+constexpr int QPF = 104;    // PRECISE: fp32 row pitch of the q|k|v staging buffer (96 + 8 words: 8-byte C-fragment stores of a
+                            // half-warp, rows g = 0..3, land on 32 distinct banks)
 
-constexpr int SMEM_W = 2 * LAYER_WORDS * 4;
-constexpr int SMEM_QKV = SROWS * QP * 2;
-constexpr int SMEM_TOTAL = SMEM_W + SMEM_QKV;
+template <bool PRECISE> struct Smem {
+  static constexpr int LAYER = PRECISE ? LAYER_WORDS_FULL : LAYER_WORDS;  // words loaded per layer
+  static constexpr int W_BYTES = 2 * LAYER * 4;                            // double-buffered
+  static constexpr int QKV_BYTES = PRECISE ? SROWS * QPF * 4 : SROWS * QP * 2;
+  static constexpr int TOTAL = W_BYTES + QKV_BYTES;                        // 96 256 B (two CTAs per SM) / 188 928 B (one)
+};
 
 // staging position (within a 32-wide q, k or v third) of channel c = 8p + 4e + d (head 2p+e, head-dim d): 8p + 2d + e
 __host__ __device__ constexpr int chan_of_pos(int pos) { return (pos & ~7) + 4 * (pos & 1) + ((pos & 7) >> 1); }
@@ -55,6 +66,13 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+
+// fp32 pair -> fp16 hi pair + fp16 lo pair (lo = the rounding remainder of hi)
+__device__ __forceinline__ void split_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16(a, b);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16(a - hf.x, b - hf.y);
 }
 
 __device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -102,6 +120,27 @@ __device__ __forceinline__ void ln_to_afrag(const float (&x)[4][4], uint32_t (&a
   }
 }
 
+// the same with every A-fragment register split into hi + lo (PRECISE)
+__device__ __forceinline__ void ln_to_afrag_split(const float (&x)[4][4], uint32_t (&ah)[2][4], uint32_t (&al)[2][4]) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) { s0 += x[nt][0] + x[nt][1]; s1 += x[nt][2] + x[nt][3]; }
+  const float m0 = quad_sum(s0) * (1.0f / D), m1 = quad_sum(s1) * (1.0f / D);
+  float q0 = 0.f, q1 = 0.f;  // two-pass variance like nn.LayerNorm: this path is fp32-grade
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float d0 = x[nt][0] - m0, d1 = x[nt][1] - m0, d2 = x[nt][2] - m1, d3 = x[nt][3] - m1;
+    q0 = fmaf(d0, d0, fmaf(d1, d1, q0));
+    q1 = fmaf(d2, d2, fmaf(d3, d3, q1));
+  }
+  const float r0 = rsqrtf(quad_sum(q0) * (1.0f / D) + 1e-6f), r1 = rsqrtf(quad_sum(q1) * (1.0f / D) + 1e-6f);
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    split_f16((x[nt][0] - m0) * r0, (x[nt][1] - m0) * r0, ah[nt >> 1][(nt & 1) * 2 + 0], al[nt >> 1][(nt & 1) * 2 + 0]);
+    split_f16((x[nt][2] - m1) * r1, (x[nt][3] - m1) * r1, ah[nt >> 1][(nt & 1) * 2 + 1], al[nt >> 1][(nt & 1) * 2 + 1]);
+  }
+}
+
 // one output tile column (8 features) for both row tiles of the warp: acc = bias, then KT k-steps; every B fragment
 // read from the packed blob feeds two MMAs
 template <int KT>
@@ -122,10 +161,37 @@ __device__ __forceinline__ void gemm_tile2(float (&c0)[4], float (&c1)[4], const
   }
 }
 
+// split form (PRECISE): per k-step hi.hi + lo.hi + hi.lo into the same fp32 accumulators; wlo = the LO fragments of the
+// same matrix (FRAG_WORDS + VEC_WORDS words behind the hi fragments)
+template <int KT>
+__device__ __forceinline__ void gemm_tile2_split(float (&c0)[4], float (&c1)[4], const uint32_t (&a0h)[KT][4], const uint32_t (&a0l)[KT][4],
+                                                 const uint32_t (&a1h)[KT][4], const uint32_t (&a1l)[KT][4],
+                                                 const uint32_t* __restrict__ wfrag, int nt, const float* __restrict__ bias, int lane,
+                                                 int t) {
+  const uint32_t* __restrict__ wlo = wfrag + LAYER_WORDS;
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + 16 * nt + 4 * t);
+#pragma unroll
+  for (int kt = 0; kt < KT; ++kt) {
+    const uint2 bh = *reinterpret_cast<const uint2*>(wfrag + ((nt * KT + kt) * 32 + lane) * 2);
+    const uint2 bl = *reinterpret_cast<const uint2*>(wlo + ((nt * KT + kt) * 32 + lane) * 2);
+    if (kt == 0) {
+      mma_f16_16816_bias(c0, a0h[0], bl.x, bl.y, b4);
+      mma_f16_16816_bias(c1, a1h[0], bl.x, bl.y, b4);
+    } else {
+      mma_f16_16816(c0, a0h[kt], bl.x, bl.y);
+      mma_f16_16816(c1, a1h[kt], bl.x, bl.y);
+    }
+    mma_f16_16816(c0, a0l[kt], bh.x, bh.y);
+    mma_f16_16816(c1, a1l[kt], bh.x, bh.y);
+    mma_f16_16816(c0, a0h[kt], bh.x, bh.y);
+    mma_f16_16816(c1, a1h[kt], bh.x, bh.y);
+  }
+}
+
 struct SptArgs {
   const float* x_in;                  // [V, B, J, 32] joint embeddings (null: the embedding is computed here, io.embed)
   float* x_out;                       // [V, B, J, 32] after the stack and Spatial_norm (null: tokens are written here, io.token)
-  const uint32_t* wpack[kMaxViews];   // per view stack: [depth][LAYER_WORDS]
+  const uint32_t* wpack[kMaxViews];   // per view stack: [depth][LAYER_WORDS_FULL]
   const float* sn_w;
   const float* sn_b;
   const float* conf;                  // [V, B, J] or null: confidence_as_attention_uncertainty_weight (unfused embed only)
@@ -145,8 +211,9 @@ __device__ __forceinline__ float pose_conf(const SptArgs& a, int view, int64_t g
   return __ldg(a.io.embed.poses[view] + b * a.io.embed.pose_stride + j * 3 + 2);
 }
 
+template <int WORDS>
 __device__ __forceinline__ void load_layer_async(uint32_t* dst, const uint32_t* src) {
-  constexpr int CHUNKS = LAYER_WORDS * 4 / 16;  // 1112 x 16 bytes
+  constexpr int CHUNKS = WORDS * 4 / 16;  // 1136 (2160 with the lo fragments) x 16 bytes
   for (int i = threadIdx.x; i < CHUNKS; i += THREADS) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + i * 4);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i * 4) : "memory");
@@ -172,10 +239,14 @@ __device__ __forceinline__ __half2 ex2_h2(__half2 x) {
 // applications; keys are walked in two passes (max, then exp2 / sum / PV with the scores recomputed), fp16 partial
 // sums flushed into fp32 every 17 keys.  Rows come from and go back to the fp32 token buffer in place.
 template <bool PRECISE, bool GROUPED>
-__global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs args) {
+__global__ void __launch_bounds__(THREADS, PRECISE ? 1 : 2) spt_fused_kernel(const SptArgs args) {
+  static_assert(!(PRECISE && GROUPED), "the grouped (keypoint-token FPT) form exists for the packed-half2 arithmetic only");
+  using SM = Smem<PRECISE>;
+  constexpr int LW = SM::LAYER;
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* wbuf = reinterpret_cast<uint32_t*>(smem);
-  uint32_t* qkv_w = reinterpret_cast<uint32_t*>(smem + SMEM_W);  // fp16 staging viewed as half2 words, row pitch QPW
+  uint32_t* qkv_w = reinterpret_cast<uint32_t*>(smem + SM::W_BYTES);  // fp16 staging viewed as half2 words, row pitch QPW
+  float* qkv_f = reinterpret_cast<float*>(smem + SM::W_BYTES);        // PRECISE: fp32 staging, row pitch QPF
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -185,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
   const int64_t view_row0 = (int64_t)view * rows_in_view;
   const uint32_t* wsrc = args.wpack[view];
 
-  load_layer_async(wbuf, wsrc);
+  load_layer_async<LW>(wbuf, wsrc);
 
   // residual stream: C-fragment layout per row tile mt: x[mt][nt][0..1] = row r0 cols 8nt+2t,+1 ; [2..3] = row r0 + 8
   float x[2][4][4];
@@ -259,16 +330,29 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
   for (int layer = 0; layer < args.depth; ++layer) {
     wait_async_all();
     __syncthreads();  // this layer's weights have landed; every warp is done with the other buffer
-    const uint32_t* w = wbuf + (layer & 1) * LAYER_WORDS;
+    const uint32_t* w = wbuf + (layer & 1) * LW;
     const float* wv = reinterpret_cast<const float*>(w + FRAG_WORDS);
-    if (layer + 1 < args.depth) load_layer_async(wbuf + ((layer + 1) & 1) * LAYER_WORDS, wsrc + (size_t)(layer + 1) * LAYER_WORDS);
+    if (layer + 1 < args.depth) load_layer_async<LW>(wbuf + ((layer + 1) & 1) * LW, wsrc + (size_t)(layer + 1) * LAYER_WORDS_FULL);
 
     // block applications of this layer (multiview_mpl.py:405-410): [confidence-weighted], [last layer: once more], plain
     const int n_apps = (args.conf_weighted ? 1 : 0) + (layer == args.depth - 1 ? 2 : 1);
     for (int app = 0; app < n_apps; ++app) {
       const bool weighted = args.conf_weighted && app == 0;
       // ---- LN1 + QKV -> fp16 staging (q pre-scaled by scale * log2 e through the packed weights) ----
-      {
+      if constexpr (PRECISE) {
+        uint32_t a0h[2][4], a0l[2][4], a1h[2][4], a1l[2][4];
+        ln_to_afrag_split(x[0], a0h, a0l);
+        ln_to_afrag_split(x[1], a1h, a1l);
+#pragma unroll
+        for (int nt = 0; nt < 12; ++nt) {
+          float c0[4], c1[4];
+          gemm_tile2_split<2>(c0, c1, a0h, a0l, a1h, a1l, w + OFF_QKV, nt, wv + F_QKVB, lane, t);
+          *reinterpret_cast<float2*>(qkv_f + lr[0] * QPF + 8 * nt + 2 * t) = make_float2(c0[0], c0[1]);
+          *reinterpret_cast<float2*>(qkv_f + (lr[0] + 8) * QPF + 8 * nt + 2 * t) = make_float2(c0[2], c0[3]);
+          *reinterpret_cast<float2*>(qkv_f + lr[1] * QPF + 8 * nt + 2 * t) = make_float2(c1[0], c1[1]);
+          *reinterpret_cast<float2*>(qkv_f + (lr[1] + 8) * QPF + 8 * nt + 2 * t) = make_float2(c1[2], c1[3]);
+        }
+      } else {
         uint32_t a0[2][4], a1[2][4];
         ln_to_afrag(x[0], a0);
         ln_to_afrag(x[1], a1);
@@ -350,52 +434,42 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
           }
         }
       } else       if constexpr (PRECISE) {
-        uint4* rowps[2] = {reinterpret_cast<uint4*>(qkv_w + ra * QPW), reinterpret_cast<uint4*>(qkv_w + rb * QPW)};
+        // fp32 staging: word = one value; a head pair p owns words 8p .. 8p+7 = (dim 0: head 2p, head 2p+1), (dim 1: ..), ..
+        float4* rowps[2] = {reinterpret_cast<float4*>(qkv_f + ra * QPF), reinterpret_cast<float4*>(qkv_f + rb * QPF)};
         const float rsc[2] = {weighted ? aconf_a : 1.0f, weighted ? aconf_b : 1.0f};
-        const uint4* setp = reinterpret_cast<const uint4*>(qkv_w + aset0 * QPW);
-        constexpr int RP4 = QPW / 4;
+        const float4* setp = reinterpret_cast<const float4*>(qkv_f + aset0 * QPF);
+        constexpr int RP4 = QPF / 4;  // row pitch in float4 units (26)
 #pragma unroll 1
         for (int pp = 0; pp < 2; ++pp) {
           const int p = ahh + 2 * pp;
 #pragma unroll 1
           for (int rr = 0; rr < 2; ++rr) {
             if (rr == 1 && !two) break;
-            const uint4 qu = rowps[rr][p];
-            const float2 q0 = __half22float2(h2(qu.x)), q1 = __half22float2(h2(qu.y)), q2 = __half22float2(h2(qu.z)),
-                         q3 = __half22float2(h2(qu.w));  // word d = (head 2p dim d, head 2p+1 dim d)
+            const float4 qa = rowps[rr][2 * p], qb = rowps[rr][2 * p + 1];  // (d0h0, d0h1, d1h0, d1h1), (d2h0, d2h1, d3h0, d3h1)
             float s0[J], s1[J];
             float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-              const uint4 ku = setp[j * RP4 + 4 + p];
-              const float2 k0 = __half22float2(h2(ku.x)), k1 = __half22float2(h2(ku.y)), k2 = __half22float2(h2(ku.z)),
-                           k3 = __half22float2(h2(ku.w));
-              s0[j] = fmaf(q3.x, k3.x, fmaf(q2.x, k2.x, fmaf(q1.x, k1.x, q0.x * k0.x)));
-              s1[j] = fmaf(q3.y, k3.y, fmaf(q2.y, k2.y, fmaf(q1.y, k1.y, q0.y * k0.y)));
+              const float4 ka = setp[j * RP4 + 8 + 2 * p], kb = setp[j * RP4 + 9 + 2 * p];
+              s0[j] = fmaf(qb.z, kb.z, fmaf(qb.x, kb.x, fmaf(qa.z, ka.z, qa.x * ka.x)));
+              s1[j] = fmaf(qb.w, kb.w, fmaf(qb.y, kb.y, fmaf(qa.w, ka.w, qa.y * ka.y)));
               m0 = fmaxf(m0, s0[j]);
               m1 = fmaxf(m1, s1[j]);
             }
             float sum0 = 0.f, sum1 = 0.f;
-            float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+            float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-              const uint4 vu = setp[j * RP4 + 8 + p];
-              const float2 v0 = __half22float2(h2(vu.x)), v1 = __half22float2(h2(vu.y)), v2 = __half22float2(h2(vu.z)),
-                           v3 = __half22float2(h2(vu.w));
-              float e0, e1;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0[j] - m0));
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1[j] - m1));
+              const float4 va = setp[j * RP4 + 16 + 2 * p], vb = setp[j * RP4 + 17 + 2 * p];
+              const float e0 = exp2f(s0[j] - m0), e1 = exp2f(s1[j] - m1);
               sum0 += e0; sum1 += e1;
-              o0.x = fmaf(e0, v0.x, o0.x); o0.y = fmaf(e1, v0.y, o0.y);
-              o1.x = fmaf(e0, v1.x, o1.x); o1.y = fmaf(e1, v1.y, o1.y);
-              o2.x = fmaf(e0, v2.x, o2.x); o2.y = fmaf(e1, v2.y, o2.y);
-              o3.x = fmaf(e0, v3.x, o3.x); o3.y = fmaf(e1, v3.y, o3.y);
+              oa.x = fmaf(e0, va.x, oa.x); oa.y = fmaf(e1, va.y, oa.y); oa.z = fmaf(e0, va.z, oa.z); oa.w = fmaf(e1, va.w, oa.w);
+              ob.x = fmaf(e0, vb.x, ob.x); ob.y = fmaf(e1, vb.y, ob.y); ob.z = fmaf(e0, vb.z, ob.z); ob.w = fmaf(e1, vb.w, ob.w);
             }
             const float i0 = rsc[rr] / sum0, i1 = rsc[rr] / sum1;
-            uint4 o;
-            o.x = pack_f16(o0.x * i0, o0.y * i1); o.y = pack_f16(o1.x * i0, o1.y * i1);
-            o.z = pack_f16(o2.x * i0, o2.y * i1); o.w = pack_f16(o3.x * i0, o3.y * i1);
-            rowps[rr][p] = o;  // the q slot of this row / head pair is consumed: it now holds the attention output
+            // the q slot of this row / head pair is consumed: it now holds the attention output
+            rowps[rr][2 * p] = make_float4(oa.x * i0, oa.y * i1, oa.z * i0, oa.w * i1);
+            rowps[rr][2 * p + 1] = make_float4(ob.x * i0, ob.y * i1, ob.z * i0, ob.w * i1);
           }
         }
       } else       {
@@ -452,7 +526,27 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
       }
       __syncthreads();
       // ---- proj + residual ----
-      {
+      if constexpr (PRECISE) {
+        uint32_t a0h[2][4], a0l[2][4], a1h[2][4], a1l[2][4];
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {  // fragment register r: row + 8 * (r & 1), columns 16 kt + 8 * (r >> 1) + 2t, +1
+            const int off = (r & 1) * 8 * QPF + 16 * kt + (r >> 1) * 8 + 2 * t;
+            const float2 v0 = *reinterpret_cast<const float2*>(qkv_f + lr[0] * QPF + off);
+            const float2 v1 = *reinterpret_cast<const float2*>(qkv_f + lr[1] * QPF + off);
+            split_f16(v0.x, v0.y, a0h[kt][r], a0l[kt][r]);
+            split_f16(v1.x, v1.y, a1h[kt][r], a1l[kt][r]);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          float c0[4], c1[4];
+          gemm_tile2_split<2>(c0, c1, a0h, a0l, a1h, a1l, w + OFF_PROJ, nt, wv + F_PROJB, lane, t);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { x[0][nt][i] += c0[i]; x[1][nt][i] += c1[i]; }
+        }
+      } else {
         uint32_t a0[2][4], a1[2][4];
 #pragma unroll
         for (int kt = 0; kt < 2; ++kt) {
@@ -474,7 +568,29 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
         }
       }
       // ---- LN2 + fc1 + GELU + fc2 + residual ----
-      {
+      if constexpr (PRECISE) {
+        uint32_t a0h[2][4], a0l[2][4], a1h[2][4], a1l[2][4];
+        ln_to_afrag_split(x[0], a0h, a0l);
+        ln_to_afrag_split(x[1], a1h, a1l);
+        uint32_t h0h[4][4], h0l[4][4], h1h[4][4], h1l[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          float c0[4], c1[4];
+          gemm_tile2_split<2>(c0, c1, a0h, a0l, a1h, a1l, w + OFF_FC1, nt, wv + F_FC1B, lane, t);
+          const int kt = nt >> 1, r = (nt & 1) * 2;
+          split_f16(gelu_erf(c0[0]), gelu_erf(c0[1]), h0h[kt][r], h0l[kt][r]);
+          split_f16(gelu_erf(c0[2]), gelu_erf(c0[3]), h0h[kt][r + 1], h0l[kt][r + 1]);
+          split_f16(gelu_erf(c1[0]), gelu_erf(c1[1]), h1h[kt][r], h1l[kt][r]);
+          split_f16(gelu_erf(c1[2]), gelu_erf(c1[3]), h1h[kt][r + 1], h1l[kt][r + 1]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          float c0[4], c1[4];
+          gemm_tile2_split<4>(c0, c1, h0h, h0l, h1h, h1l, w + OFF_FC2, nt, wv + F_FC2B, lane, t);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { x[0][nt][i] += c0[i]; x[1][nt][i] += c1[i]; }
+        }
+      } else {
         uint32_t a0[2][4], a1[2][4];
         ln_to_afrag(x[0], a0);
         ln_to_afrag(x[1], a1);
@@ -483,17 +599,10 @@ __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel(const SptArgs arg
         for (int nt = 0; nt < 8; ++nt) {
           float c0[4], c1[4];
           gemm_tile2<2>(c0, c1, a0, a1, w + OFF_FC1, nt, wv + F_FC1B, lane, t);
-          if constexpr (PRECISE) {
-            h0[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(gelu_erf(c0[0]), gelu_erf(c0[1]));
-            h0[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(gelu_erf(c0[2]), gelu_erf(c0[3]));
-            h1[nt >> 1][(nt & 1) * 2 + 0] = pack_f16(gelu_erf(c1[0]), gelu_erf(c1[1]));
-            h1[nt >> 1][(nt & 1) * 2 + 1] = pack_f16(gelu_erf(c1[2]), gelu_erf(c1[3]));
-          } else {
-            h0[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c0[0], c0[1]));
-            h0[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c0[2], c0[3]));
-            h1[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c1[0], c1[1]));
-            h1[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c1[2], c1[3]));
-          }
+          h0[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c0[0], c0[1]));
+          h0[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c0[2], c0[3]));
+          h1[nt >> 1][(nt & 1) * 2 + 0] = gelu_tanh_fit_h2(pack_f16(c1[0], c1[1]));
+          h1[nt >> 1][(nt & 1) * 2 + 1] = gelu_tanh_fit_h2(pack_f16(c1[2], c1[3]));
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -609,8 +718,10 @@ __device__ __forceinline__ uint32_t pack_f16_rn(float lo, float hi) {
 }
 
 __global__ void spt_pack_kernel(const SptPackArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= LAYER_WORDS) return;
+  const int i_out = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i_out >= LAYER_WORDS_FULL) return;
+  const bool lo_part = i_out >= LAYER_WORDS;       // the LO fragments: fp16(w - fp16(w)), same order as the hi fragments
+  const int i = lo_part ? i_out - LAYER_WORDS : i_out;
   if (i < FRAG_WORDS) {
     const float* W;
     int K, KT, base, kind;  // kind 0 qkv (output rows permuted), 1 proj (input columns permuted), 2 plain
@@ -634,7 +745,14 @@ __global__ void spt_pack_kernel(const SptPackArgs a) {
     // the LayerNorm in front of QKV / fc1 leaves its gamma here (W' = W diag(gamma)) and its beta in the bias below
     const float* gam = (i < OFF_PROJ) ? a.n1w : ((i >= OFF_FC1 && i < OFF_FC2) ? a.n2w : nullptr);
     const float g0 = gam ? gam[k0] : 1.0f, g1 = gam ? gam[k1] : 1.0f;
-    a.dst[i] = pack_f16_rn(W[n * K + k0] * sc * g0, W[n * K + k1] * sc * g1);
+    const float w0 = W[n * K + k0] * sc * g0, w1 = W[n * K + k1] * sc * g1;
+    const uint32_t hi = pack_f16_rn(w0, w1);
+    if (lo_part) {
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+      a.dst[i_out] = pack_f16_rn(w0 - hf.x, w1 - hf.y);
+    } else {
+      a.dst[i_out] = hi;
+    }
   } else {
     const int f = i - FRAG_WORDS;
     // bias quads: word (16 nt + 4 t + comp) of a section = bias of output column 8 nt + 2 t + (comp & 1)
@@ -662,14 +780,14 @@ __global__ void spt_pack_kernel(const SptPackArgs a) {
 }  // namespace
 
 bool spt_fused_supports(int J_, int d, int H, int hidden) { return J_ == J && d == D && H == HEADS && hidden == HID; }
-size_t spt_fused_layer_bytes() { return (size_t)LAYER_WORDS * 4; }
+size_t spt_fused_layer_bytes() { return (size_t)LAYER_WORDS_FULL * 4; }
 
 int launch_spt_pack_layer(const float* n1w, const float* n1b, const float* qkvw, const float* qkvb, const float* projw,
                           const float* projb, const float* n2w, const float* n2b, const float* fc1w, const float* fc1b,
                           const float* fc2w, const float* fc2b, float scale, void* dst, cudaStream_t s) {
   SptPackArgs a{n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, reinterpret_cast<uint32_t*>(dst),
                 scale * 1.4426950408889634f};
-  spt_pack_kernel<<<(LAYER_WORDS + 255) / 256, 256, 0, s>>>(a);
+  spt_pack_kernel<<<(LAYER_WORDS_FULL + 255) / 256, 256, 0, s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
@@ -696,16 +814,18 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
   a.conf = conf;
   a.B = B;
   a.depth = depth;
-  static bool attr_set[64][2] = {};  // per device: function attributes live in the device's context (DataParallel replicas)
+  // per device: function attributes live in the device's context (DataParallel replicas); setting one twice is harmless
+  static std::atomic<unsigned char> attr_set[64][2];
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
   auto kern = precise ? spt_fused_kernel<true, false> : spt_fused_kernel<false, false>;
-  if (dev < 0 || dev >= 64 || !attr_set[dev][precise ? 1 : 0]) {
-    MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    if (dev >= 0 && dev < 64) attr_set[dev][precise ? 1 : 0] = true;
+  const int smem_bytes = precise ? Smem<true>::TOTAL : Smem<false>::TOTAL;
+  if (dev < 0 || dev >= 64 || !attr_set[dev][precise ? 1 : 0].load(std::memory_order_acquire)) {
+    MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (dev >= 0 && dev < 64) attr_set[dev][precise ? 1 : 0].store(1, std::memory_order_release);
   }
   dim3 grid((unsigned)ceil_div(B, SETS), (unsigned)V);
-  kern<<<grid, THREADS, SMEM_TOTAL, s>>>(a);
+  kern<<<grid, THREADS, smem_bytes, s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
@@ -728,16 +848,16 @@ int launch_fpt_kp_fused(float* tok, const void* wpack, int V, int64_t B, int dep
   const int sets_used = (SETS / V) * V;
   a.rows_used = sets_used * J;
   a.final_norm = 0;
-  static bool attr_set[64] = {};
+  static std::atomic<unsigned char> attr_set[64];
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
   auto kern = spt_fused_kernel<false, true>;
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
+    MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<false>::TOTAL));
+    if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
   }
   dim3 grid((unsigned)ceil_div(B * V, sets_used), 1);
-  kern<<<grid, THREADS, SMEM_TOTAL, s>>>(a);
+  kern<<<grid, THREADS, Smem<false>::TOTAL, s>>>(a);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

@@ -24,8 +24,9 @@ import torch.nn as nn
 from .. import _lib
 from ..spec import BUFFER_KINDS, CTOR_DEFAULTS, make_config, param_spec
 
-# "fp32" is the parity-grade default (<= 1e-3 of the output scale vs the reference, measured ~1e-6); "bf16" is the
-# throughput mode (tcgen05 bf16 projections + fused bf16-mma SPT, stated bound 3e-2); "tf32" = single-pass kind::tf32.
+# "fp32" is the bit-for-intent default (CUDA-core fp32, ~1e-6 of the output scale vs the reference); "tf32" is the
+# fp32-grade TENSOR-CORE mode (split bf16 hi/lo operands, three tcgen05 MMAs per product; carries the north-star bound
+# <= 1e-3 of scale / 0.1 mm); "bf16" is the throughput mode (tcgen05 bf16 projections + fused fp16-mma SPT).
 DEFAULT_PRECISION = os.environ.get("MPL_B200_PRECISION", "fp32")
 
 
@@ -102,11 +103,14 @@ class MultiView_MPL(nn.Module):
                  deep_head=False,
                  head_kadkhod=False,
                  hidden_dim=1024,
-                 FPT_blocks_view_keypoint_tokens=False, *, precision=None):
+                 FPT_blocks_view_keypoint_tokens=False, *, precision=None, ln_fusion=True, gemm_cta_group=2):
         super().__init__()
         kw = {k: v for k, v in locals().items() if k in CTOR_DEFAULTS}
         self.cfg = make_config(**kw)
         self.precision = precision or DEFAULT_PRECISION
+        # implementation switches (MplDesc.ln_fusion / gemm_cta_group): bf16 mode folds the FPT LayerNorms into the GEMMs
+        # unless ln_fusion=False (checkpoints whose residual rows have |mean| >> std)
+        self.ln_fusion, self.gemm_cta_group = bool(ln_fusion), int(gemm_cta_group)
         self.num_joints, self.num_views, self.embed_dim_ratio = num_joints, num_views, embed_dim_ratio
         self._spec = param_spec(self.cfg)
         for name, (shape, kind, fan_in) in self._spec.items():
@@ -125,7 +129,7 @@ class MultiView_MPL(nn.Module):
             index = torch.cuda.current_device() if torch.cuda.is_available() else -1
         if index not in self._h.ptrs:
             L = _lib.lib()
-            desc = _lib.make_desc(self.cfg.kw, self.precision)
+            desc = _lib.make_desc(self.cfg.kw, self.precision, self.ln_fusion, self.gemm_cta_group)
             h = ctypes.c_void_p()
             _lib.check(L.mpl_create(ctypes.byref(desc), ctypes.byref(h)))
             n = L.mpl_num_params(h)
@@ -427,6 +431,8 @@ class MultiView_MPL_G(nn.Module):
             hidden_dim=net.TRANSFORMER_OUTPUT_HEAD_HIDDEN_DIM,
             FPT_blocks_view_keypoint_tokens=net.TRANSFORMER_FPT_BLOCKS_VIEW_KEYPOINT_TOKENS,
             precision=kwargs.get("precision"),
+            ln_fusion=kwargs.get("ln_fusion", True),
+            gemm_cta_group=kwargs.get("gemm_cta_group", 2),
         )
 
     def forward(self, x, centers=None, rays=None):

@@ -6,16 +6,17 @@ from oracle import mpl_oracle
 from openmpl_b200.models import multiview_mpl_b200 as mb
 
 # Stated tolerances (per-coordinate max abs error / output scale), BASELINE.json north_star:
-#   fp32  : the path that carries the "<= 1e-3 of scale, dMPJPE <= 0.1 mm" claim (measured ~1e-6)
-#   tf32  : single-pass tcgen05 kind::tf32 projections; measured 0.6e-3 .. 2.1e-3 of scale on the parity cases, i.e. it
-#           does NOT always meet 1e-3 (SURVEY.md §7-H5 predicted this) -> stated bound 4e-3, opt-in only
-#   bf16  : bf16 tensor-core operands, fp32 accumulate / LayerNorm / softmax / residual -> stated bound 3e-2
-TOL = {"fp32": 2e-5, "tf32": 4e-3, "bf16": 3e-2}
-DMPJPE_MM = {"fp32": 0.1, "tf32": 0.5, "bf16": 1.5}     # |MPJPE(new) - MPJPE(reference)| in mm (targets in metres)
+#   fp32  : CUDA-core fp32 arithmetic (measured ~1e-6)
+#   tf32  : the fp32-grade TENSOR-CORE mode that carries the north-star claim "<= 1e-3 of scale, dMPJPE <= 0.1 mm for the
+#           fp32/TF32 path": tcgen05 on split bf16 hi/lo operands (three MMAs per product), fp32 everything else
+#   bf16  : bf16 tensor-core operands, fp32 accumulate / LayerNorm statistics / softmax / residual.  Measured 1.0e-3 ..
+#           4.1e-3 on the shipped architectures, 1.0e-2 on the worst parity case -> stated bound 1.2e-2, 0.5 mm
+TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 1.2e-2}
+DMPJPE_MM = {"fp32": 0.1, "tf32": 0.1, "bf16": 0.5}     # |MPJPE(new) - MPJPE(reference)| in mm (targets in metres)
 
 
-def build_module(kw, weights, precision, device="cuda"):
-    m = mb.MultiView_MPL(**kw, precision=precision)
+def build_module(kw, weights, precision, device="cuda", **impl):
+    m = mb.MultiView_MPL(**kw, precision=precision, **impl)
     m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}, strict=True)
     return m.to(device).eval()
 

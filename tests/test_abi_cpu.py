@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().mpl_abi_version() == 1
+    assert _lib.lib().mpl_abi_version() == _lib.ABI_VERSION
 
 
 def _lib_param_table(kw, precision="fp32"):
@@ -101,7 +101,7 @@ def test_workspace_and_packed_sizes_are_monotone():
 def test_module_state_dict_names_and_ctor_signature():
     import inspect
     sig = inspect.signature(mb.MultiView_MPL.__init__)
-    names = [p for p in sig.parameters if p not in ("self", "precision")]
+    names = [p for p, q in sig.parameters.items() if p != "self" and q.kind != q.KEYWORD_ONLY]   # keyword-only = implementation switches
     assert names == list(spec.CTOR_DEFAULTS)
     for k, v in spec.CTOR_DEFAULTS.items():
         assert sig.parameters[k].default == v, k

@@ -164,20 +164,14 @@ def test_fused_spt_kernel_variants_against_oracle(flags, B):
 def test_layernorm_fusion_on_and_off_agree_with_the_reference(name):
     """bf16 mode folds the FPT LayerNorms into the projection GEMMs (rank-1 form); the unfused form
     (separate LayerNorm kernels) stays selectable.  Both must meet the bf16 bound and agree with each other closely."""
-    from openmpl_b200 import _lib
-    L = _lib.lib()
     case = CASES[name]
     g = load_golden(name)
     cfg, weights, batch = make_inputs(case)
     outs = {}
-    try:
-        for fused in (1, 0):
-            assert L.mpl_set_ln_fusion(fused) == 0 and L.mpl_get_ln_fusion() == fused
-            m = build_module(case["kw"], weights, "bf16")
-            outs[fused] = run_module(m, batch)[0]
-            assert rel_err(outs[fused], g["out64_0"]) <= TOL["bf16"]
-    finally:
-        L.mpl_set_ln_fusion(1)
+    for fused in (1, 0):
+        m = build_module(case["kw"], weights, "bf16", ln_fusion=bool(fused))
+        outs[fused] = run_module(m, batch)[0]
+        assert rel_err(outs[fused], g["out64_0"]) <= TOL["bf16"]
     assert rel_err(outs[1], outs[0].astype(np.float64)) <= TOL["bf16"]
 
 
