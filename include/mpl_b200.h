@@ -196,6 +196,18 @@ int mpl_synth_project(uint64_t seed, int64_t start, int64_t batch, int num_views
 int mpl_test_gemm(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
                   int epilogue, int out_fp32, int cta_group, mpl_stream_t stream);
 
+/* The LayerNorm-fused epilogues of the bf16 mode in isolation.
+ *   epilogue 4 / 5 (LayerNorm-apply, QKV / fc1): Y[M,N] (bf16, or fp16 when out_fp16) = act(rstd * (A W'^T - mu * colsum) + bias),
+ *       A = raw residual rows rounded to bf16, W' = bf16(W diag(gamma)), colsum[n] = sum_k W'[n,k], bias = b + W beta,
+ *       (mu, rstd) from stats_in = [slots_in][M rounded up to 256] float2 partial (sum x, sum x^2) per row, eps = LayerNorm eps;
+ *   epilogue 6 (residual-emit, proj / fc2): the residual stream x [M,N] as two bf16 planes (Y = hi, x_lo = lo), updated in place:
+ *       x += A W^T + bias; stats_out = [mpl_test_gemm_ln_slots(N)][M rounded up to 256] float2 partial (sum, sum^2) of the new x;
+ *       ab_fp16: A and W hold fp16 instead of bf16. */
+int mpl_test_gemm_ln(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int epilogue,
+                     const float* colsum, const void* stats_in, int slots_in, void* stats_out, void* x_lo, float eps,
+                     int ab_fp16, int out_fp16, int cta_group, mpl_stream_t stream);
+int mpl_test_gemm_ln_slots(int N);
+
 #ifdef __cplusplus
 }
 #endif

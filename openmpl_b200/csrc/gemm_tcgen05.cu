@@ -13,6 +13,8 @@
 //                             never read by the SM).  Two warps per TMEM lane quarter, 64 columns per step.
 //                             bf16 mode folds the LayerNorms in: LN-apply epilogues (EPI 4 / 5) for QKV / fc1 and
 //                             residual-emit epilogues (EPI 6 / 7) for proj / fc2, see GemmLn below.
+//   warp 3     residual producer (EPI 6 / 7 only): TMA-loads the old residual boxes (two bf16 planes) into a ring of
+//                             shared-memory slots, running ahead of the epilogue warps across tile boundaries
 // CG = 1: one CTA per 128 x 256 output tile.  CG = 2: a CTA pair (cluster 2x1x1, cta_group::2) per 256 x 256 tile, each
 // CTA staging half of A and half of W, which halves the shared-memory and L2 operand traffic per MMA.
 // Every FPT width is a multiple of 17 (D = 1088 = 17*64): ragged N tiles use a narrower UMMA N (multiple of 16) and
@@ -45,14 +47,34 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CG;                    // W rows staged per CTA
   static constexpr int B_BYTES = B_ROWS * KB_BYTES;         // 32 KB / 16 KB
   static constexpr int STAGE_BYTES = OPS * (A_BYTES + B_BYTES);  // 48 KB / 32 KB (split: 96 KB / 64 KB)
-  // 192 KB of operand ring.  The residual-emit epilogue (EPI 6) trades two stages for a shared-memory prefetch ring of
-  // old residual values (measured: the ring depth does not matter for K = 1088 and costs K = 2176 little)
-  static constexpr int XRING_BYTES = (EPI == 6) ? NUM_EPI_WARPS * 2 * 4096 : 0;  // two 4 KB chunks per epilogue warp
-  static constexpr int STAGES = (KIND == 1) ? ((CG == 1) ? 2 : 3) : (EPI == 6) ? ((CG == 1) ? 2 : 4) : ((CG == 1) ? 4 : 6);
-  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 4096; // per epilogue warp: one 32-row x 128-byte output box
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + XRING_BYTES + BAR_BYTES;
+  // The residual-emit epilogues keep the old residual in a TMA-fed ring of 8 KB slots (a 32-row x 64-column box of each
+  // bf16 plane) that is updated in place and stored back from the same slot, paid for with operand stages: the short-K proj
+  // (EPI 6) is epilogue / HBM bound -> 4 stages + 12 slots; the long-K fc2 (EPI 7) is MMA bound -> 5 stages + 8 slots.
+  static constexpr bool RESID = (KIND == 0) && (EPI == 6 || EPI == 7);
+  static constexpr int RING_SLOTS = !RESID ? 0 : (EPI == 6 ? 12 : 8);
+  static constexpr int SLOT_BYTES = 8192;
+  static constexpr int RING_BYTES = RING_SLOTS * SLOT_BYTES;
+  static constexpr int STAGES = (KIND == 1) ? ((CG == 1) ? 2 : 3)
+                                : (EPI == 6) ? ((CG == 1) ? 2 : 4) : (EPI == 7) ? ((CG == 1) ? 3 : 5) : ((CG == 1) ? 4 : 6);
+  static constexpr int STAGING_BYTES = RESID ? 0 : NUM_EPI_WARPS * 4096;  // per epilogue warp: one 32-row x 128-byte output box
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + RING_BYTES + BAR_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
+
+// Output columns are dealt to T tiles in whole 64-column groups, as evenly as possible: the first r tiles take q + 1 groups,
+// the others q (the last one clipped at N).  N = 1088 (17 groups) -> 256 | 256 | 192 | 192 | 192, N = 2176 -> 7 x 256 + 2 x 192:
+// no narrow tail tile (a 64-wide tile costs far more than a quarter of a 256-wide one) and every tile starts on a
+// 128-byte boundary of the bf16 output row.
+struct TileSplit {
+  int T, q, r;
+};
+__host__ __device__ __forceinline__ void tile_cols(const TileSplit& ts, int i, int N, int& n0, int& n_size, bool& wide) {
+  wide = i < ts.r;
+  n0 = 64 * (i * ts.q + (i < ts.r ? i : ts.r));
+  const int w = 64 * (ts.q + (wide ? 1 : 0));
+  n_size = (w < N - n0) ? w : N - n0;
+}
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -76,18 +98,18 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, bool fp16 = false) 
 //      (6: shared-memory prefetch ring of the old residual, 7: register prefetch).
 //
 // LayerNorm fused around the projections (bf16 mode).  LN(x) W^T + b = rstd * (x W'^T - mu * colsum(W')) + b' with
-// W' = W diag(gamma), b' = b + W beta: the consumer GEMM (QKV, fc1; EPI 4 / 5) multiplies the RAW residual rows (a bf16
-// copy) by W' and applies the per-row (mu, rstd) in its epilogue; the producer GEMM of that residual (proj, fc2; EPI 6)
-// computes x_new = x_old + acc + bias in its epilogue, stores it (fp32) together with the bf16 copy and per-row partial
+// W' = W diag(gamma), b' = b + W beta.  The residual stream x lives in HBM as TWO bf16 planes, hi = bf16(x) and
+// lo = bf16(x - hi) (16 significand bits).  The consumer GEMM (QKV, fc1; EPI 4 / 5) multiplies the hi plane (the RAW
+// residual rows rounded to bf16) by W' and applies the per-row (mu, rstd) in its epilogue; the producer GEMM of that
+// residual (proj, fc2; EPI 6 / 7) computes x_new = hi + lo + acc + bias in its epilogue, writes both planes back in place
+// (TMA in, TMA out: 8 bytes per element instead of the 12 of an fp32 stream plus a bf16 copy) and per-row partial
 // (sum, sum of squares) of its column slice into a fixed slot -> no LayerNorm kernel, no atomics, bitwise reproducible.
 struct GemmLn {
   const float* colsum;      // [N]  sum_k bf16(W'[n,k])                       (EPI 4 / 5)
   const float2* stats_in;   // [slots_in][stats_ld] partial (sum x, sum x^2) per row, slot-major: a warp's 32 rows of one
                             // slot are one coalesced 256-byte access                           (EPI 4 / 5)
-  float2* stats_out;        // [slots_out][stats_ld]                                            (EPI 6)
+  float2* stats_out;        // [slots_out][stats_ld]                                            (EPI 6 / 7)
   int64_t stats_ld;         // rows per slot plane (M rounded up to a multiple of 256)
-  __nv_bfloat16* xb;        // [M, N] bf16 copy of the updated residual         (EPI 6)
-  float* y_raw;             // [M, N] the fp32 residual (read in the epilogue)  (EPI 6)
   int slots_in, slots_out;
   float inv_k, eps;         // 1 / LayerNorm width (= K of the consumer), LayerNorm eps
   int flags;                // bit 1: A and W are fp16 (not bf16); bit 2: the 16-bit output is fp16 and GELU runs in packed half2
@@ -183,27 +205,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmY2,
-                    const float* __restrict__ bias, int64_t M, int N, int K,
-                    int bn, const GemmLn ln) {  // bn: output-tile width (256 / 192 / 128), chosen so that no interior tile is narrow
-  // tmA2 / tmB2 / tmY2: the lo planes of the split mode (KIND 1); copies of tmA / tmB / tmY otherwise
+                    const float* __restrict__ bias, int64_t M, int N, int K, const TileSplit ts, const GemmLn ln) {
+  // tmA2 / tmY2: the lo planes of the split mode (KIND 1) and of the residual stream (EPI 6 / 7).  tmB2: the lo plane of W in
+  // split mode; otherwise the W box of the narrow tiles (q groups; tmB serves the wide ones, q + 1 groups)
   using C = Cfg<CG, EPI, KIND>;
   constexpr bool SPLIT = (KIND == 1);
-  constexpr int ESZ = 2;
-  constexpr int BK = KB_BYTES / ESZ;  // K elements per stage
+  constexpr bool RESID = C::RESID;
+  constexpr int BK = KB_BYTES / 2;  // K elements per stage (16-bit operands)
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte aligned bases
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;  // 1024-aligned: stage sizes are multiples of 1 KB
-  const uint32_t xring_base = staging_base + C::STAGING_BYTES;
-  const uint32_t bar_base = xring_base + C::XRING_BYTES;
+  const uint32_t ring_base = staging_base + C::STAGING_BYTES;
+  const uint32_t bar_base = ring_base + C::RING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 5 + s); };
+  auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 5 + C::RING_SLOTS + s); };
+  static_assert(8 * (2 * C::STAGES + 5 + 2 * C::RING_SLOTS) <= C::BAR_BYTES, "barrier area too small");
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + C::XRING_BYTES + 8 * (2 * C::STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + C::RING_BYTES + 8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
@@ -213,9 +238,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     ptx::prefetch_tensormap(&tmY);
-    if constexpr (SPLIT) {
+    ptx::prefetch_tensormap(&tmB2);
+    if constexpr (SPLIT || RESID) {
       ptx::prefetch_tensormap(&tmA2);
-      ptx::prefetch_tensormap(&tmB2);
       ptx::prefetch_tensormap(&tmY2);
     }
   }
@@ -228,6 +253,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_init(tfull_bar(s), 1);        // one tcgen05.commit
       ptx::mbar_init(tempty_bar(s), NUM_EPI_WARPS * CG);  // one arrive per epilogue warp of every CTA of the pair
     }
+    for (int s = 0; s < C::RING_SLOTS; ++s) {
+      ptx::mbar_init(rfull_bar(s), 1);   // the residual producer's arrive.expect_tx
+      ptx::mbar_init(rempty_bar(s), 1);  // the consuming epilogue warp's release
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -239,8 +268,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int n_tiles = (N + bn - 1) / bn;
-  const uint32_t stage_tx = (uint32_t)(C::OPS * (C::A_BYTES + (bn / CG) * KB_BYTES));  // bytes one CTA's TMA boxes deliver per stage
+  const int n_tiles = ts.T;
+  // W rows one CTA stages per k-block for a wide / narrow tile (split mode has no narrow box: its tmB2 is the lo plane)
+  const int wide_rows = 64 * (ts.q + (ts.r > 0 ? 1 : 0)) / CG;
+  const int narrow_rows = SPLIT ? wide_rows : 64 * ts.q / CG;
   const int64_t m_tiles = (M + (int64_t)BM * CG - 1) / ((int64_t)BM * CG);
   const int64_t total_tiles = m_tiles * n_tiles;
   const int64_t first_tile = blockIdx.x / CG;
@@ -256,9 +287,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int64_t m_blk = tile / n_tiles;
         const int n_blk = (int)(tile % n_tiles);
-        const int n_size = min(bn, N - n_blk * bn);
+        int nt0, n_size;
+        bool wide;
+        tile_cols(ts, n_blk, N, nt0, n_size, wide);
         const int32_t m0 = (int32_t)(m_blk * BM * CG + cta_rank * BM);
-        const int32_t n0 = n_blk * bn + (int32_t)cta_rank * (n_size / CG);
+        const int32_t n0 = nt0 + (int32_t)cta_rank * (n_size / CG);
+        const bool use_narrow = !SPLIT && !wide;
+        const CUtensorMap* tb = use_narrow ? &tmB2 : &tmB;
+        const uint32_t stage_tx = (uint32_t)(C::OPS * (C::A_BYTES + (use_narrow ? narrow_rows : wide_rows) * KB_BYTES));
         // The A rows of a tile come from HBM exactly once (the n-tiles of one row block run concurrently on
         // neighbouring CTAs and share them through L2).  Whoever will open the next row block pulls its A rows into
         // L2 now, one tile ahead, so those first-touch misses do not stall the operand ring.
@@ -276,7 +312,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (CG == 1) {
             ptx::mbar_arrive_expect_tx(full_bar(stage), stage_tx);
             ptx::tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, m0);
-            ptx::tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, n0);
+            ptx::tma_load_2d(b_dst, tb, full_bar(stage), kb * BK, n0);
             if constexpr (SPLIT) {
               ptx::tma_load_2d(a_dst + C::A_BYTES, &tmA2, full_bar(stage), kb * BK, m0);
               ptx::tma_load_2d(b_dst + C::B_BYTES, &tmB2, full_bar(stage), kb * BK, n0);
@@ -286,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // the peer's bytes may land before this expect_tx: the phase still cannot complete without this arrive
             if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
             ptx::tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
-            ptx::tma_load_2d_pair(b_dst, &tmB, lbar, kb * BK, n0);
+            ptx::tma_load_2d_pair(b_dst, tb, lbar, kb * BK, n0);
             if constexpr (SPLIT) {
               ptx::tma_load_2d_pair(a_dst + C::A_BYTES, &tmA2, lbar, kb * BK, m0);
               ptx::tma_load_2d_pair(b_dst + C::B_BYTES, &tmB2, lbar, kb * BK, n0);
@@ -306,7 +342,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t acc_phase = 0;
       for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int n_blk = (int)(tile % n_tiles);
-        const int n_size = min(bn, N - n_blk * bn);
+        int nt0, n_size;
+        bool wide;
+        tile_cols(ts, n_blk, N, nt0, n_size, wide);
         const uint32_t idesc = make_idesc(BM * CG, n_size, (ln.flags & 2) != 0);
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
@@ -341,6 +379,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    // ===================================== residual producer (EPI 6 / 7) =====================
+    // Items = (tile, 64-column group g, 32-row quarter q) in that order; item i lives in ring slot i % RING_SLOTS and is
+    // consumed by epilogue warp (q, g & 1).  The producer runs as far ahead as the ring allows -- across tile boundaries,
+    // i.e. the old residual of the next tile streams in while its accumulator is still being computed.
+    if constexpr (RESID) {
+      if (lane == 0) {
+        uint32_t item = 0;
+        for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
+          const int64_t m_blk = tile / n_tiles;
+          const int n_blk = (int)(tile % n_tiles);
+          int nt0, n_size;
+          bool wide;
+          tile_cols(ts, n_blk, N, nt0, n_size, wide);
+          const int ng = (n_size + 63) >> 6;
+          const int32_t row_base = (int32_t)(m_blk * BM * CG + cta_rank * BM);
+          for (int g = 0; g < ng; ++g) {
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q, ++item) {
+              const uint32_t slot = item % C::RING_SLOTS, ph = (item / C::RING_SLOTS) & 1u;
+              ptx::mbar_wait(rempty_bar(slot), ph ^ 1u);
+              const uint32_t dst = ring_base + slot * C::SLOT_BYTES;
+              ptx::mbar_arrive_expect_tx(rfull_bar(slot), C::SLOT_BYTES);
+              ptx::tma_load_2d(dst, &tmY, rfull_bar(slot), nt0 + 64 * g, row_base + 32 * q);
+              ptx::tma_load_2d(dst + 4096, &tmY2, rfull_bar(slot), nt0 + 64 * g, row_base + 32 * q);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
     const int q = warp & 3;            // TMEM lane quarter this warp may read (warp id % 4)
@@ -352,45 +421,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t leader_tempty0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : 0u;
-    // ---- EPI 6: prefetch ring of old residual values.  This warp's 32 x 32 chunks form one stream across its tiles; a
-    // fetch cursor runs TWO chunks ahead of the consumer and copies each chunk with cp.async (16 bytes per lane and row
-    // group, the coalesced layout the consumer reads back) into one of two 4 KB slots: no registers are tied up and the
-    // DRAM latency of a chunk is covered by two chunk times, across tile boundaries too.
-    const int e6_rs = lane >> 3, e6_c4 = lane & 7;
-    auto e6_chunk_col = [&](int ci) { return half * 64 + (ci >> 1) * 128 + (ci & 1) * 32; };
-    const uint32_t e6_ring = xring_base + (uint32_t)(warp - 4) * 8192u + (uint32_t)lane * 16u;
-    int64_t f_tile = first_tile;  // fetch cursor
-    int f_ci = -1;
-    uint32_t f_seq = 0, c_seq = 0;
-    auto e6_fetch_next = [&]() {  // advance the cursor to the next chunk of the stream and start copying it
-      if constexpr (EPI == 6) {
-        for (;;) {
-          if (f_tile >= total_tiles) break;
-          ++f_ci;
-          const int nn = (int)(f_tile % n_tiles);
-          if (f_ci < BN / 64 && e6_chunk_col(f_ci) < min(bn, N - nn * bn)) {
-            const float* p = ln.y_raw + ((f_tile / n_tiles) * BM * CG + cta_rank * BM + q * 32 + e6_rs) * (int64_t)N + nn * bn +
-                             4 * e6_c4 + e6_chunk_col(f_ci);
-            const uint32_t dst = e6_ring + (f_seq & 1u) * 4096u;
-#pragma unroll
-            for (int it = 0; it < 8; ++it)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + it * 512), "l"(p + (int64_t)it * 4 * N) : "memory");
-            break;
-          }
-          f_tile += tile_stride;
-          f_ci = -1;
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per call, empty past the end of the stream
-        ++f_seq;
-      }
-    };
-    if constexpr (EPI == 6) { e6_fetch_next(); e6_fetch_next(); }
+    uint32_t item_base = 0;  // RESID: items of this CTA before the current tile
+    int held_slot = -1;      // RESID: ring slot whose TMA stores may still be reading shared memory
     for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const int64_t m_blk = tile / n_tiles;
       const int n_blk = (int)(tile % n_tiles);
-      const int n_size = min(bn, N - n_blk * bn);
+      int ncol0, n_size;
+      bool wide;
+      tile_cols(ts, n_blk, N, ncol0, n_size, wide);
       const int32_t row0 = (int32_t)(m_blk * BM * CG + cta_rank * BM + q * 32);  // first row of this warp's 32-row box
-      const int ncol0 = n_blk * bn;
       const int64_t my_row = (int64_t)row0 + lane;
       const bool row_ok = my_row < M;
       float mu = 0.f, rstd = 1.f;
@@ -410,70 +449,89 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mu = s1 * ln.inv_k;
         rstd = rsqrtf(fmaxf(fmaf(-mu, mu, s2 * ln.inv_k), 0.f) + ln.eps);
       }
-      if constexpr (EPI == 6) {
-        // Residual update x_new = x_old + acc + bias, 32-column chunks.  The accumulator arrives one row per lane; the
-        // residual is read and written in a COALESCED layout instead (lane = (row & 3, 16-byte column group): 4 rows x
-        // 128 B per instruction), the staging box doing the transpose; x_old comes from the prefetch ring above.
-        // No predicates: N % 32 == 0 makes a chunk valid for all lanes or none, and the caller pads the residual, its
-        // bf16 copy and the statistics to a multiple of BM * CG rows, so rows past M are scratch (read, updated, ignored).
-        const int rs = e6_rs, c4 = e6_c4;
-        float* const lp = ln.y_raw + ((int64_t)row0 + rs) * N + ncol0 + 4 * c4;
-        __nv_bfloat16* const lb = ln.xb + ((int64_t)row0 + rs) * N + ncol0 + 4 * c4;
-        const int64_t rowstep = 4 * (int64_t)N;
-        float s1[8], s2[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) { s1[it] = 0.f; s2[it] = 0.f; }
+      if constexpr (RESID) {
+        // Residual update x_new = (hi + lo) + acc + bias on two bf16 planes.  The old planes arrive by TMA in the ring slot
+        // (128B-swizzled 32-row x 64-column boxes, so this lane's row is eight conflict-free 16-byte chunks per plane --
+        // the same one-row-per-lane layout the accumulator has, no transposition); the new planes overwrite them in place
+        // and leave by TMA from the same slot.  Rows past M and columns past N are zero-filled on the way in and clipped
+        // on the way out by the tensor maps.  The row statistics are per-lane sums: no shuffles.
+        const int ng = (n_size + 63) >> 6;
+        float s1 = 0.f, s2 = 0.f;
         ptx::mbar_wait(tfull_bar(acc), acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-        const uint32_t rd_base = box + rs * 128;  // this lane reads rows 4*it + rs of the box: (4*it + rs) & 7 = ((it & 1) * 4 + rs)
-        const uint32_t rd_sw0 = (uint32_t)((c4 ^ rs) << 4), rd_sw1 = (uint32_t)((c4 ^ (4 + rs)) << 4);
+        for (int g = half; g < ng; g += 2) {
+          const uint32_t item = item_base + (uint32_t)(4 * g + q);
+          const uint32_t slot = item % C::RING_SLOTS, ph = (item / C::RING_SLOTS) & 1u;
+          if (held_slot >= 0) {  // hand the previous slot back before waiting for the next one (no hold-and-wait)
+            if (lane == 0) {
+              ptx::bulk_wait_read<0>();
+              ptx::mbar_arrive(rempty_bar(held_slot));
+            }
+            held_slot = -1;
+          }
+          ptx::mbar_wait(rfull_bar(slot), ph);
+          const uint32_t rowh = ring_base + slot * C::SLOT_BYTES + (uint32_t)lane * 128u;
+          const uint32_t rowl = rowh + 4096u;
+          const int gcol = ncol0 + 64 * g;
 #pragma unroll
-        for (int ci = 0; ci < BN / 64; ++ci) {  // at most 4 chunks of 32 columns per warp and tile
-          const int cc = e6_chunk_col(ci);
-          if (cc >= n_size) break;
-          uint32_t va[32];
-          ptx::tmem_ld_32x32(taddr + cc, va);
-          ptx::tmem_ld_wait();
-          float f[32];
-          epilogue_math<KIND, 0>(va, bias, ncol0 + cc, N, f);
-          stage_row_f32(box, lane, f);
-          asm volatile("cp.async.wait_group 1;" ::: "memory");  // this chunk's old values have landed (own copies only)
+          for (int hb = 0; hb < 2; ++hb) {
+            uint32_t va[32];
+            ptx::tmem_ld_32x32(taddr + 64 * g + 32 * hb, va);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = 4 * hb + jj;
+              const int col = gcol + 8 * j;
+              const uint32_t sw = (uint32_t)((j ^ (lane & 7)) << 4);
+              uint32_t h[4], l[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(rowh + sw));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(rowl + sw));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + min(col, N - 4)));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + min(col + 4, N - 4)));
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float v[8];
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const float x0 = __uint_as_float(h[w] << 16) + __uint_as_float(l[w] << 16);
+                const float x1 = __uint_as_float(h[w] & 0xffff0000u) + __uint_as_float(l[w] & 0xffff0000u);
+                v[2 * w] = (__uint_as_float(va[8 * jj + 2 * w]) + bb[2 * w]) + x0;
+                v[2 * w + 1] = (__uint_as_float(va[8 * jj + 2 * w + 1]) + bb[2 * w + 1]) + x1;
+              }
+              if (col < N) {  // (whole 8-column chunks: N % 8 == 0) columns past N carry stale accumulator values
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+              }
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * w], v[2 * w + 1]);
+                h[w] = *reinterpret_cast<const uint32_t*>(&hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * w] - __uint_as_float(h[w] << 16),
+                                                                v[2 * w + 1] - __uint_as_float(h[w] & 0xffff0000u));
+                l[w] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              ptx::st_shared_v4(rowh + sw, h[0], h[1], h[2], h[3]);
+              ptx::st_shared_v4(rowl + sw, l[0], l[1], l[2], l[3]);
+            }
+          }
+          ptx::fence_proxy_async();
           __syncwarp();
-          const uint32_t xsrc = e6_ring + (c_seq & 1u) * 4096u;
-          float* sp = lp + cc;
-          __nv_bfloat16* sb = lb + cc;
-#pragma unroll
-          for (int it = 0; it < 8; ++it, sp += rowstep, sb += rowstep) {
-            float4 v, o;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(rd_base + it * 512 + ((it & 1) ? rd_sw1 : rd_sw0)));
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(xsrc + it * 512));
-            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            s1[it] += (v.x + v.y) + (v.z + v.w);
-            s2[it] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[it]))));
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<float4*>(sp) = v;
-            *reinterpret_cast<uint2*>(sb) = pk;
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmY, ring_base + slot * C::SLOT_BYTES, gcol, row0);
+            ptx::tma_store_2d(&tmY2, ring_base + slot * C::SLOT_BYTES + 4096u, gcol, row0);
+            ptx::bulk_commit();
           }
-          ++c_seq;
-          e6_fetch_next();  // the slot just consumed takes the chunk two ahead
-          __syncwarp();     // every lane is done reading the box before the next chunk is staged
+          held_slot = (int)slot;
         }
-        // per-row partial statistics: sum over the 8 lanes that share a row, fixed order
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-#pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            s1[it] += __shfl_xor_sync(0xffffffffu, s1[it], o);
-            s2[it] += __shfl_xor_sync(0xffffffffu, s2[it], o);
+        if (held_slot >= 0) {  // nothing is held across tiles: the producer prefetches the next tile's boxes meanwhile
+          if (lane == 0) {
+            ptx::bulk_wait_read<0>();
+            ptx::mbar_arrive(rempty_bar(held_slot));
           }
-          if (c4 == 0) ln.stats_out[(2 * n_blk + half) * ln.stats_ld + row0 + 4 * it + rs] = make_float2(s1[it], s2[it]);
+          held_slot = -1;
         }
+        // per-row partial statistics of this warp's column slice (rows past M land in the padding of the slot plane)
+        ln.stats_out[(2 * n_blk + half) * ln.stats_ld + my_row] = make_float2(s1, s2);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -481,86 +539,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else ptx::mbar_arrive_cluster(leader_tempty0 + 8u * acc);
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        continue;
-      }
-      if constexpr (EPI == 7) {
-        // Residual update, register-prefetch form (long K: the main loop hides the epilogue, all six ring stages kept).
-        // Residual update x_new = x_old + acc + bias, 32-column chunks.  The accumulator arrives one row per lane; the
-        // residual is read and written in a COALESCED layout instead (lane = (row & 3, 16-byte column group): 4 rows x
-        // 128 B per instruction), the staging box doing the transpose.  x_old of the next chunk is prefetched into
-        // registers while the current one is processed (the first one before the accumulator is even complete).
-        const int rs = lane >> 3, c4 = lane & 7;
-        auto chunk_col = [&](int ci) { return half * 64 + (ci >> 1) * 128 + (ci & 1) * 32; };
-        // No predicates: N % 32 == 0 makes a chunk valid for all lanes or none, and the caller pads the residual, its
-        // bf16 copy and the statistics to a multiple of BM * CG rows, so rows past M are scratch (read, updated, ignored).
-        float* const lp = ln.y_raw + ((int64_t)row0 + rs) * N + ncol0 + 4 * c4;
-        __nv_bfloat16* const lb = ln.xb + ((int64_t)row0 + rs) * N + ncol0 + 4 * c4;
-        const int64_t rowstep = 4 * (int64_t)N;
-        auto load_xold = [&](int ci, float4 (&xo)[8]) {
-          const float* p = lp + chunk_col(ci);
-#pragma unroll
-          for (int it = 0; it < 8; ++it, p += rowstep) xo[it] = *reinterpret_cast<const float4*>(p);
-        };
-        float s1[8], s2[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) { s1[it] = 0.f; s2[it] = 0.f; }
-        float4 xo[2][8];  // ping-pong prefetch buffers (the chunk loop is fully unrolled: compile-time indices, no copies)
-        load_xold(0, xo[0]);
-        ptx::mbar_wait(tfull_bar(acc), acc_phase);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-        const uint32_t rd_base = box + rs * 128;  // this lane reads rows 4*it + rs of the box: (4*it + rs) & 7 = ((it & 1) * 4 + rs)
-        const uint32_t rd_sw0 = (uint32_t)((c4 ^ rs) << 4), rd_sw1 = (uint32_t)((c4 ^ (4 + rs)) << 4);
-#pragma unroll
-        for (int ci = 0; ci < BN / 64; ++ci) {  // at most 4 chunks of 32 columns per warp and tile
-          const int cc = chunk_col(ci);
-          if (cc >= n_size) break;
-          uint32_t va[32];
-          ptx::tmem_ld_32x32(taddr + cc, va);
-          if (ci + 1 < BN / 64 && chunk_col(ci + 1) < n_size) load_xold(ci + 1, xo[(ci + 1) & 1]);
-          ptx::tmem_ld_wait();
-          float f[32];
-          epilogue_math<KIND, 0>(va, bias, ncol0 + cc, N, f);
-          stage_row_f32(box, lane, f);
-          __syncwarp();
-          float* sp = lp + cc;
-          __nv_bfloat16* sb = lb + cc;
-#pragma unroll
-          for (int it = 0; it < 8; ++it, sp += rowstep, sb += rowstep) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(rd_base + it * 512 + ((it & 1) ? rd_sw1 : rd_sw0)));
-            const float4 o = xo[ci & 1][it];
-            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            s1[it] += (v.x + v.y) + (v.z + v.w);
-            s2[it] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[it]))));
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<float4*>(sp) = v;
-            *reinterpret_cast<uint2*>(sb) = pk;
-          }
-          __syncwarp();  // every lane is done reading the box before the next chunk is staged
-        }
-        // per-row partial statistics: sum over the 8 lanes that share a row, fixed order
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-#pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            s1[it] += __shfl_xor_sync(0xffffffffu, s1[it], o);
-            s2[it] += __shfl_xor_sync(0xffffffffu, s2[it], o);
-          }
-          if (c4 == 0) ln.stats_out[(2 * n_blk + half) * ln.stats_ld + row0 + 4 * it + rs] = make_float2(s1[it], s2[it]);
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
-          else ptx::mbar_arrive_cluster(leader_tempty0 + 8u * acc);
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        item_base += (uint32_t)(4 * ng);
         continue;
       }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
@@ -644,7 +623,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if constexpr (EPI == 6) asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) ptx::bulk_wait_all();  // every output tile has landed before the CTA retires
     __syncwarp();
   }
@@ -702,7 +680,8 @@ struct GemmMaps {
 };
 
 template <int CG, int KIND, int EPI>
-int launch_one(const GemmMaps& tm, const float* bias, int64_t M, int N, int K, int bn, const GemmLn& ln, cudaStream_t s) {
+int launch_one(const GemmMaps& tm, const float* bias, int64_t M, int N, int K, const TileSplit& ts, const GemmLn& ln,
+               cudaStream_t s) {
   using C = Cfg<CG, EPI, KIND>;
   auto kern = gemm_tcgen05_kernel<CG, KIND, EPI>;
   // per instantiation and device (function attributes live in the device's context); a benign race: two threads may both set it
@@ -713,9 +692,8 @@ int launch_one(const GemmMaps& tm, const float* bias, int64_t M, int N, int K, i
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
   }
-  const int n_tiles = (N + bn - 1) / bn;
   const int64_t m_tiles = ceil_div(M, (int64_t)BM * CG);
-  const int64_t total = m_tiles * n_tiles;
+  const int64_t total = m_tiles * ts.T;
   const int64_t max_groups = kNumSMs / CG;
   const unsigned groups = (unsigned)(total < max_groups ? total : max_groups);
   cudaLaunchConfig_t cfg{};
@@ -730,12 +708,12 @@ int launch_one(const GemmMaps& tm, const float* bias, int64_t M, int N, int K, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.y, tm.a2, tm.b2, tm.y2, bias, M, N, K, bn, ln));
+  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.y, tm.a2, tm.b2, tm.y2, bias, M, N, K, ts, ln));
   return MPL_OK;
 }
 
 template <int CG, int KIND>
-int launch_epi(int epi, const GemmMaps& tm, const float* bias, int64_t M, int N, int K, int bn, const GemmLn& ln,
+int launch_epi(int epi, const GemmMaps& tm, const float* bias, int64_t M, int N, int K, const TileSplit& bn, const GemmLn& ln,
                cudaStream_t s) {
   switch (epi) {
     case 0: return launch_one<CG, KIND, 0>(tm, bias, M, N, K, bn, ln, s);
@@ -757,24 +735,16 @@ int launch_epi(int epi, const GemmMaps& tm, const float* bias, int64_t M, int N,
   return MPL_ERR_UNSUPPORTED;
 }
 
-// Output-tile width.  Interior tiles must be multiples of 64 columns (the epilogue stores 64-column groups).  Wide tiles
-// win: measured on B200, N = 1088 as 4 x 256 + 64 beats 5 x 192 + 128 by 8 % (fewer re-reads of A per output column),
-// so 256 is kept unless the tail would be narrower than 64 columns (N = 544 -> 192 + 192 + 160 instead of 256 + 256 + 32).
-int pick_tile_n(int N, bool out32 = false) {
-  if (out32 && N > 256) {
-    // fp32-output epilogues work in 32-column chunks: balance the tiles instead of leaving a narrow tail
-    // (N = 1088: 4 x 224 + 192 instead of 4 x 256 + 64 -- the 64-wide tile costs far more than a quarter tile;
-    // measured: fc2 17.1 -> 15.5 ms, proj 12.0 -> 11.8 ms per step)
-    const int n_tiles = (N + 255) / 256;
-    return ((N + n_tiles - 1) / n_tiles + 31) / 32 * 32;
-  }
-  const int rem = N % 256;
-  if (rem == 0 || rem >= 64) return 256;
-  for (int bn : {192, 128}) {
-    const int r = N % bn;
-    if (r == 0 || r >= 64) return bn;
-  }
-  return 256;
+// Output tiles: whole 64-column groups dealt evenly to ceil(groups / 4) tiles of at most 256 columns (see TileSplit).
+// Measured on B200 before the even split existed: N = 1088 as 4 x 256 + 64 beat 5 x 192 + 128 by 8 % (fewer re-reads of A
+// per output column) and 4 x 224 + 192 beat 4 x 256 + 64 by another 9 % (no narrow tail tile) -- the even split has both.
+TileSplit split_tiles(int N) {
+  const int G = (N + 63) / 64;
+  TileSplit ts;
+  ts.T = (G + 3) / 4;
+  ts.q = G / ts.T;
+  ts.r = G % ts.T;
+  return ts;
 }
 
 }  // namespace
@@ -784,7 +754,7 @@ bool gemm_tcgen05_supports(int N, int K, int dtype) {
   return N >= 16 && N % 16 == 0 && K >= 1 && ((int64_t)K * 2) % 16 == 0;
 }
 
-int gemm_ln_slots(int N) { return 2 * ((N + pick_tile_n(N, true) - 1) / pick_tile_n(N, true)); }
+int gemm_ln_slots(int N) { return 2 * split_tiles(N).T; }
 
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
                         int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* lnargs, int cta_group) {
@@ -798,16 +768,14 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
     ln.colsum = lnargs->colsum;
     ln.stats_in = reinterpret_cast<const float2*>(lnargs->stats_in);
     ln.stats_out = reinterpret_cast<float2*>(lnargs->stats_out);
-    ln.xb = reinterpret_cast<__nv_bfloat16*>(lnargs->xb);
-    ln.y_raw = reinterpret_cast<float*>(Y);
     ln.slots_in = lnargs->slots_in;
     ln.stats_ld = (int64_t)align_up((size_t)M, 256);
     ln.slots_out = gemm_ln_slots(N);
     ln.inv_k = 1.0f / (float)K;
     ln.eps = lnargs->eps;
     ln.flags = (lnargs->ab_fp16 ? 2 : 0) | (lnargs->out_fp16 ? 4 : 0);
-    if (epilogue == EPI_RESIDUAL_EMIT && (N % 32 != 0 || ln.stats_out == nullptr || ln.xb == nullptr)) {
-      set_error("launch_gemm_tcgen05: residual-emit epilogue needs N %% 32 == 0, a statistics buffer and a bf16 copy buffer");
+    if (epilogue == EPI_RESIDUAL_EMIT && (N % 16 != 0 || ln.stats_out == nullptr || lnargs->x_lo == nullptr)) {
+      set_error("launch_gemm_tcgen05: residual-emit epilogue needs N %% 16 == 0, a statistics buffer and the lo plane of the residual");
       return MPL_ERR_INVALID_ARGUMENT;
     }
     if (epilogue != EPI_RESIDUAL_EMIT && (ln.colsum == nullptr || ln.stats_in == nullptr || ln.slots_in < 1)) {
@@ -832,27 +800,31 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
   int epi = epilogue;
   if (epilogue == EPI_BIAS && out_fp32) epi = 3;
   // output boxes: 32 rows x 128 bytes (64 bf16 or 32 fp32 columns), 128B swizzle like the staging writes
-  const bool out_bf16 = epi == 0 || epi == 1 || epi == 4 || epi == 5;
-  // residual-emit: short K (proj) is epilogue-bound -> shared-memory prefetch ring on a 4-stage operand ring (EPI 6);
-  // long K (fc2) hides the epilogue behind the main loop -> register prefetch, all 6 stages (EPI 7)
+  // residual-emit: short K (proj) is epilogue / HBM bound -> 4 operand stages + 12 residual slots (EPI 6);
+  // long K (fc2) is MMA bound -> 5 stages + 8 slots (EPI 7)
   if (epi == 6 && K > 1536) epi = 7;
-  const int bn = pick_tile_n(N, epi == 2 || epi == 6 || epi == 7);  // EPI 0 / 1 / 3 store through 64-column steps: keep 64-multiples
+  const bool resid = epi == 6 || epi == 7;
+  const bool out_bf16 = epi == 0 || epi == 1 || epi == 4 || epi == 5 || resid;
+  const TileSplit ts = split_tiles(N);
+  const int wide_rows = 64 * (ts.q + (ts.r > 0 ? 1 : 0)) / cg, narrow_rows = 64 * ts.q / cg;
   GemmMaps tm;
   MPL_TRY(make_tmap(&tm.a, A, M, K, 2, BM));
-  MPL_TRY(make_tmap(&tm.b, W, N, K, 2, bn / cg));
+  MPL_TRY(make_tmap(&tm.b, W, N, K, 2, wide_rows));
   MPL_TRY(make_tmap(&tm.y, Y, M, N, out_bf16 ? 2 : 4, 32, out_bf16 ? 64 : 32));
+  tm.a2 = tm.a;
+  tm.y2 = tm.y;
   if (split) {
     MPL_TRY(make_tmap(&tm.a2, reinterpret_cast<const __nv_bfloat16*>(A) + M * (int64_t)K, M, K, 2, BM));
-    MPL_TRY(make_tmap(&tm.b2, reinterpret_cast<const __nv_bfloat16*>(W) + (int64_t)N * K, N, K, 2, bn / cg));
+    MPL_TRY(make_tmap(&tm.b2, reinterpret_cast<const __nv_bfloat16*>(W) + (int64_t)N * K, N, K, 2, wide_rows));
     if (out_bf16) MPL_TRY(make_tmap(&tm.y2, reinterpret_cast<__nv_bfloat16*>(Y) + M * (int64_t)N, M, N, 2, 32, 64));
-    else tm.y2 = tm.y;
   } else {
-    tm.a2 = tm.a; tm.b2 = tm.b; tm.y2 = tm.y;
+    MPL_TRY(make_tmap(&tm.b2, W, N, K, 2, narrow_rows));  // the W box of the narrow tiles
+    if (resid) MPL_TRY(make_tmap(&tm.y2, lnargs->x_lo, M, N, 2, 32, 64));  // Y = the hi plane, x_lo = the lo plane
   }
   if (cg == 1) {
-    return split ? launch_epi<1, 1>(epi, tm, bias, M, N, K, bn, ln, s) : launch_epi<1, 0>(epi, tm, bias, M, N, K, bn, ln, s);
+    return split ? launch_epi<1, 1>(epi, tm, bias, M, N, K, ts, ln, s) : launch_epi<1, 0>(epi, tm, bias, M, N, K, ts, ln, s);
   }
-  return split ? launch_epi<2, 1>(epi, tm, bias, M, N, K, bn, ln, s) : launch_epi<2, 0>(epi, tm, bias, M, N, K, bn, ln, s);
+  return split ? launch_epi<2, 1>(epi, tm, bias, M, N, K, ts, ln, s) : launch_epi<2, 0>(epi, tm, bias, M, N, K, ts, ln, s);
 }
 
 }  // namespace mpl

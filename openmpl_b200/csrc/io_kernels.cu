@@ -6,6 +6,8 @@
 
 #include <algorithm>
 
+#include <atomic>
+
 #include "kernels.cuh"
 
 namespace mpl {
@@ -167,7 +169,8 @@ __global__ void __launch_bounds__(256) token_build_vec_kernel(const TokenArgs a)
 __device__ __forceinline__ float2 f2(float v) { return make_float2(v, v); }
 
 // NK: slots of two segments (ceil(S / 2) <= NK); SS: segment stride in floats, 0 = a.seg_stride; ST: S, 0 = a.E / 32
-template <int NK, int SS, int ST>
+// PL: the token rows come as two bf16 planes (hi + lo, LayerNorm-fused bf16 mode): two 4-byte loads instead of one 8-byte one
+template <int NK, int SS, int ST, bool PL>
 __device__ __forceinline__ void head_pool_pose(const HeadArgs& a, int64_t b, int lane, float2 (&p)[NK]) {
   const int S = ST ? ST : (a.E >> 5), hi = lane >> 4;
   const int stride = SS ? SS : a.seg_stride;
@@ -186,9 +189,23 @@ __device__ __forceinline__ void head_pool_pose(const HeadArgs& a, int64_t b, int
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       // a view past V re-reads view V - 1 and is dropped by its zero weight below
-      const float* r = a.tok + (b * a.V + min(v0 + u, a.V - 1)) * (int64_t)a.tok_w + col0;
+      const int64_t roff = (b * a.V + min(v0 + u, a.V - 1)) * (int64_t)a.tok_w + col0;
+      if constexpr (PL) {
 #pragma unroll
-      for (int k = 0; k < NK; ++k) x[u][k] = ok[k] ? *reinterpret_cast<const float2*>(r + 2 * k * stride) : f2(0.f);
+        for (int k = 0; k < NK; ++k) {
+          x[u][k] = f2(0.f);
+          if (ok[k]) {
+            const uint32_t h = *reinterpret_cast<const uint32_t*>(a.tok_hi + roff + 2 * k * stride);
+            const uint32_t l = *reinterpret_cast<const uint32_t*>(a.tok_lo + roff + 2 * k * stride);
+            x[u][k] = make_float2(__uint_as_float(h << 16) + __uint_as_float(l << 16),
+                                  __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u));
+          }
+        }
+      } else {
+        const float* r = a.tok + roff;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) x[u][k] = ok[k] ? *reinterpret_cast<const float2*>(r + 2 * k * stride) : f2(0.f);
+      }
     }
     float m[4], rs[4];
 #pragma unroll
@@ -280,7 +297,7 @@ __device__ __forceinline__ void mma_f16_acc(float (&c)[4], const uint32_t (&a)[4
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int NK, int SS, int ST>
+template <int NK, int SS, int ST, bool PL>
 __global__ void __launch_bounds__(HEAD_WARPS * 32, 2) head_block_kernel(const HeadArgs a) {
   extern __shared__ __align__(16) float hsm[];  // pool [HEAD_PB][pitch]; reused as partial [HEAD_WARPS][HEAD_PB][64]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, 2) head_block_kernel(const He
     for (int pi = 0; pi < 2; ++pi) {
       const int p0 = warp * 2 + pi;
       float2 pp[NK];
-      head_pool_pose<NK, SS, ST>(a, min(b0 + p0, a.B - 1), lane, pp);
+      head_pool_pose<NK, SS, ST, PL>(a, min(b0 + p0, a.B - 1), lane, pp);
 #pragma unroll
       for (int k = 0; k < NK; ++k)
         if (2 * k + (lane >> 4) < S) *reinterpret_cast<float2*>(hsm + p0 * pitch + ch0 + 64 * k) = pp[k];
@@ -405,28 +422,37 @@ int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s) {
   return MPL_OK;
 }
 
+bool head_warp_supports(const HeadArgs& a) {
+  if (a.E > 32 * 18 || a.E % 32 != 0 || a.out_dim > 64 || !(a.seg_len == 32 || a.seg_len == a.E)) return false;
+  const int stride = a.seg_len == a.E ? 32 : a.seg_stride;
+  return a.tok_w % 2 == 0 && stride % 2 == 0;
+}
+
 int try_launch_head_warp(const HeadArgs& a, cudaStream_t s) {
-  if (a.E > 32 * 18 || a.E % 32 != 0 || a.out_dim > 64 || a.hwT == nullptr || !(a.seg_len == 32 || a.seg_len == a.E)) return 1;
+  if (!head_warp_supports(a) || a.hwT == nullptr) return 1;
   const int stride = a.seg_len == a.E ? 32 : a.seg_stride;  // contiguous row: segment i starts at column 32 i
   auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
-  if (!aligned8(a.tok) || a.tok_w % 2 != 0 || stride % 2 != 0 || !aligned8(a.vn_w) || !aligned8(a.vn_b) || !aligned8(a.hn_w) ||
-      !aligned8(a.hn_b))
+  const bool planes = a.tok_hi != nullptr;
+  if ((planes ? (!aligned8(a.tok_hi) || !aligned8(a.tok_lo)) : !aligned8(a.tok)) || a.tok_w % 2 != 0 || stride % 2 != 0 ||
+      !aligned8(a.vn_w) || !aligned8(a.vn_b) || !aligned8(a.hn_w) || !aligned8(a.hn_b))
     return 1;
   if (a.B == 0) return MPL_OK;
   const int64_t blocks = std::min<int64_t>(ceil_div(a.B, HEAD_PB), (int64_t)kNumSMs * 2);
   const size_t smem = std::max((size_t)(a.E + 8) * HEAD_PB, (size_t)HEAD_WARPS * HEAD_PB * 64) * sizeof(float);
-  static bool attr_set[64][4] = {};
+  static std::atomic<unsigned char> attr_set[64][8];  // per device and instantiation; setting an attribute twice is harmless
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
   // the shipped width (17 segments; ray-stripped or contiguous rows) with everything compiled in, else runtime
-  // stride / segment count with 9 slots (up to 18 segments) or 5 (up to 10)
-  const int which = a.E == 32 * 17 && stride == 64 ? 0 : (a.E == 32 * 17 && stride == 32 ? 1 : (a.E > 32 * 10 ? 2 : 3));
-  void (*const kerns[4])(const HeadArgs) = {head_block_kernel<9, 64, 17>, head_block_kernel<9, 32, 17>, head_block_kernel<9, 0, 0>,
-                                            head_block_kernel<5, 0, 0>};
+  // stride / segment count with 9 slots (up to 18 segments) or 5 (up to 10); x2: fp32 rows or two bf16 planes
+  const int which = (a.E == 32 * 17 && stride == 64 ? 0 : (a.E == 32 * 17 && stride == 32 ? 1 : (a.E > 32 * 10 ? 2 : 3))) + (planes ? 4 : 0);
+  void (*const kerns[8])(const HeadArgs) = {head_block_kernel<9, 64, 17, false>, head_block_kernel<9, 32, 17, false>,
+                                            head_block_kernel<9, 0, 0, false>,   head_block_kernel<5, 0, 0, false>,
+                                            head_block_kernel<9, 64, 17, true>,  head_block_kernel<9, 32, 17, true>,
+                                            head_block_kernel<9, 0, 0, true>,    head_block_kernel<5, 0, 0, true>};
   auto kern = kerns[which];
-  if (dev < 0 || dev >= 64 || !attr_set[dev][which]) {
+  if (dev < 0 || dev >= 64 || !attr_set[dev][which].load(std::memory_order_acquire)) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (dev >= 0 && dev < 64) attr_set[dev][which] = true;
+    if (dev >= 0 && dev < 64) attr_set[dev][which].store(1, std::memory_order_release);
   }
   HeadArgs b = a;
   b.seg_stride = stride;

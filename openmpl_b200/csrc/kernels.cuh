@@ -61,9 +61,12 @@ int launch_layernorm_bf16(const float* x, int64_t ldx, const float* w, const flo
 int launch_layernorm_split(const float* x, int64_t ldx, const float* w, const float* b, float eps, __nv_bfloat16* y,
                            int64_t ldy, int64_t plane, int64_t rows, int C, cudaStream_t s);
 
-// entry of the LayerNorm-fused FPT: raw bf16 copy of the rows + (sum, sum^2) in statistics slot 0 of `slots`
-int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, int64_t ldb, void* stats, int slots, int64_t rows, int C,
-                   cudaStream_t s);
+// entry of the LayerNorm-fused FPT: the fp32 token rows as two bf16 planes (hi = bf16(x), lo = bf16(x - hi), row pitch ldb)
+// + their (sum, sum^2) in statistics slot 0 of `slots`
+int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo, int64_t ldb, void* stats, int slots,
+                   int64_t rows, int C, cudaStream_t s);
+// hi + lo planes -> fp32 (the heads that are not served by the plane-reading head kernel)
+int launch_join_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int64_t n, cudaStream_t s);
 // pack time: W' = bf16(W diag(gamma)), colsum = row sums of W', bias' = b + W beta
 int launch_ln_fold(const float* W, const float* b, const float* gamma, const float* beta, __nv_bfloat16* Wf, float* colsum,
                    float* bias_f, int N, int K, cudaStream_t s);
@@ -90,7 +93,9 @@ int launch_view_mean(const float* x, const float* w, const float* bias, float* y
 // ---- K5: fused head for the default head (multiview_mpl.py:425-446,517-523):
 //      strip ray channels -> View_norm -> view-weighted mean -> LayerNorm(1e-5) -> Linear(E -> 3J) ------------------
 struct HeadArgs {
-  const float* tok;  // [B, V, tok_w] fp32 residual stream after the FPT
+  const float* tok;  // [B, V, tok_w] fp32 residual stream after the FPT ...
+  const __nv_bfloat16* tok_hi;  // ... or (LayerNorm-fused bf16 mode) its two bf16 planes, same shape; tok is ignored when set
+  const __nv_bfloat16* tok_lo;
   int64_t B;
   int V, tok_w, E, seg_len, seg_stride, out_dim;
   const float* vn_w; const float* vn_b;  // View_norm
@@ -103,6 +108,7 @@ struct HeadArgs {
 };
 int launch_head_fused(const HeadArgs& a, cudaStream_t s);
 int try_launch_head_warp(const HeadArgs& a, cudaStream_t s);
+bool head_warp_supports(const HeadArgs& a);  // shape test of the K5 kernel (E, out_dim, seg_len, seg_stride, tok_w)
 int launch_head_transpose(const float* W, float* WT, int out_dim, int E, cudaStream_t s);
 
 // ---- pack helpers ---------------------------------------------------------------------------------------------------
@@ -116,16 +122,16 @@ int launch_to_split(const float* src, __nv_bfloat16* dst, int64_t n, int64_t pla
 // ---- tcgen05 projection GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
 enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESIDUAL = 2, EPI_LN_BIAS = 4, EPI_LN_BIAS_GELU = 5, EPI_RESIDUAL_EMIT = 6 };
 // LayerNorm fused around the bf16 projections (see gemm_tcgen05.cu):
-//   EPI_RESIDUAL_EMIT  Y(fp32) = Y + A W^T + bias, plus xb = bf16(Y) and per-row partial (sum, sum^2) into stats_out
-//                      [gemm_ln_slots(N)][M rounded up to 256] float2 (slot-major).  Y, xb and stats_out must be ALLOCATED for M rounded up to a
-//                      multiple of 256 rows (the epilogue reads and writes whole row tiles unpredicated), N % 32 == 0;
-//   EPI_LN_BIAS(_GELU) Y = act(rstd * (A W'^T - mu * colsum) + bias) with A = xb (raw residual rows), W' = W diag(gamma),
+//   EPI_RESIDUAL_EMIT  the residual stream x [M, N] is two bf16 planes, hi = Y and lo = x_lo (x ~ hi + lo): x += A W^T + bias in
+//                      place on both planes (TMA in, TMA out), plus per-row partial (sum, sum^2) of the new x into stats_out
+//                      [gemm_ln_slots(N)][M rounded up to 256] float2 (slot-major; rows past M are scratch).  N % 16 == 0;
+//   EPI_LN_BIAS(_GELU) Y = act(rstd * (A W'^T - mu * colsum) + bias) with A = the hi plane (raw residual rows), W' = W diag(gamma),
 //                      bias = b + W beta, (mu, rstd) from stats_in [slots_in][M rounded up to 256].
 struct GemmLnArgs {
   const float* colsum;
   const void* stats_in;
   void* stats_out;
-  void* xb;
+  void* x_lo;
   int slots_in;
   float eps;
   int ab_fp16;   // A and W hold fp16 (not bf16) values

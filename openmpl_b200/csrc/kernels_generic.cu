@@ -292,12 +292,13 @@ int launch_layernorm_split(const float* x, int64_t ldx, const float* w, const fl
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Entry of the LayerNorm-fused FPT (bf16 mode): the residual rows as a raw bf16 copy + their (sum, sum of squares) in
-// statistics slot 0 (the other slots zeroed) -- what the residual-emit GEMM epilogue produces for every later block.
+// Entry of the LayerNorm-fused FPT (bf16 mode): the residual rows as two bf16 planes (hi, lo) + their (sum, sum of squares)
+// in statistics slot 0 (the other slots zeroed) -- what the residual-emit GEMM epilogue produces for every later block.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MAXV4>
 __global__ void __launch_bounds__(256) ln_prep_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ xb,
-                                                      int64_t ldb, float2* __restrict__ stats, int slots, int64_t rows, int C) {
+                                                      __nv_bfloat16* __restrict__ xl, int64_t ldb, float2* __restrict__ stats,
+                                                      int slots, int64_t rows, int C) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -311,11 +312,7 @@ __global__ void __launch_bounds__(256) ln_prep_kernel(const float* __restrict__ 
       const float4 v = xr[e4];
       s += (v.x + v.y) + (v.z + v.w);
       q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      reinterpret_cast<uint2*>(xb + row * ldb)[e4] = pk;
+      store_split4(xb + row * ldb + 4 * e4, xl - xb, v.x, v.y, v.z, v.w);
     }
   }
   s = warp_sum(s);
@@ -324,8 +321,8 @@ __global__ void __launch_bounds__(256) ln_prep_kernel(const float* __restrict__ 
   for (int i = lane; i < slots; i += 32) stats[i * ld + row] = (i == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
 }
 
-int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, int64_t ldb, void* stats, int slots, int64_t rows, int C,
-                   cudaStream_t s) {
+int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, __nv_bfloat16* xl, int64_t ldb, void* stats, int slots,
+                   int64_t rows, int C, cudaStream_t s) {
   if (rows == 0) return MPL_OK;
   if (C % 4 != 0 || ldx % 4 != 0 || ldb % 4 != 0 || C > 32 * 4 * 17) {
     set_error("launch_ln_prep: width %d is not supported", C);
@@ -333,9 +330,9 @@ int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, int64_t ldb, 
   }
   const unsigned grid = (unsigned)ceil_div(rows, 8);
   float2* st = reinterpret_cast<float2*>(stats);
-  if (C <= 32 * 4 * 5) ln_prep_kernel<5><<<grid, 256, 0, s>>>(x, ldx, xb, ldb, st, slots, rows, C);
-  else if (C <= 32 * 4 * 9) ln_prep_kernel<9><<<grid, 256, 0, s>>>(x, ldx, xb, ldb, st, slots, rows, C);
-  else ln_prep_kernel<17><<<grid, 256, 0, s>>>(x, ldx, xb, ldb, st, slots, rows, C);
+  if (C <= 32 * 4 * 5) ln_prep_kernel<5><<<grid, 256, 0, s>>>(x, ldx, xb, xl, ldb, st, slots, rows, C);
+  else if (C <= 32 * 4 * 9) ln_prep_kernel<9><<<grid, 256, 0, s>>>(x, ldx, xb, xl, ldb, st, slots, rows, C);
+  else ln_prep_kernel<17><<<grid, 256, 0, s>>>(x, ldx, xb, xl, ldb, st, slots, rows, C);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
@@ -1096,6 +1093,17 @@ __global__ void to_f16_kernel(const float* src, __half* dst, int64_t n) {
 int launch_to_f16(const float* src, void* dst, int64_t n, cudaStream_t s) {
   if (n == 0) return MPL_OK;
   to_f16_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+__global__ void join_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                   float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+int launch_join_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return MPL_OK;
+  join_planes_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(hi, lo, out, n);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

@@ -288,6 +288,7 @@ struct Workspace {
   float *xs, *xn, *qkv, *att, *hid, *conf;       // SPT, [V*Bc*J, .]
   float* tok;                                    // [Bc, V*tok_w] fp32 residual stream of the FPT
   void *fxn, *fqkv, *fatt, *fhid;                // FPT activations (fp32 / bf16 per precision)
+  void* fxl;                                     // LayerNorm-fused bf16 mode: lo plane of the residual stream (fxn = hi plane)
   void* fstats;                                  // [Bc*N, ln_slots] float2 row statistics (LayerNorm-fused bf16 mode)
   float *vn, *pooled, *hn, *h1, *h2, *cat;       // head
   size_t bytes;
@@ -311,14 +312,13 @@ static Workspace layout_workspace(const MplModel* m, int64_t Bc, uint8_t* base) 
     w.hid = (float*)take(Rs * m->spt_hidden * 4);
   }
   if (m->d.confidence_as_attention_uncertainty_weight) w.conf = (float*)take(Rs * 4);
-  // LayerNorm-fused mode: the residual-emit epilogue touches whole 256-row tiles -> rows padded (pad rows are scratch)
-  const int64_t tok_rows_pad = m->ln_fused ? (int64_t)align_up((size_t)(Bc * m->fpt_tokens), 256) * m->fpt_dim : 0;
-  w.tok = (float*)take(std::max<int64_t>(Bc * (int64_t)m->V * m->tok_w, tok_rows_pad) * 4);
+  w.tok = (float*)take(Bc * (int64_t)m->V * m->tok_w * 4);
   if (!m->d.no_transformer_fpt && !m->fpt_kp_fused) {
     const int64_t Rf = m->ln_fused ? (int64_t)align_up((size_t)(Bc * m->fpt_tokens), 256) : Bc * m->fpt_tokens;
     const int64_t D = m->fpt_dim, Hf = m->fpt_hidden;
     const int esz = (m->fpt_tc && m->d.precision == MPL_PREC_BF16) ? 2 : 4;
     w.fxn = take(Rf * D * esz);
+    if (m->ln_fused) w.fxl = take(Rf * D * 2);
     w.fqkv = take(Rf * 3 * D * esz);
     w.fatt = take(Rf * D * esz);
     w.fhid = take(Rf * Hf * esz);
@@ -431,29 +431,30 @@ static int block_f32(MplModel* m, bool fpt, const BlockW& w, float* x, int64_t r
 // MMA per k-step).  tf32-named mode = fp32-grade "split" arithmetic: every GEMM operand is a pair of bf16 planes (hi, lo) and
 // the tensor cores accumulate hi.hi + hi.lo + lo.hi (the producers -- LayerNorm, attention, the fc1 epilogue -- write planes).
 static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_t sets, int N, int C, int hidden, float scale,
-                    void* xn, void* qkv, void* att, void* hid, void* stats, cudaStream_t s) {
+                    void* xn, void* xl, void* qkv, void* att, void* hid, void* stats, cudaStream_t s) {
   const int prec = m->d.precision;
   const int hd = C / m->H;
   const int cg = m->cta_group;
   if (m->ln_fused) {
-    // xn holds the raw bf16 copy of x and `stats` its per-row (sum, sum^2) partials, both written by the previous
-    // residual-emit epilogue (or by launch_ln_prep before the first block): 5 launches per block, no LayerNorm kernel
+    // The residual stream lives in two bf16 planes: xn = hi (also the A operand of QKV / fc1), xl = lo; `stats` holds its
+    // per-row (sum, sum^2) partials.  All three are rewritten by every residual-emit epilogue (launch_ln_prep makes them from
+    // the fp32 tokens before the first block): 5 launches per block, no LayerNorm kernel, x (fp32) is not touched.
     GemmLnArgs app{};  // LayerNorm-apply side (QKV, fc1)
     app.stats_in = stats;
     app.slots_in = m->ln_slots;
     app.eps = 1e-6f;
     GemmLnArgs emit{};  // residual-emit side (proj, fc2)
     emit.stats_out = stats;
-    emit.xb = xn;
+    emit.x_lo = xl;
     app.colsum = w.qkv_cs;
     LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkv_bf, qkv, rows, 3 * C, C, prec, EPI_LN_BIAS, 0, s, &app, cg));
     LC(CAT_FPT_ATTN, launch_attention_bf16((const __nv_bfloat16*)qkv, (__nv_bfloat16*)att, sets, N, m->H, hd, scale, s));
-    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, x, rows, C, C, prec, EPI_RESIDUAL_EMIT, 1, s, &emit, cg));
+    LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, xn, rows, C, C, prec, EPI_RESIDUAL_EMIT, 0, s, &emit, cg));
     app.colsum = w.fc1_cs;
     app.out_fp16 = 1;   // hidden activations in fp16 (GELU in packed half2), fc2 runs kind::f16 on fp16 operands
     LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1_bf, hid, rows, hidden, C, prec, EPI_LN_BIAS_GELU, 0, s, &app, cg));
     emit.ab_fp16 = 1;
-    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, x, rows, C, hidden, prec, EPI_RESIDUAL_EMIT, 1, s, &emit, cg));
+    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, xn, rows, C, hidden, prec, EPI_RESIDUAL_EMIT, 0, s, &emit, cg));
     return MPL_OK;
   }
   if (prec == MPL_PREC_BF16) {
@@ -602,13 +603,13 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
     const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
     const int64_t rows = Bc * N;
     if (m->ln_fused)
-      LC(CAT_FPT_LN, launch_ln_prep(w.tok, D, (__nv_bfloat16*)w.fxn, D, w.fstats, m->ln_slots, rows, D, s));
+      LC(CAT_FPT_LN, launch_ln_prep(w.tok, D, (__nv_bfloat16*)w.fxn, (__nv_bfloat16*)w.fxl, D, w.fstats, m->ln_slots, rows, D, s));
     for (int ix = 0; ix < m->depth; ++ix) {
       const BlockW bw = block_weights(m, P, "blocks." + std::to_string(ix) + ".", m->fpt_tc);
       const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
       for (int r = 0; r < reps; ++r) {
         if (m->fpt_tc)
-          MPL_TRY(block_tc(m, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, w.fxn, w.fqkv, w.fatt, w.fhid, w.fstats, s));
+          MPL_TRY(block_tc(m, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, w.fxn, w.fxl, w.fqkv, w.fatt, w.fhid, w.fstats, s));
         else
           MPL_TRY(block_f32(m, true, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, nullptr, (float*)w.fxn, (float*)w.fqkv, (float*)w.fatt, (float*)w.fhid, s));
       }
@@ -619,9 +620,21 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   if (m->ray_layout == 1) { seg_len = dim; seg_stride = 2 * dim; }  // [J, 2d] -> first d of every joint slot
   const int out_dim = 3 * J;
   const bool fused_head = !d.linear_weighted_mean && !d.deep_head && !d.head_kadkhod;
+  // LayerNorm-fused mode: the FPT left the residual stream in two bf16 planes.  The K5 head kernel reads them directly; every
+  // other head takes the fp32 token buffer, refilled from the planes first.
+  const bool planes = m->ln_fused && !d.no_transformer_fpt && m->depth > 0 && !m->fpt_kp_fused;
+  bool head_planes = false;
+  if (planes) {
+    HeadArgs probe{};
+    probe.E = E; probe.out_dim = out_dim; probe.seg_len = seg_len; probe.seg_stride = seg_stride; probe.tok_w = m->tok_w;
+    head_planes = fused_head && m->dindex.count("headT") && head_warp_supports(probe);
+    if (!head_planes)
+      LC(CAT_HEAD, launch_join_planes((const __nv_bfloat16*)w.fxn, (const __nv_bfloat16*)w.fxl, w.tok, Bc * (int64_t)V * m->tok_w, s));
+  }
   if (fused_head) {
     HeadArgs ha{};
-    ha.tok = w.tok; ha.B = Bc; ha.V = V; ha.tok_w = m->tok_w; ha.E = E; ha.seg_len = seg_len; ha.seg_stride = seg_stride;
+    ha.tok = w.tok;
+    if (head_planes) { ha.tok_hi = (const __nv_bfloat16*)w.fxn; ha.tok_lo = (const __nv_bfloat16*)w.fxl; } ha.B = Bc; ha.V = V; ha.tok_w = m->tok_w; ha.E = E; ha.seg_len = seg_len; ha.seg_stride = seg_stride;
     ha.out_dim = out_dim;
     ha.vn_w = P.f("View_norm.weight"); ha.vn_b = P.f("View_norm.bias");
     ha.wm_w = P.f("weighted_mean.weight"); ha.wm_b = P.f("weighted_mean.bias");
@@ -1070,5 +1083,25 @@ int mpl_test_gemm(const void* A, const void* W, const float* bias, void* Y, int6
                              cta_group);
   MPL_API_END
 }
+
+/* The LayerNorm-fused epilogues of the same kernel in isolation (tests/test_gemm_ln_gpu.py). */
+int mpl_test_gemm_ln(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int epilogue,
+                     const float* colsum, const void* stats_in, int slots_in, void* stats_out, void* x_lo, float eps,
+                     int ab_fp16, int out_fp16, int cta_group, mpl_stream_t stream) {
+  MPL_API_BEGIN
+  GemmLnArgs a{};
+  a.colsum = colsum;
+  a.stats_in = stats_in;
+  a.slots_in = slots_in;
+  a.stats_out = stats_out;
+  a.x_lo = x_lo;
+  a.eps = eps;
+  a.ab_fp16 = ab_fp16;
+  a.out_fp16 = out_fp16;
+  return launch_gemm_tcgen05(A, W, bias, Y, M, N, K, MPL_PREC_BF16, epilogue, 0, reinterpret_cast<cudaStream_t>(stream), &a,
+                             cta_group);
+  MPL_API_END
+}
+int mpl_test_gemm_ln_slots(int N) { return gemm_ln_slots(N); }
 
 }  // extern "C"
