@@ -157,10 +157,13 @@ int mpl_profile_collect(MplModel* m, double* ms_per_category, int64_t* launches_
  *   acc layout (doubles): [0,J) sum_b ||pred-gt|| per joint (absolute); [J,2J) same, root-relative;
  *   [2J,5J) sum_b |pred-gt| per joint-dim over unmasked entries (absolute); [5J,8J) same, root-relative;
  *   [8J,11J) unmasked count per joint-dim; [11J] pose count.
- *   conf3d may be NULL (no masking); unit_scale = 100 if OUTPUT_IN_METER else 1. */
+ *   conf3d may be NULL (no masking); unit_scale = 100 if OUTPUT_IN_METER else 1.
+ *   room_affine: NULL, or a HOST array of 6 floats (scale x, y, z, offset x, y, z): the un-scaling validate() applies to the
+ *   predictions and targets of room-normalised datasets before it stores them (function_mpl.py:476-488), v * scale + offset in
+ *   fp32: (s, s, s, centre) for 'room_scaled_equal', (sx, sy, 1, 0, 0, 0) otherwise. */
 #define MPL_METRIC_ACC_LEN(J) (11 * (J) + 1)
 int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t batch, int num_joints,
-                         float unit_scale, double* acc, mpl_stream_t stream);
+                         float unit_scale, const float* room_affine, double* acc, mpl_stream_t stream);
 
 /* Procrustes-aligned error (P-MPJPE) as running fp64 sums: per pose, PoseUtils.procrustes(A = gt, B = pred)
  * (MPL/lib/utils/pose_utils.py:61-143) after the unit rule above, then the per-joint distances of calc_mpjpe between the

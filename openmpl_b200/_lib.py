@@ -105,7 +105,7 @@ def lib():
                                   c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]
         L.mpl_last_launch_count.argtypes = [c_void_p]
         L.mpl_last_launch_count.restype = c_int64
-        L.mpl_mpjpe_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]
+        L.mpl_mpjpe_accumulate.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, POINTER(c_float), c_void_p, c_void_p]
         L.mpl_pmpjpe_accumulate.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p]
         L.mpl_build_inputs.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         L.mpl_test_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,

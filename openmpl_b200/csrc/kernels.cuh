@@ -171,8 +171,9 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
 int launch_fpt_kp_fused(float* tok, const void* wpack, int V, int64_t B, int depth, cudaStream_t s);
 
 // ---- metric + input builder -----------------------------------------------------------------------------------------
+// room_affine: host pointer to 6 floats (scale xyz, offset xyz) or null -- the room un-scaling of function_mpl.py:476-488
 int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t B, int J, float unit_scale,
-                            double* acc, cudaStream_t s);
+                            const float* room_affine, double* acc, cudaStream_t s);
 int launch_pmpjpe_accumulate(const float* pred, const float* gt, int64_t B, int J, float unit_scale, int scaling,
                              int reflection, double* acc, cudaStream_t s);
 int launch_build_inputs(const float* pix, const double* calib, int64_t B, int V, int J, float* poses, float* rays,

@@ -13,9 +13,16 @@ namespace mpl {
 //   [5J,8J)    same, root-relative
 //   [8J,11J)   unmasked count per joint-dim
 //   [11J]      pose count
+// room: the un-scaling validate() applies to predictions and targets of room-normalised datasets before storing them
+// (function_mpl.py:476-488): v * scale + centre per coordinate, in fp32 like the numpy arrays it works on (identity when unused)
+struct RoomAffine {
+  float scale[3], offset[3];
+  int live;
+};
+
 __global__ void __launch_bounds__(256) mpjpe_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                     const float* __restrict__ conf, int64_t B, int J, float unit,
-                                                    double* __restrict__ acc) {
+                                                    const RoomAffine room, double* __restrict__ acc) {
   extern __shared__ double sacc[];  // 11 J + 1
   const int L = 11 * J + 1;
   for (int i = threadIdx.x; i < L; i += blockDim.x) sacc[i] = 0.0;
@@ -39,9 +46,16 @@ __global__ void __launch_bounds__(256) mpjpe_kernel(const float* __restrict__ pr
       for (int k = 0; k < 3; ++k) {
         const bool ok = conf == nullptr || conf[(b * J + j) * 3 + k] > 0.f;
         const bool root_ok = conf == nullptr || conf[b * J * 3 + k] > 0.f;
-        const double pk = (double)p[k] * unit, gk = (double)g[k] * unit;
+        float pf = p[k], gf = g[k], p0f = p0[k], g0f = g0[k];
+        if (room.live) {
+          pf = __fadd_rn(__fmul_rn(pf, room.scale[k]), room.offset[k]);
+          gf = __fadd_rn(__fmul_rn(gf, room.scale[k]), room.offset[k]);
+          p0f = __fadd_rn(__fmul_rn(p0f, room.scale[k]), room.offset[k]);
+          g0f = __fadd_rn(__fmul_rn(g0f, room.scale[k]), room.offset[k]);
+        }
+        const double pk = (double)pf * unit, gk = (double)gf * unit;
         const double da = pk - gk;
-        const double dr = (pk - (double)p0[k] * unit) - (gk - (double)g0[k] * unit);
+        const double dr = (pk - (double)p0f * unit) - (gk - (double)g0f * unit);
         if (ok) {
           sa = fma(da, da, sa);
           d_abs[k] += fabs(da);
@@ -71,11 +85,16 @@ __global__ void __launch_bounds__(256) mpjpe_kernel(const float* __restrict__ pr
 }
 
 int launch_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t B, int J, float unit_scale,
-                            double* acc, cudaStream_t s) {
+                            const float* room_affine, double* acc, cudaStream_t s) {
   if (B == 0) return MPL_OK;
+  RoomAffine room{};
+  if (room_affine != nullptr) {
+    for (int k = 0; k < 3; ++k) { room.scale[k] = room_affine[k]; room.offset[k] = room_affine[3 + k]; }
+    room.live = 1;
+  }
   const int64_t want = ceil_div(B, 8 * 16);  // 8 warps per block, ~16 poses per warp
   const unsigned grid = (unsigned)(want < 1 ? 1 : (want > 8 * kNumSMs ? 8 * kNumSMs : want));
-  mpjpe_kernel<<<grid, 256, (size_t)(11 * J + 1) * sizeof(double), s>>>(pred, gt, conf3d, B, J, unit_scale, acc);
+  mpjpe_kernel<<<grid, 256, (size_t)(11 * J + 1) * sizeof(double), s>>>(pred, gt, conf3d, B, J, unit_scale, room, acc);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

@@ -1034,13 +1034,14 @@ int mpl_forward(MplModel* m, const void* packed, const float* const* poses, cons
 int64_t mpl_last_launch_count(const MplModel* m) { return m ? m->launches : 0; }
 
 int mpl_mpjpe_accumulate(const float* pred, const float* gt, const float* conf3d, int64_t batch, int num_joints,
-                         float unit_scale, double* acc, mpl_stream_t stream) {
+                         float unit_scale, const float* room_affine, double* acc, mpl_stream_t stream) {
   if (batch == 0 && acc != nullptr) return MPL_OK;
   if (pred == nullptr || gt == nullptr || acc == nullptr || batch < 0 || num_joints < 1) {
     set_error("mpl_mpjpe_accumulate: bad argument");
     return MPL_ERR_INVALID_ARGUMENT;
   }
-  return launch_mpjpe_accumulate(pred, gt, conf3d, batch, num_joints, unit_scale, acc, reinterpret_cast<cudaStream_t>(stream));
+  return launch_mpjpe_accumulate(pred, gt, conf3d, batch, num_joints, unit_scale, room_affine, acc,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mpl_pmpjpe_accumulate(const float* pred, const float* gt, int64_t batch, int num_joints, float unit_scale,

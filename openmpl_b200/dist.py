@@ -38,8 +38,14 @@ def shard_range(total: int, rank: int, world: int):
 def broadcast_state(module: torch.nn.Module, src: int = 0):
     """Optional: make every rank's replica bit-identical to rank `src` (one broadcast per tensor at init)."""
     if dist.is_initialized() and dist.get_world_size() > 1:
-        for t in list(module.parameters()) + list(module.buffers()):
-            dist.broadcast(t.data, src=src)
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t, src=src)
+        # the lifter keeps a packed device copy of its weights: tell it they changed (a collective writes in place without
+        # necessarily bumping Tensor._version)
+        for m in module.modules():
+            if hasattr(m, "invalidate"):
+                m.invalidate()
 
 
 def max_over_ranks(value: float, device=None) -> float:

@@ -25,9 +25,22 @@ class MpjpeAccumulator:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.acc = torch.zeros(acc_len(num_joints), dtype=torch.float64, device=self.device)
 
-    def update(self, pred: torch.Tensor, gt: torch.Tensor, conf3d: torch.Tensor | None = None):
-        """pred, gt: [B, J, 3] fp32 on the device; conf3d: None, [B, J], [B, J, 1] or [B, J, 3]."""
+    def update(self, pred: torch.Tensor, gt: torch.Tensor, conf3d: torch.Tensor | None = None, room: dict | None = None):
+        """pred, gt: [B, J, 3] fp32 on the device; conf3d: None, [B, J], [B, J, 1] or [B, J, 3] (the dataset's
+        `joints_3d_conf`, `function_mpl.py:489-490,682-684`).  room: the `meta` entries of a room-normalised dataset --
+        {'room_x_scale', 'room_center'} when 'room_scaled_equal', else {'room_x_scale', 'room_y_scale'} -- for the
+        un-scaling `validate()` applies before it stores predictions and targets (`function_mpl.py:476-488`)."""
         B = pred.shape[0]
+        affine = None
+        if room is not None:
+            if "room_center" in room:                     # 'room_scaled_equal': v * s + centre on every axis
+                s = float(room["room_x_scale"])
+                c = [float(x) for x in room["room_center"]]
+                vals = [s, s, s] + c
+            else:                                         # x and y scaled separately, z untouched
+                vals = [float(room["room_x_scale"]), float(room["room_y_scale"]), 1.0, 0.0, 0.0, 0.0]
+            import ctypes
+            affine = (ctypes.c_float * 6)(*vals)
         pred = pred.to(self.device, torch.float32).contiguous()
         gt = gt.to(self.device, torch.float32).contiguous()
         if conf3d is not None:
@@ -39,7 +52,7 @@ class MpjpeAccumulator:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             _lib.check(_lib.lib().mpl_mpjpe_accumulate(pred.data_ptr(), gt.data_ptr(),
                                                        conf3d.data_ptr() if conf3d is not None else None, B, self.J,
-                                                       self.unit, self.acc.data_ptr(), stream))
+                                                       self.unit, affine, self.acc.data_ptr(), stream))
 
     def all_reduce(self):
         """Sum the accumulators over all ranks (NCCL over NVLink on the GPU box; one call of `11 J + 1` doubles)."""

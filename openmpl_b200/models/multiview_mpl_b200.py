@@ -79,6 +79,10 @@ def _default_init(shape, kind, fan_in):
     raise ValueError(kind)
 
 
+def _invalidate_after_load(module, incompatible_keys):
+    module.invalidate()
+
+
 class MultiView_MPL(nn.Module):
     """Same keyword arguments and defaults as the reference constructor (multiview_mpl.py:95-117)."""
 
@@ -121,7 +125,10 @@ class MultiView_MPL(nn.Module):
         self._lock = threading.Lock()
         self._origin = [self]        # survives DataParallel's shallow replica copies: the module that owns the parameters
         self._chunk = None
+        self._epoch = [0]            # bumped by invalidate(); part of the packed-weights stamp (shared with replicas)
         self.last_launches = 0
+        # a loaded checkpoint always repacks, whatever path the copy took (utils.py:148-153 of the reference)
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
 
     # ---- handle / packing ------------------------------------------------------------------------------------------
     def _get_handle(self, index=None):
@@ -163,7 +170,7 @@ class MultiView_MPL(nn.Module):
         # The stamp is taken on the parameters of the ORIGINAL module: DataParallel re-broadcasts fresh copies to the
         # replicas on every call, which must not trigger a repack while the master's weights are unchanged.
         origin = self._origin[0]
-        stamp = tuple((t.data_ptr(), t._version) for t in (origin._tensor(n) for n in self._names))
+        stamp = (origin._epoch[0],) + tuple((t.data_ptr(), t._version) for t in (origin._tensor(n) for n in self._names))
         with self._lock:
             st = self._dev.get(device.index)
             if st is None or st["stamp"] != stamp:
@@ -180,6 +187,16 @@ class MultiView_MPL(nn.Module):
                 st = {"packed": packed, "stamp": stamp, "workspace": st["workspace"] if st else None}
                 self._dev[device.index] = st
             return st
+
+    def invalidate(self):
+        """Force a repack of the device-side weight blob at the next forward.
+
+        The packed blob is refreshed automatically when a parameter is replaced or modified through autograd-visible
+        in-place operations (`p.copy_()`, `load_state_dict`, optimizer steps: they bump `Tensor._version`).  Writes that
+        go through `p.data` (`p.data.copy_()`, `dist.broadcast(p.data)`, EMA updates on `.data`) bump nothing PyTorch
+        exposes -- call `invalidate()` after those.  `dist.broadcast_state` and `load_state_dict` already do."""
+        self._origin[0]._epoch[0] += 1
+        return self
 
     def set_chunk_poses(self, chunk: int):
         self._chunk = int(chunk)
@@ -218,6 +235,8 @@ class MultiView_MPL(nn.Module):
                 new.__dict__[k] = {}
             elif k == "_origin":
                 new.__dict__[k] = [new]
+            elif k == "_epoch":
+                new.__dict__[k] = [0]
             elif k == "_lock":
                 new.__dict__[k] = threading.Lock()
             else:

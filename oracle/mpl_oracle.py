@@ -239,6 +239,24 @@ def evaluate(pred, gt, output_in_meter=True, conf_3d=None, relative=False):
     return {"pjpe": pjpe, "mpjpe": mpjpe, "dist_per_dim_per_kp": dist_kp, "dist_per_dim": dist}
 
 
+def room_unscale(preds, gts, room):
+    """The un-scaling `validate()` applies to a batch before storing it (function_mpl.py:474-488), on fp32 arrays like
+    there.  room: {'room_x_scale', 'room_center'} ('room_scaled_equal') or {'room_x_scale', 'room_y_scale'}."""
+    preds = np.array(preds, dtype=np.float32)
+    gts = np.array(gts, dtype=np.float32)
+    if "room_center" in room:
+        room_scale = float(room["room_x_scale"])
+        room_center = np.asarray(room["room_center"], dtype=np.float32)
+        preds = preds * room_scale + room_center
+        gts = gts * room_scale + room_center
+    else:
+        preds[:, :, 0] = preds[:, :, 0] * float(room["room_x_scale"])
+        preds[:, :, 1] = preds[:, :, 1] * float(room["room_y_scale"])
+        gts[:, :, 0] = gts[:, :, 0] * float(room["room_x_scale"])
+        gts[:, :, 1] = gts[:, :, 1] * float(room["room_y_scale"])
+    return preds, gts
+
+
 def metric_sums(pred, gt, conf_3d=None, output_in_meter=True):
     """The running sums `mpl_mpjpe_accumulate` keeps (layout in include/mpl_b200.h), restated from evaluate() above:
     finalising them must reproduce evaluate(relative=False/True) exactly."""

@@ -43,6 +43,26 @@ def test_mpjpe_accumulator_matches_reference_metric(B, J, masked):
     np.testing.assert_allclose(np.nan_to_num(res["dist_rel"]), np.nan_to_num(r["dist_per_dim_per_kp"]), rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("equal", [True, False])
+def test_mpjpe_accumulator_room_unscaling_and_3d_confidence(equal):
+    """The tail of validate() for room-normalised datasets (function_mpl.py:476-490): predictions and targets are un-scaled
+    (v * s + centre, or x / y scaled separately) before the metric, joints with joints_3d_conf <= 0 are masked."""
+    rng = np.random.default_rng(11)
+    B, J = 300, 17
+    pred = rng.normal(size=(B, J, 3)).astype(np.float32)
+    gt = (pred + rng.normal(0, 0.05, size=(B, J, 3))).astype(np.float32)
+    conf = (rng.random((B, J)) > 0.1).astype(np.float32)
+    room = {"room_x_scale": 2.5, "room_center": [0.25, -0.5, 0.9]} if equal else {"room_x_scale": 2.5, "room_y_scale": 1.75}
+    acc = metric.MpjpeAccumulator(J, output_in_meter=True)
+    acc.update(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(conf).cuda(), room=room)
+    p2, g2 = mpl_oracle.room_unscale(pred, gt, room)
+    want = mpl_oracle.metric_sums(p2, g2, conf[:, :, None])
+    np.testing.assert_allclose(acc.acc.cpu().numpy(), want, rtol=1e-9, atol=1e-9)
+    plain = metric.MpjpeAccumulator(J, output_in_meter=True)
+    plain.update(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(conf).cuda())
+    assert abs(plain.result()["mpjpe_abs"] - acc.result()["mpjpe_abs"]) > 1e-3       # the un-scaling changes the metric
+
+
 PROCRUSTES_MODES = [(True, "best"), (False, "best"), (True, False), (True, True)]
 
 

@@ -210,3 +210,30 @@ def test_procrustes_invariances_random():
         np.testing.assert_allclose(Z, Z2, atol=1e-9)
         dr, Zr, tr = mpl_oracle.procrustes(A, B, scaling=False)          # rigid: scale reported as 1, residual larger
         assert tr["scale"] == 1 and ((Zr - A) ** 2).sum() >= ((Z - A) ** 2).sum() - 1e-10
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not mounted (GPU box)")
+@pytest.mark.parametrize("equal", [True, False])
+def test_room_unscaling_is_the_reference_validate_tail(equal):
+    """`oracle.room_unscale` against the reference's own statements: lines 474-488 of MPL/lib/core/function_mpl.py are read
+    from the checkout and executed verbatim on a synthetic batch (the module itself cannot be imported: h5py / wandb)."""
+    import textwrap
+    import torch
+    src = open(os.path.join(ref_loader.REF_ROOT, "MPL/lib/core/function_mpl.py")).read().splitlines()
+    snippet = textwrap.dedent("\n".join(src[473:488]))
+    assert snippet.startswith("preds = output.clone().cpu().numpy()") and "room_y_scale" in snippet
+    rng = np.random.default_rng(3)
+    out = rng.normal(size=(9, 17, 3)).astype(np.float32)
+    tgt = rng.normal(size=(9, 17, 3)).astype(np.float32)
+    meta0 = {"room_scaled": torch.ones(9), "room_x_scale": torch.full((9,), 3.25, dtype=torch.float64),
+             "room_y_scale": torch.full((9,), 1.75, dtype=torch.float64)}
+    room = {"room_x_scale": 3.25, "room_y_scale": 1.75}
+    if equal:
+        meta0["room_scaled_equal"] = torch.ones(9)
+        meta0["room_center"] = torch.tensor([[0.5, -0.25, 0.9]] * 9, dtype=torch.float32)
+        room = {"room_x_scale": 3.25, "room_center": [0.5, -0.25, 0.9]}
+    env = {"output": torch.from_numpy(out), "t": torch.from_numpy(tgt), "meta": [meta0]}
+    exec(snippet, env)
+    p, g = mpl_oracle.room_unscale(out, tgt, room)
+    np.testing.assert_array_equal(p, env["preds"])
+    np.testing.assert_array_equal(g, env["gts"])

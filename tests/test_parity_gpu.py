@@ -100,6 +100,25 @@ def test_weights_are_repacked_after_load_state_dict():
     assert rel_err(b, ref) <= TOL["fp32"] and rel_err(a, ref) > 1e-2
 
 
+def test_data_writes_need_invalidate_and_get_it_from_the_helpers():
+    """Writes through `p.data` bump nothing PyTorch exposes: the packed blob stays until `invalidate()` (ADVICE r1);
+    `load_state_dict` and `dist.broadcast_state` invalidate on their own."""
+    case = CASES["flag_learn3d"]
+    cfg, weights, batch = make_inputs(case)
+    m = build_module(case["kw"], weights, "fp32")
+    a = run_module(m, batch)[0]
+    w2 = synth.named_weights(spec.param_spec(cfg), seed=123)
+    with torch.no_grad():
+        for k, p in m.state_dict(keep_vars=True).items():
+            p.data.copy_(torch.from_numpy(w2[k]).to(p.device))          # invisible to the version counter
+    stale = run_module(m, batch)[0]
+    np.testing.assert_array_equal(stale, a)                              # documented behaviour: still the old weights
+    m.invalidate()
+    fresh = run_module(m, batch)[0]
+    ref = oracle_outputs(cfg, w2, batch)[0]
+    assert rel_err(fresh, ref) <= TOL["fp32"] and rel_err(a, ref) > 1e-2
+
+
 @pytest.mark.parametrize("precision,name,B", [("bf16", "hm0_v4_d12", 2048), ("tf32", "hm0_v4_d12", 1024),
                                              ("bf16", "chosen_v4_d12", 4096), ("bf16", "kptok_v4_d12", 2048),
                                              ("bf16", "cmu_v5_d2_hm0flags", 3000)])
