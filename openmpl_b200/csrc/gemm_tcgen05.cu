@@ -36,8 +36,7 @@ constexpr int BM = 128;          // accumulator rows per CTA (TMEM lanes)
 constexpr int BN = 256;          // accumulator columns per tile
 constexpr int KB_BYTES = 128;    // bytes of K per stage row = one 128B swizzle span
 constexpr int UMMA_K_BYTES = 32; // bytes of K per tcgen05.mma
-constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter: even / odd 32-column chunks
-constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter: even / odd 64-column groups
 constexpr int TMEM_COLS = 512;
 
 template <int CG, int EPI = 0, int KIND = 0>
@@ -47,16 +46,29 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CG;                    // W rows staged per CTA
   static constexpr int B_BYTES = B_ROWS * KB_BYTES;         // 32 KB / 16 KB
   static constexpr int STAGE_BYTES = OPS * (A_BYTES + B_BYTES);  // 48 KB / 32 KB (split: 96 KB / 64 KB)
-  // The residual-emit epilogues keep the old residual in a TMA-fed ring of 8 KB slots (a 32-row x 64-column box of each
-  // bf16 plane) that is updated in place and stored back from the same slot, paid for with operand stages: the short-K proj
-  // (EPI 6) is epilogue / HBM bound -> 4 stages + 12 slots; the long-K fc2 (EPI 7) is MMA bound -> 5 stages + 8 slots.
+  // The residual-emit epilogues keep the old residual in TMA-fed shared-memory slots of 8 KB (a 32-row x 64-column box of each
+  // bf16 plane) that are updated in place and stored back from the same slot.  Slots are PRIVATE to an epilogue warp (its
+  // mbarrier phases are then observed in order by construction -- a shared ring lets a warp wait for generation n + 1 of a
+  // slot whose generation n it never saw complete, and a parity wait cannot tell those apart).  A tile has 3 or 4 groups of 64
+  // columns: the even-group warps always take two, the odd-group warps one or two.  The slots are paid for with operand
+  // stages: the short-K proj (EPI 6) is epilogue / HBM bound -> 4 stages, two slots per even-group warp + one per odd-group
+  // warp (12); the long-K fc2 (EPI 7) is MMA bound -> 5 stages, one slot per warp (8; a second group waits for its box).
   static constexpr bool RESID = (KIND == 0) && (EPI == 6 || EPI == 7);
-  static constexpr int RING_SLOTS = !RESID ? 0 : (EPI == 6 ? 12 : 8);
+  static constexpr int EPI_WARPS = NUM_EPI_WARPS;
+  static constexpr int THREADS = (4 + EPI_WARPS) * 32;
+  static constexpr int SLOTS_EVEN = !RESID ? 0 : (EPI == 6 ? 2 : 1);  // slots of an even-group warp (odd-group warps: 1)
+  static constexpr int RING_SLOTS = !RESID ? 0 : 4 * SLOTS_EVEN + 4;
   static constexpr int SLOT_BYTES = 8192;
   static constexpr int RING_BYTES = RING_SLOTS * SLOT_BYTES;
   static constexpr int STAGES = (KIND == 1) ? ((CG == 1) ? 2 : 3)
                                 : (EPI == 6) ? ((CG == 1) ? 2 : 4) : (EPI == 7) ? ((CG == 1) ? 3 : 5) : ((CG == 1) ? 4 : 6);
-  static constexpr int STAGING_BYTES = RESID ? 0 : NUM_EPI_WARPS * 4096;  // per epilogue warp: one 32-row x 128-byte output box
+  static constexpr int STAGING_BYTES = RESID ? 0 : EPI_WARPS * 4096;  // per epilogue warp: one 32-row x 128-byte output box
+  // slot and mbarrier phase of the n-th residual box (n = 0, 1, ...) of epilogue warp (lane quarter q, group parity `odd`)
+  static constexpr uint32_t SE = SLOTS_EVEN ? SLOTS_EVEN : 1;
+  __host__ __device__ static constexpr uint32_t slot_of(int q, int odd, uint32_t n) {
+    return odd ? (uint32_t)(4 * SLOTS_EVEN + q) : (uint32_t)(SLOTS_EVEN * q) + n % SE;
+  }
+  __host__ __device__ static constexpr uint32_t phase_of(int odd, uint32_t n) { return (odd ? n : n / SE) & 1u; }
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + RING_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -201,7 +213,7 @@ __device__ __forceinline__ void stage_row_f16(uint32_t box, int lane, int j0, co
 }
 
 template <int CG, int KIND, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((Cfg<CG, EPI, KIND>::THREADS), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmY2,
@@ -251,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);        // one tcgen05.commit
-      ptx::mbar_init(tempty_bar(s), NUM_EPI_WARPS * CG);  // one arrive per epilogue warp of every CTA of the pair
+      ptx::mbar_init(tempty_bar(s), C::EPI_WARPS * CG);  // one arrive per epilogue warp of every CTA of the pair
     }
     for (int s = 0; s < C::RING_SLOTS; ++s) {
       ptx::mbar_init(rfull_bar(s), 1);   // the residual producer's arrive.expect_tx
@@ -381,12 +393,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 3) {
     // ===================================== residual producer (EPI 6 / 7) =====================
-    // Items = (tile, 64-column group g, 32-row quarter q) in that order; item i lives in ring slot i % RING_SLOTS and is
-    // consumed by epilogue warp (q, g & 1).  The producer runs as far ahead as the ring allows -- across tile boundaries,
-    // i.e. the old residual of the next tile streams in while its accumulator is still being computed.
+    // Boxes are requested in (tile, 64-column group g, 32-row quarter q) order, each into a slot of the epilogue warp
+    // (q, g & 1) that will consume it; the producer runs as far ahead as free slots allow -- across tile boundaries, i.e. the
+    // old residual of the next tile streams in while its accumulator is still being computed.
     if constexpr (RESID) {
       if (lane == 0) {
-        uint32_t item = 0;
+        uint32_t cnt[2] = {0u, 0u};  // boxes handed to an even- / odd-group warp so far (the same for every quarter)
         for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
           const int64_t m_blk = tile / n_tiles;
           const int n_blk = (int)(tile % n_tiles);
@@ -396,9 +408,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int ng = (n_size + 63) >> 6;
           const int32_t row_base = (int32_t)(m_blk * BM * CG + cta_rank * BM);
           for (int g = 0; g < ng; ++g) {
+            const int odd = g & 1;
+            const uint32_t n = cnt[odd]++;
+            const uint32_t ph = C::phase_of(odd, n);
 #pragma unroll 1
-            for (int q = 0; q < 4; ++q, ++item) {
-              const uint32_t slot = item % C::RING_SLOTS, ph = (item / C::RING_SLOTS) & 1u;
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t slot = C::slot_of(q, odd, n);
               ptx::mbar_wait(rempty_bar(slot), ph ^ 1u);
               const uint32_t dst = ring_base + slot * C::SLOT_BYTES;
               ptx::mbar_arrive_expect_tx(rfull_bar(slot), C::SLOT_BYTES);
@@ -413,7 +428,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp >= 4) {
     // ===================================== epilogue ==========================================
     const int q = warp & 3;            // TMEM lane quarter this warp may read (warp id % 4)
-    const int half = (warp - 4) >> 2;  // 0: even 64-column groups, 1: odd groups
+    const int half = (warp - 4) >> 2;  // 0: even 64-column groups, 1: odd groups (residual-emit: group index mod 4)
     constexpr bool OUT_BF16 = (KIND == 0) && (EPI == 0 || EPI == 1 || EPI == 4 || EPI == 5);
     constexpr bool OUT_SPLIT = SPLIT && (EPI == 0 || EPI == 1);  // two bf16 planes (hi through tmY, lo through tmY2)
     constexpr bool LNF = (EPI == 4 || EPI == 5);
@@ -421,8 +436,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t leader_tempty0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : 0u;
-    uint32_t item_base = 0;  // RESID: items of this CTA before the current tile
-    int held_slot = -1;      // RESID: ring slot whose TMA stores may still be reading shared memory
+    uint32_t box_count = 0;  // RESID: residual boxes this warp has consumed so far (selects its slot and mbarrier phase)
+    int held_slot = -1;      // RESID: slot whose TMA stores may still be reading shared memory
     for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const int64_t m_blk = tile / n_tiles;
       const int n_blk = (int)(tile % n_tiles);
@@ -456,13 +471,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // and leave by TMA from the same slot.  Rows past M and columns past N are zero-filled on the way in and clipped
         // on the way out by the tensor maps.  The row statistics are per-lane sums: no shuffles.
         const int ng = (n_size + 63) >> 6;
-        float s1 = 0.f, s2 = 0.f;
+        float2 s1 = make_float2(0.f, 0.f), s2 = s1;  // (even, odd) column partial sums
         ptx::mbar_wait(tfull_bar(acc), acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-        for (int g = half; g < ng; g += 2) {
-          const uint32_t item = item_base + (uint32_t)(4 * g + q);
-          const uint32_t slot = item % C::RING_SLOTS, ph = (item / C::RING_SLOTS) & 1u;
+        for (int g = half; g < ng; g += 2, ++box_count) {
+          const uint32_t slot = C::slot_of(q, half, box_count), ph = C::phase_of(half, box_count);
           if (held_slot >= 0) {  // hand the previous slot back before waiting for the next one (no hold-and-wait)
             if (lane == 0) {
               ptx::bulk_wait_read<0>();
@@ -489,25 +503,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(rowl + sw));
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + min(col, N - 4)));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + min(col + 4, N - 4)));
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              float v[8];
+              const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+              // element pairs on packed f32x2 instructions (half the FADD / FFMA count of the scalar form)
+              float2 v[4];
 #pragma unroll
               for (int w = 0; w < 4; ++w) {
-                const float x0 = __uint_as_float(h[w] << 16) + __uint_as_float(l[w] << 16);
-                const float x1 = __uint_as_float(h[w] & 0xffff0000u) + __uint_as_float(l[w] & 0xffff0000u);
-                v[2 * w] = (__uint_as_float(va[8 * jj + 2 * w]) + bb[2 * w]) + x0;
-                v[2 * w + 1] = (__uint_as_float(va[8 * jj + 2 * w + 1]) + bb[2 * w + 1]) + x1;
+                const float2 xo = __fadd2_rn(make_float2(__uint_as_float(h[w] << 16), __uint_as_float(h[w] & 0xffff0000u)),
+                                             make_float2(__uint_as_float(l[w] << 16), __uint_as_float(l[w] & 0xffff0000u)));
+                const float2 ab = __fadd2_rn(make_float2(__uint_as_float(va[8 * jj + 2 * w]), __uint_as_float(va[8 * jj + 2 * w + 1])), bb[w]);
+                v[w] = __fadd2_rn(ab, xo);
               }
               if (col < N) {  // (whole 8-column chunks: N % 8 == 0) columns past N carry stale accumulator values
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+                for (int w = 0; w < 4; ++w) {
+                  s1 = __fadd2_rn(s1, v[w]);
+                  s2 = __ffma2_rn(v[w], v[w], s2);
+                }
               }
 #pragma unroll
               for (int w = 0; w < 4; ++w) {
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * w], v[2 * w + 1]);
+                const __nv_bfloat162 hh = __float22bfloat162_rn(v[w]);
                 h[w] = *reinterpret_cast<const uint32_t*>(&hh);
-                const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * w] - __uint_as_float(h[w] << 16),
-                                                                v[2 * w + 1] - __uint_as_float(h[w] & 0xffff0000u));
+                const float2 rem = __fadd2_rn(v[w], make_float2(-__uint_as_float(h[w] << 16), -__uint_as_float(h[w] & 0xffff0000u)));
+                const __nv_bfloat162 ll = __float22bfloat162_rn(rem);
                 l[w] = *reinterpret_cast<const uint32_t*>(&ll);
               }
               ptx::st_shared_v4(rowh + sw, h[0], h[1], h[2], h[3]);
@@ -531,7 +549,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           held_slot = -1;
         }
         // per-row partial statistics of this warp's column slice (rows past M land in the padding of the slot plane)
-        ln.stats_out[(2 * n_blk + half) * ln.stats_ld + my_row] = make_float2(s1, s2);
+        ln.stats_out[(2 * n_blk + half) * ln.stats_ld + my_row] = make_float2(s1.x + s1.y, s2.x + s2.y);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -539,7 +557,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else ptx::mbar_arrive_cluster(leader_tempty0 + 8u * acc);
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        item_base += (uint32_t)(4 * ng);
         continue;
       }
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
@@ -698,7 +715,7 @@ int launch_one(const GemmMaps& tm, const float* bias, int64_t M, int N, int K, c
   const unsigned groups = (unsigned)(total < max_groups ? total : max_groups);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * CG);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -754,7 +771,7 @@ bool gemm_tcgen05_supports(int N, int K, int dtype) {
   return N >= 16 && N % 16 == 0 && K >= 1 && ((int64_t)K * 2) % 16 == 0;
 }
 
-int gemm_ln_slots(int N) { return 2 * split_tiles(N).T; }
+int gemm_ln_slots(int N) { return 2 * split_tiles(N).T; }  // one slot per (tile, epilogue warp of a lane quarter)
 
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, int dtype,
                         int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* lnargs, int cta_group) {

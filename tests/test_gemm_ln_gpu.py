@@ -71,7 +71,9 @@ def test_layernorm_apply_epilogue(M, N, K, gelu, out_fp16, cg):
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("M,N,K,fp16", [(1000, 1088, 1088, False), (777, 1088, 2176, True), (513, 544, 544, False),
                                          (300, 544, 1088, True), (2049, 1088, 1088, False), (100, 32, 64, False),
-                                         (4100, 544, 2176, False)])
+                                         (4100, 544, 2176, False),
+                                         # many tiles per CTA: the residual slots and their mbarrier phases wrap many times
+                                         (40000, 1088, 1088, False), (36000, 1088, 2176, True), (50000, 544, 544, False)])
 def test_residual_emit_epilogue(M, N, K, fp16, cg):
     L = _lib.lib()
     g = torch.Generator(device="cuda").manual_seed(2 * M + N + K)
