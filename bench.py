@@ -2,10 +2,13 @@
 """bench.py — poses/s of the MPL lifter forward (BASELINE.json metric) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|tf32|fp32]
+                    [--arch hm0|chosen|cmu0|kptok] [--views V] [--depth D] [--batch B]
 
 One "step" = one forward of the H36M 4-view 17-joint `hm_0` lifter (depth 12, D = 1088, 114 M parameters) over a
 batch of 65 536 synthetic poses per GPU (BASELINE.json configs[1]).  Ranks shard the pose index range; there is no
 data-path collective, only one all-reduce of the MPJPE accumulators after the timed region.  Prints ONE JSON line.
+`--arch / --views / --depth` select the other BASELINE.json configurations (CMU Panoptic V = 5 depth 2, the "chosen"
+ablation, the view sweep in both token layouts) with the same keys.
 """
 from __future__ import annotations
 
@@ -25,6 +28,11 @@ import numpy as np  # noqa: E402
 
 METRIC = "poses/sec MPL forward (H36M 4-view, 17 joints)"
 ARCH = dict(num_joints=17, embed_dim_ratio=32, num_heads=8, depth=12, num_views=4, drop_path_rate=0.1)
+ARCH_NAMES = {"hm0": "H36M hm_0 (MultiSPT, Conf3rd, Raytoken, Add3dEncRays)", "cmu0": "CMU Panoptic cmu_0 flags (= hm_0 flags)",
+              "chosen": "'chosen' ablation (single SPT, no ray token)", "kptok": "view x keypoint-token FPT"}
+ARCH_DEPTH = {"hm0": 12, "chosen": 12, "kptok": 12, "cmu0": 2}
+ARCH_VIEWS = {"hm0": 4, "chosen": 4, "kptok": 4, "cmu0": 5}
+ARCH_RIG = {"hm0": "h36m", "chosen": "h36m", "kptok": "h36m", "cmu0": "cmu"}
 
 
 def parse():
@@ -37,8 +45,15 @@ def parse():
     p.add_argument("--batch", type=int, default=65536, help="poses per GPU per step")
     p.add_argument("--cpu-batch", type=int, default=1024, help="poses per CPU-baseline forward")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--depth", type=int, default=12)
-    return p.parse_args()
+    p.add_argument("--arch", default="hm0", choices=sorted(ARCH_NAMES))
+    p.add_argument("--views", type=int, default=None)
+    p.add_argument("--depth", type=int, default=None)
+    p.add_argument("--parity-poses", type=int, default=512, help="poses of the step checked against the oracle (outside the timed regions)")
+    p.add_argument("--no-extras", action="store_true", help="skip the latency_b256 and fp32-grade-mode side measurements")
+    a = p.parse_args()
+    a.views = a.views or ARCH_VIEWS[a.arch]
+    a.depth = ARCH_DEPTH[a.arch] if a.depth is None else a.depth
+    return a
 
 
 def peaks():
@@ -50,52 +65,86 @@ def peaks():
 
 def workload(args):
     from openmpl_b200 import spec
-    kw = dict(ARCH, depth=args.depth, **spec.HM0_FLAGS)
+    flags = {"hm0": spec.HM0_FLAGS, "cmu0": spec.HM0_FLAGS, "chosen": spec.CHOSEN_FLAGS,
+             "kptok": dict(pose_3d_emb_learnable=True, confidence_input_as_third=True, FPT_blocks_view_keypoint_tokens=True)}[args.arch]
+    kw = dict(ARCH, depth=args.depth, num_views=args.views, **flags)
     return kw, spec.make_config(**kw)
 
 
+def metric_name(args):
+    if args.arch == "hm0" and args.views == 4:
+        return METRIC
+    rig = "H36M" if ARCH_RIG[args.arch] == "h36m" else "CMU Panoptic"
+    return f"poses/sec MPL forward ({rig} {args.views}-view, 17 joints)"
+
+
+def workload_name(args, cfg, batch, what):
+    rig = "H36M" if ARCH_RIG[args.arch] == "h36m" else "CMU Panoptic"
+    return (f"{rig} {cfg.V}-view 17-joint lifter forward, {ARCH_NAMES[args.arch]}, depth {cfg.depth}, D={cfg.fpt_dim}, "
+            f"{cfg.fpt_tokens} FPT tokens, {what}")
+
+
 def cpu_forward_timer(args, steps, warmup):
-    """The reference forward's CPU path timed on the host cores: the torch-CPU restatement (same ATen/MKL calls the
-    reference module makes, fp32, all cores) — the reference itself is Python and does not travel to the GPU box."""
+    """The reference forward timed on the host cores, fp32, all cores.  kind "reference": the UNMODIFIED reference module
+    (`MPL/lib/models/multiview_mpl.py`, staged byte for byte under the git-ignored oracle/_ref/ by oracle/stage_reference.py)
+    run through its own forward; kind "port" (only when the staged file is missing): the torch-CPU restatement making the
+    same ATen calls.  Returns (per-forward seconds, kind)."""
     import torch
     from openmpl_b200 import spec, synth
-    from oracle import torch_port                                   # cpu_baseline / --impl reference legs only
+    from oracle import ref_loader                                   # cpu_baseline / --impl reference legs only
     torch.set_num_threads(os.cpu_count() or 1)
     kw, cfg = workload(args)
-    weights = synth.named_weights(spec.param_spec(cfg), seed=0)
-    batch = synth.make_batch(args.cpu_batch, synth.make_rig(cfg.V), seed=1)
-    p = {k: torch.from_numpy(v) for k, v in weights.items()}
-    x = [torch.from_numpy(batch[k]) for k in ("poses", "rays", "centers")]
+    batch = synth.make_batch(args.cpu_batch, synth.make_rig(cfg.V, ARCH_RIG[args.arch]), seed=1)
+    V = cfg.V
+    if ref_loader.model_file() is not None:
+        kind = "reference"
+        mod = ref_loader.load_model_module()
+        torch.manual_seed(0)
+        model = mod.MultiView_MPL(**kw).eval()                      # PyTorch default init under seed 0 = the reference's 'scratch' init
+        lists = [[torch.from_numpy(np.ascontiguousarray(batch[k][:, v])) for v in range(V)] for k in ("poses", "rays", "centers")]
+
+        def fwd():
+            with torch.no_grad():
+                return model(lists[0], rays=lists[1], centers=lists[2])
+    else:
+        kind = "port"
+        from oracle import torch_port
+        weights = synth.named_weights(spec.param_spec(cfg), seed=0)
+        p = {k: torch.from_numpy(v) for k, v in weights.items()}
+        x = [torch.from_numpy(batch[k]) for k in ("poses", "rays", "centers")]
+        fwd = lambda: torch_port.forward(p, cfg, *x)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        torch_port.forward(p, cfg, *x)
+        fwd()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return times
+    return times, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's CPU path (oracle port; the reference itself is pure Python/PyTorch and
-    does not travel to the GPU box) on all host cores; each step = one forward over a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path (the unmodified module when staged, see
+    cpu_forward_timer) on all host cores; each step = one forward over a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     steps, warmup = max(1, min(args.steps, 100)), max(1, min(args.warmup, 5))   # K timed forwards, W untimed
-    times = cpu_forward_timer(args, steps, warmup)
+    times, kind = cpu_forward_timer(args, steps, warmup)
     total = sum(times)
     value = args.cpu_batch * len(times) / total
     kw, cfg = workload(args)
+    what = ("the unmodified reference module (MPL/lib/models/multiview_mpl.py) through its own forward" if kind == "reference"
+            else "torch-CPU fp32 restatement of MultiView_MPL.forward (same ATen calls as the reference)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": len(times),
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": len(times),
         "warmup": warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"H36M 4-view 17-joint hm_0 lifter forward (MultiSPT, Conf3rd, Raytoken, Add3dEncRays), depth {cfg.depth}, "
-                               f"D={cfg.fpt_dim}, bounded sample of {args.cpu_batch} poses per step",
-                   "batch_per_step": args.cpu_batch, "views": cfg.V, "joints": cfg.J, "note": "torch-CPU fp32 restatement of MultiView_MPL.forward (same ATen calls as the reference) on all host cores"},
-        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": cores, "kind": "port",
+        "config": {"workload": workload_name(args, cfg, args.batch, f"batch {args.batch} per GPU"),
+                   "sample": f"bounded sample of {args.cpu_batch} poses per step", "batch_per_step": args.cpu_batch,
+                   "views": cfg.V, "joints": cfg.J, "note": what + ", all host cores"},
+        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": cores, "kind": kind,
                          "sample": f"{len(times)} forwards of {args.cpu_batch} poses"},
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -178,7 +227,7 @@ def run_ours(args):
 
     # ---- synthetic inputs of this rank's shard of the global pose range ----
     start, _ = mdist.shard_range(B * world, rank, world)
-    rig = synth.make_rig(cfg.V, "h36m")
+    rig = synth.make_rig(cfg.V, ARCH_RIG[args.arch])
     batch = synth.make_batch(B, rig, seed=1, start=start)
     host = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("poses", "rays", "centers", "target")}
     devin = {k: v.to(dev) for k, v in host.items()}
@@ -203,19 +252,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- parity spot-check against the oracle (checker only; outside every timed region) ----
+    # ---- parity against the oracle (checker only; outside every timed region): poses spread over the whole batch, i.e.
+    # over every forward chunk and many GEMM tiles ----
     out = step_device()
     parity = None
-    if rank == 0:
+    if rank == 0 and args.parity_poses > 0:
         from oracle import mpl_oracle
-        idx = np.arange(0, B, max(1, B // 8))[:8]
+        n = min(args.parity_poses, B)
+        idx = np.unique(np.linspace(0, B - 1, n).astype(np.int64))
         ref = mpl_oracle.forward(weights, cfg, batch["poses"][idx], batch["rays"][idx], batch["centers"][idx])
         got = out[torch.from_numpy(idx).to(dev)].cpu().numpy()
         scale = float(np.abs(ref).max())
         tgt = batch["target"][idx].astype(np.float64)
         mp = lambda p: float(np.sqrt(((p - tgt) ** 2).sum(-1)).mean()) * 1000.0
+        chunk0 = int(model.chunk_poses())
         parity = {"max_abs_err_over_scale": float(np.abs(got - ref).max()) / scale, "poses_checked": int(len(idx)),
-                  "delta_mpjpe_mm": abs(mp(got.astype(np.float64)) - mp(ref))}
+                  "chunks_covered": int(len(np.unique(idx // chunk0))), "delta_mpjpe_mm": abs(mp(got.astype(np.float64)) - mp(ref)),
+                  "stated_bound": {"bf16": 1.2e-2, "tf32": 1e-3, "fp32": 2e-5}[args.precision]}
 
     # ---- timed region 1: device-resident inputs (value) ----
     for _ in range(max(args.warmup, 3)):
@@ -264,7 +317,7 @@ def run_ours(args):
     chunks = -(-B // chunk_poses)
     roofline, breakdown = None, {}
     try:      # per-launch DRAM traffic of the GEMM launches from the committed `ncu --set full` capture (profiles/)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.arch, {})
     except Exception:
         traffic = {}
     tot_ms = sum(a[0] for a in agg.values())
@@ -282,6 +335,8 @@ def run_ours(args):
                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic.get("gemm_tcgen05_kernel", {}).get("bytes_per_launch"),
                     "traffic_note": traffic.get("gemm_tcgen05_kernel", {}).get("note"),
+                    "traffic_capture": {k: traffic.get("gemm_tcgen05_kernel", {}).get(k) for k in ("capture", "git_rev_at_capture", "lib_sha256_16")},
+                    "per_gemm_tflops": {c: flops_per_launch[c] / chunks * agg[c][1] / (agg[c][0] / 1000.0) / 1e12 for c in gemm_cats},
                     "algorithmic_flops_per_launch": g_flops / g_n,
                     "peak_source": f"{pk_src} bf16_tflops_sustained" + (" / 3 (split bf16 hi/lo operands)" if args.precision == "tf32" else ""),
                     "avg_launch_ms": g_ms / g_n, "launches_timed": g_n, "share_of_step": g_ms / tot_ms}
@@ -298,7 +353,8 @@ def run_ours(args):
         "embed": Bc * cfg.V * (cfg.J * 12 + cfg.J * cfg.d * 4),
         "token_build": Bc * cfg.V * (cfg.J * cfg.d * 4 + 2 * cfg.J * 12 + 12 + cfg.tok_w * 4),
         "fpt_attention": rows_f * (3 * D + D) * esz,
-        "fpt_layernorm": rows_f * (D * 4 + D * esz),
+        # bf16 mode: ln_prep (fp32 tokens -> two bf16 planes), once per chunk; other modes: LayerNorm kernels
+        "fpt_layernorm": rows_f * (D * 4 + D * (4 if args.precision != "fp32" else 4)),
         "head": Bc * (cfg.V * cfg.E * 4 + cfg.J * 12),
     }
     memory_kernels = {}
@@ -322,19 +378,77 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times = cpu_forward_timer(args, steps=3, warmup=1)
+        times, kind = cpu_forward_timer(args, steps=3, warmup=1)
         v = args.cpu_batch * len(times) / sum(times)
-        cpu = {"value": v, "unit": "poses/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{len(times)} forwards of {args.cpu_batch} poses (torch-CPU fp32 restatement of the reference forward, all cores)"}
+        cpu = {"value": v, "unit": "poses/s", "cores": os.cpu_count(), "kind": kind,
+               "sample": f"{len(times)} forwards of {args.cpu_batch} poses ("
+                         + ("the unmodified reference module" if kind == "reference" else "torch-CPU fp32 restatement of the reference forward")
+                         + ", fp32, all cores)"}
+
+    # ---- side measurements (rank 0, N = 1; outside the timed regions above) ----
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # (1) the reference runner's own batch size (TEST.BATCH_SIZE 256, lists of host tensors, valid_mpl.py:205-210): end to
+        # end through the module, CUDA-graph path vs kernel-by-kernel launches
+        b256 = synth.make_batch(256, rig, seed=2)
+        lists = [[torch.from_numpy(np.ascontiguousarray(b256[k][:, v])).pin_memory() for v in range(cfg.V)]
+                 for k in ("poses", "rays", "centers")]
+        lat = {}
+        for tag, gb in (("cuda_graph", 2048), ("kernel_by_kernel", 0)):
+            m2 = MultiView_MPL(**kw, precision=args.precision, graph_batch=gb, **impl)
+            m2.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+            m2 = m2.to(dev).eval()
+            res_host = torch.empty((256, cfg.J, 3), dtype=torch.float32).pin_memory()
+
+            def call():
+                with torch.no_grad():
+                    o = m2(lists[0], rays=lists[1], centers=lists[2])
+                res_host.copy_(o, non_blocking=True)
+                torch.cuda.synchronize()
+            for _ in range(5):
+                call()
+            t0 = time.perf_counter()
+            for _ in range(50):
+                call()
+            dt = (time.perf_counter() - t0) / 50
+            lat[tag] = {"ms": dt * 1e3, "poses_per_s": 256 / dt, "launches": m2.last_launches}
+            del m2
+        extras["latency_b256"] = dict(lat, note="host lists in -> pinned host result out, H2D + D2H inside, mean of 50 calls")
+        # (2) the fp32-grade tensor-core mode (split bf16 hi/lo operands) on the same workload: the mode that carries the
+        # 1e-3 / 0.1 mm parity bound
+        if args.precision == "bf16":
+            m3 = MultiView_MPL(**kw, precision="tf32", **impl)
+            m3.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+            m3 = m3.to(dev).eval()
+            with torch.no_grad():
+                o3 = m3(devin["poses"], rays=devin["rays"], centers=devin["centers"])
+                for _ in range(2):
+                    m3(devin["poses"], rays=devin["rays"], centers=devin["centers"])
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(3):
+                    m3(devin["poses"], rays=devin["rays"], centers=devin["centers"])
+                a1.record()
+                torch.cuda.synchronize()
+            ms3 = a0.elapsed_time(a1) / 3
+            err3 = None
+            if parity is not None:
+                got3 = o3[torch.from_numpy(idx).to(dev)].cpu().numpy()
+                err3 = float(np.abs(got3 - ref).max()) / scale
+            extras["fp32_grade_mode"] = {"precision": "tf32 (split bf16 hi/lo operands, three tcgen05 MMAs per product)",
+                                         "value": B / (ms3 / 1e3), "unit": "poses/s", "ms_per_step": ms3,
+                                         "max_abs_err_over_scale": err3, "stated_bound": 1e-3}
+            del m3
 
     if rank == 0:
         flops = spec.flops_per_pose(cfg)
         line = {
-            "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": metric_name(args), "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"H36M 4-view 17-joint hm_0 lifter forward (MultiSPT, Conf3rd, Raytoken, Add3dEncRays), depth {cfg.depth}, "
-                                   f"D={cfg.fpt_dim}, batch {B} per GPU", "batch_per_gpu": B, "views": cfg.V, "joints": cfg.J,
+            "config": {"workload": workload_name(args, cfg, B, f"batch {B} per GPU"), "arch": args.arch,
+                       "batch_per_gpu": B, "views": cfg.V, "joints": cfg.J,
                        "parallelism": f"pose-sharded x{world}, no data-path collective",
                        "l2": "activation working set per step (GBs) far exceeds the 126 MB L2; no explicit flush",
                        "flops_per_pose": flops, "gemm_cta_group": int(os.environ.get("MPL_GEMM_CTA_GROUP", "0")) or None},
@@ -343,7 +457,7 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "whole_path_tflops": value / world * flops / 1e12,
             "breakdown": breakdown, "memory_bound_kernels": memory_kernels, "hbm_peak_gbs": pk.get("hbm_gbs"),
-            "cpu_baseline": cpu, "parity": parity,
+            "cpu_baseline": cpu, "parity": parity, **extras,
             "mpjpe_cm": {"absolute": res["mpjpe_abs"], "root_relative": res["mpjpe_rel"], "procrustes_aligned": pres["p_mpjpe"],
                          "poses": res["n"],
                          "note": "random-init weights: the values only exercise the accumulators + all-reduce"},

@@ -140,6 +140,16 @@ int mpl_forward(MplModel* m, const void* packed, const float* const* poses, cons
                 const float* const* centers, int64_t pose_stride, int64_t center_stride, float* out, float* aux1,
                 float* aux2, int64_t batch, void* workspace, size_t workspace_bytes, mpl_stream_t stream);
 
+/* Small-batch path (the reference's runner calls the model at TEST.BATCH_SIZE = 256, configs/h36m/mpl_amass/hm_0_*.yaml:144,
+ * MPL/run/valid_mpl.py:205-210, where ~130 launches per forward are latency-bound): with max_batch > 0, an mpl_forward of at most
+ * max_batch poses is captured ONCE per (batch, packed, input / output / workspace pointers) as a CUDA graph and later calls
+ * with the same arguments replay it with a single graph launch on the caller's stream.  The caller keeps those buffers
+ * alive and at the same addresses (the nn.Module stages inputs in persistent buffers for this).  Up to 16 graphs are kept
+ * per handle (least recently used evicted); 0 switches the path off and frees them.  A stream that is itself being
+ * captured, and profiling mode, take the plain path. */
+int mpl_set_graph_batch(MplModel* m, int64_t max_batch);
+int mpl_graph_stats(const MplModel* m, int64_t* captures, int64_t* replays);
+
 /* Number of kernel launches the last mpl_forward on this handle enqueued (bench.py's gpu_launches). */
 int64_t mpl_last_launch_count(const MplModel* m);
 

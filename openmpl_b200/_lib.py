@@ -28,7 +28,7 @@ EXPORTS = [
     "mpl_packed_bytes", "mpl_pack_weights", "mpl_workspace_bytes", "mpl_chunk_poses", "mpl_set_chunk_poses",
     "mpl_forward", "mpl_last_launch_count", "mpl_mpjpe_accumulate", "mpl_build_inputs", "mpl_test_gemm",
     "mpl_set_profile", "mpl_profile_categories", "mpl_profile_category_name", "mpl_profile_collect", "mpl_synth_project",
-    "mpl_pmpjpe_accumulate", "mpl_test_gemm_ln", "mpl_test_gemm_ln_slots",
+    "mpl_pmpjpe_accumulate", "mpl_test_gemm_ln", "mpl_test_gemm_ln_slots", "mpl_set_graph_batch", "mpl_graph_stats",
 ]
 
 _DESC_FLAGS = [
@@ -113,6 +113,8 @@ def lib():
         L.mpl_test_gemm_ln.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p]
         L.mpl_test_gemm_ln_slots.argtypes = [c_int]
+        L.mpl_set_graph_batch.argtypes = [c_void_p, c_int64]
+        L.mpl_graph_stats.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64)]
         L.mpl_set_profile.argtypes = [c_void_p, c_int]
         L.mpl_profile_category_name.argtypes = [c_int]
         L.mpl_profile_category_name.restype = c_char_p

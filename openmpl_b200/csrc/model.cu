@@ -42,6 +42,12 @@ struct BnFold {
   int N, K;
 };
 
+struct BlockW {
+  const float *n1w, *n1b, *qkvw, *qkvb, *projw, *projb, *n2w, *n2b, *fc1w, *fc1b, *fc2w, *fc2b;
+  const void *qkvw_tc, *projw_tc, *fc1w_tc, *fc2w_tc;  // tensor-core operand copies (FPT, bf16 / tf32 modes)
+  const float *qkv_cs, *qkv_bf, *fc1_cs, *fc1_bf;      // LayerNorm-fused mode: column sums of W' and folded biases
+};
+
 }  // namespace mpl
 
 using namespace mpl;
@@ -67,6 +73,27 @@ struct MplModel {
   size_t packed_bytes = 0;
   int64_t chunk = 32768;
   int64_t launches = 0;
+  // small-batch path: the whole forward of a (batch, pointer set) captured once as a CUDA graph and replayed with one launch
+  struct GraphKey {
+    int64_t batch, pose_stride, center_stride;
+    const void* packed;
+    const void* in[3][kMaxViews];
+    void *out, *aux1, *aux2, *workspace;
+  };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    int64_t launches;
+    uint64_t last_used;
+  };
+  std::vector<GraphEntry> graphs;
+  int64_t graph_max_batch = 0;   // 0: off (mpl_set_graph_batch)
+  cudaStream_t cap_stream = nullptr;
+  uint64_t graph_clock = 0;
+  int64_t graph_hits = 0, graph_captures = 0;
+  // weight pointers of every block, resolved once per packed blob (no string lookups on the launch path)
+  const void* resolved_for = nullptr;
+  std::vector<mpl::BlockW> fpt_blocks;
   // optional per-launch CUDA-event profiling (bench.py's roofline numbers come from here)
   bool profile = false;
   struct ProfRec { int cat; cudaEvent_t e0, e1; };
@@ -372,12 +399,6 @@ static cudaEvent_t prof_event(MplModel* m) {
     }                                                        \
   } while (0)
 
-struct BlockW {
-  const float *n1w, *n1b, *qkvw, *qkvb, *projw, *projb, *n2w, *n2b, *fc1w, *fc1b, *fc2w, *fc2b;
-  const void *qkvw_tc, *projw_tc, *fc1w_tc, *fc2w_tc;  // tensor-core operand copies (FPT, bf16 / tf32 modes)
-  const float *qkv_cs, *qkv_bf, *fc1_cs, *fc1_bf;      // LayerNorm-fused mode: column sums of W' and folded biases
-};
-
 static BlockW block_weights(const MplModel* m, const Packed& P, const std::string& p, bool tc) {
   BlockW b{};
   b.n1w = P.f(p + "norm1.weight");
@@ -604,8 +625,13 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
     const int64_t rows = Bc * N;
     if (m->ln_fused)
       LC(CAT_FPT_LN, launch_ln_prep(w.tok, D, (__nv_bfloat16*)w.fxn, (__nv_bfloat16*)w.fxl, D, w.fstats, m->ln_slots, rows, D, s));
+    if (m->resolved_for != P.base) {  // once per packed blob: no string lookups on the launch path afterwards
+      m->fpt_blocks.clear();
+      for (int ix = 0; ix < m->depth; ++ix) m->fpt_blocks.push_back(block_weights(m, P, "blocks." + std::to_string(ix) + ".", m->fpt_tc));
+      m->resolved_for = P.base;
+    }
     for (int ix = 0; ix < m->depth; ++ix) {
-      const BlockW bw = block_weights(m, P, "blocks." + std::to_string(ix) + ".", m->fpt_tc);
+      const BlockW& bw = m->fpt_blocks[ix];
       const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
       for (int r = 0; r < reps; ++r) {
         if (m->fpt_tc)
@@ -782,6 +808,8 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
 
 void mpl_destroy(MplModel* m) {
   if (m == nullptr) return;
+  for (auto& e : m->graphs) cudaGraphExecDestroy(e.exec);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
   delete m;
 }
@@ -959,6 +987,8 @@ int mpl_set_chunk_poses(MplModel* m, int64_t chunk) {
     return MPL_ERR_INVALID_ARGUMENT;
   }
   m->chunk = chunk;
+  for (auto& e : m->graphs) cudaGraphExecDestroy(e.exec);  // captured graphs bake the chunking in
+  m->graphs.clear();
   return MPL_OK;
 }
 
@@ -1013,6 +1043,56 @@ int mpl_forward(MplModel* m, const void* packed, const float* const* poses, cons
   Packed P{m, reinterpret_cast<const uint8_t*>(packed)};
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int out_dim = 3 * m->J;
+  // ---- small batches: replay the captured graph of this exact call (same batch and pointers), capture it on first sight ----
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  const bool try_graph = m->graph_max_batch > 0 && batch <= m->graph_max_batch && !m->profile &&
+                         cudaStreamIsCapturing(s, &cap_status) == cudaSuccess && cap_status == cudaStreamCaptureStatusNone;
+  MplModel::GraphKey key;
+  if (try_graph) {
+    memset(&key, 0, sizeof(key));
+    key.batch = batch; key.pose_stride = pose_stride; key.center_stride = center_stride;
+    key.packed = packed; key.out = out; key.aux1 = aux1; key.aux2 = aux2; key.workspace = workspace;
+    for (int v = 0; v < m->V; ++v) {
+      key.in[0][v] = poses[v];
+      key.in[1][v] = rays ? rays[v] : nullptr;
+      key.in[2][v] = centers ? centers[v] : nullptr;
+    }
+    for (auto& e : m->graphs)
+      if (memcmp(&e.key, &key, sizeof(key)) == 0) {
+        e.last_used = ++m->graph_clock;
+        MPL_CUDA(cudaGraphLaunch(e.exec, s));
+        m->launches = e.launches;
+        ++m->graph_hits;
+        return MPL_OK;
+      }
+    if (m->cap_stream == nullptr) MPL_CUDA(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+    MPL_CUDA(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+    s = m->cap_stream;  // nothing executes during capture; the instantiated graph is launched on the caller's stream below
+  }
+  auto end_capture = [&](int status) -> int {
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(m->cap_stream, &graph);
+    if (status != MPL_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return status;
+    }
+    MPL_CUDA(e);
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    MPL_CUDA(ie);
+    if (m->graphs.size() >= 16) {  // least recently used entry makes room
+      size_t lru = 0;
+      for (size_t i = 1; i < m->graphs.size(); ++i)
+        if (m->graphs[i].last_used < m->graphs[lru].last_used) lru = i;
+      cudaGraphExecDestroy(m->graphs[lru].exec);
+      m->graphs.erase(m->graphs.begin() + lru);
+    }
+    m->graphs.push_back({key, exec, m->launches, ++m->graph_clock});
+    ++m->graph_captures;
+    MPL_CUDA(cudaGraphLaunch(exec, reinterpret_cast<cudaStream_t>(stream)));
+    return MPL_OK;
+  };
   for (int64_t b0 = 0; b0 < batch; b0 += m->chunk) {
     const int64_t Bc = std::min<int64_t>(m->chunk, batch - b0);
     const float* pp[kMaxViews];
@@ -1023,12 +1103,33 @@ int mpl_forward(MplModel* m, const void* packed, const float* const* poses, cons
       rp[v] = rays ? rays[v] + b0 * pose_stride : nullptr;
       cp[v] = centers ? centers[v] + b0 * center_stride : nullptr;
     }
-    MPL_TRY(forward_chunk(m, P, pp, rays ? rp : nullptr, centers ? cp : nullptr, pose_stride, center_stride,
-                          out + b0 * out_dim, aux1 ? aux1 + b0 * out_dim : nullptr, aux2 ? aux2 + b0 * out_dim : nullptr, Bc,
-                          w, s));
+    const int st = forward_chunk(m, P, pp, rays ? rp : nullptr, centers ? cp : nullptr, pose_stride, center_stride,
+                                 out + b0 * out_dim, aux1 ? aux1 + b0 * out_dim : nullptr, aux2 ? aux2 + b0 * out_dim : nullptr, Bc,
+                                 w, s);
+    if (st != MPL_OK) return try_graph ? end_capture(st) : st;
+  }
+  return try_graph ? end_capture(MPL_OK) : MPL_OK;
+  MPL_API_END
+}
+
+int mpl_set_graph_batch(MplModel* m, int64_t max_batch) {
+  if (m == nullptr || max_batch < 0) {
+    set_error("mpl_set_graph_batch: null handle or negative batch");
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  m->graph_max_batch = max_batch;
+  if (max_batch == 0) {
+    for (auto& e : m->graphs) cudaGraphExecDestroy(e.exec);
+    m->graphs.clear();
   }
   return MPL_OK;
-  MPL_API_END
+}
+
+int mpl_graph_stats(const MplModel* m, int64_t* captures, int64_t* replays) {
+  if (m == nullptr) return MPL_ERR_INVALID_ARGUMENT;
+  if (captures) *captures = m->graph_captures;
+  if (replays) *replays = m->graph_hits;
+  return MPL_OK;
 }
 
 int64_t mpl_last_launch_count(const MplModel* m) { return m ? m->launches : 0; }

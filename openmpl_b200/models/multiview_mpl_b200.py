@@ -107,7 +107,8 @@ class MultiView_MPL(nn.Module):
                  deep_head=False,
                  head_kadkhod=False,
                  hidden_dim=1024,
-                 FPT_blocks_view_keypoint_tokens=False, *, precision=None, ln_fusion=True, gemm_cta_group=2):
+                 FPT_blocks_view_keypoint_tokens=False, *, precision=None, ln_fusion=True, gemm_cta_group=2,
+                 graph_batch=2048):
         super().__init__()
         kw = {k: v for k, v in locals().items() if k in CTOR_DEFAULTS}
         self.cfg = make_config(**kw)
@@ -115,6 +116,9 @@ class MultiView_MPL(nn.Module):
         # implementation switches (MplDesc.ln_fusion / gemm_cta_group): bf16 mode folds the FPT LayerNorms into the GEMMs
         # unless ln_fusion=False (checkpoints whose residual rows have |mean| >> std)
         self.ln_fusion, self.gemm_cta_group = bool(ln_fusion), int(gemm_cta_group)
+        # batches of at most `graph_batch` poses (the reference runner's 256, valid_mpl.py:205-210) replay one captured CUDA
+        # graph per batch size instead of ~130 kernel launches (mpl_set_graph_batch); 0 = always launch kernel by kernel
+        self.graph_batch = int(graph_batch)
         self.num_joints, self.num_views, self.embed_dim_ratio = num_joints, num_views, embed_dim_ratio
         self._spec = param_spec(self.cfg)
         for name, (shape, kind, fan_in) in self._spec.items():
@@ -151,6 +155,7 @@ class MultiView_MPL(nn.Module):
                 raise RuntimeError("parameter table of libmpl_b200.so differs from the module's state_dict")
             if self._chunk is not None:
                 _lib.check(L.mpl_set_chunk_poses(h, int(self._chunk)))
+            _lib.check(L.mpl_set_graph_batch(h, self.graph_batch))
             self._h.ptrs[index] = h
         return self._h.ptrs[index]
 
@@ -277,6 +282,11 @@ class MultiView_MPL(nn.Module):
             n = last_shape[0] * last_shape[1]
             return [t[:, v] for v in range(V)], V * n
 
+        # Small batches: persistent staging buffers + one CUDA-graph launch
+        small = self._graph_plan(poses, rays, centers)
+        if small is not None:
+            return self._forward_graph(small, device)
+
         # Host inputs larger than one forward chunk: the host->device copy of chunk i+1 runs on a side stream while
         # chunk i computes (same result, the copy disappears behind the kernels).
         pipelined = self._pipeline_plan(poses, rays, centers, device)
@@ -309,6 +319,95 @@ class MultiView_MPL(nn.Module):
             return out, [aux[0], aux[1]]
         return out
 
+
+    # ---- small batches: persistent buffers + CUDA graph replay -------------------------------------------------------
+    def _graph_plan(self, poses, rays, centers):
+        """(inputs per kind, packed?, B) when the call qualifies for the graph path: well-formed fp32 inputs of at most
+        `graph_batch` poses (anything else takes the plain path, which validates and reports errors)."""
+        if self.graph_batch <= 0:
+            return None
+        V, J = self.cfg.V, self.cfg.J
+        plan, B, packed_all = {}, None, None
+        for kind, x, last in (("poses", poses, (J, 3)), ("rays", rays, (J, 3)), ("centers", centers, (1, 3))):
+            if x is None:
+                plan[kind] = None
+                continue
+            packed = not isinstance(x, (list, tuple))
+            ts = [x] if packed else list(x)
+            want = ((V,) + last) if packed else last
+            if not packed and len(ts) != V:
+                return None
+            for t in ts:
+                if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.dim() == len(want) + 1
+                        and tuple(t.shape[1:]) == want):
+                    return None
+                if B is None:
+                    B = t.shape[0]
+                if t.shape[0] != B:
+                    return None
+            if packed_all is None:
+                packed_all = packed
+            if kind == "rays" and packed != packed_all:
+                return None
+            plan[kind] = (ts, packed)
+        if plan["poses"] is None or B is None or B == 0 or B > self.graph_batch:
+            return None
+        return plan, B
+
+    def _forward_graph(self, planned, device):
+        plan, B = planned
+        V, J = self.cfg.V, self.cfg.J
+        L = _lib.lib()
+        kad = self.cfg.kw["head_kadkhod"]
+        with torch.cuda.device(device):
+            st = self._state(device)
+            h = self._get_handle(device.index)
+            key = (B,) + tuple(None if v is None else v[1] for v in plan.values())
+            bufs = st.setdefault("static", {}).get(key)
+            if bufs is None:
+                bufs = {k: ([torch.empty(t.shape, dtype=torch.float32, device=device) for t in v[0]] if v is not None else None)
+                        for k, v in plan.items()}
+                bufs["out"] = torch.empty((B, J, 3), dtype=torch.float32, device=device)
+                bufs["aux"] = [torch.empty_like(bufs["out"]), torch.empty_like(bufs["out"])] if kad else [None, None]
+                if len(st["static"]) >= 16:
+                    st["static"].pop(next(iter(st["static"])))
+                st["static"][key] = bufs
+            for k, v in plan.items():
+                if v is not None:
+                    for d, t in zip(bufs[k], v[0]):
+                        d.copy_(t, non_blocking=True)           # host or device source; same stream as the graph launch
+            need = L.mpl_workspace_bytes(h, max(B, self.graph_batch))
+            ws = st["workspace"]
+            if ws is None or ws.numel() < need:
+                st["workspace"] = ws = torch.empty(need, dtype=torch.uint8, device=device)
+
+            def views(k, row):
+                if bufs[k] is None:
+                    return None, 0
+                if plan[k][1]:
+                    return [bufs[k][0][:, v] for v in range(V)], V * row
+                return bufs[k], row
+
+            p_list, p_stride = views("poses", J * 3)
+            r_list, _ = views("rays", J * 3)
+            c_list, c_stride = views("centers", 3)
+            arr = lambda ts: (ctypes.c_void_p * V)(*[t.data_ptr() for t in ts]) if ts is not None else None
+            out, aux = bufs["out"], bufs["aux"]
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(L.mpl_forward(h, st["packed"].data_ptr(), arr(p_list), arr(r_list), arr(c_list), p_stride, c_stride,
+                                     out.data_ptr(), aux[0].data_ptr() if kad else None, aux[1].data_ptr() if kad else None,
+                                     B, ws.data_ptr(), ws.numel(), stream))
+            self.last_launches = int(L.mpl_last_launch_count(h))
+            # the persistent output buffer is overwritten by the next call of this batch size: hand out a copy
+            if kad:
+                return out.clone(), [aux[0].clone(), aux[1].clone()]
+            return out.clone()
+
+    def graph_stats(self):
+        """(captures, replays) of the CUDA-graph path on the current device."""
+        c, r = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(_lib.lib().mpl_graph_stats(self._get_handle(), ctypes.byref(c), ctypes.byref(r)))
+        return c.value, r.value
 
     # ---- pipelined host -> device staging ---------------------------------------------------------------------------
     def _pipeline_plan(self, poses, rays, centers, device):
@@ -452,6 +551,7 @@ class MultiView_MPL_G(nn.Module):
             precision=kwargs.get("precision"),
             ln_fusion=kwargs.get("ln_fusion", True),
             gemm_cta_group=kwargs.get("gemm_cta_group", 2),
+            graph_batch=kwargs.get("graph_batch", 2048),
         )
 
     def forward(self, x, centers=None, rays=None):

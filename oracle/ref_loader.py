@@ -14,10 +14,22 @@ import types
 
 REF_ROOT = os.environ.get("MPL_REFERENCE_ROOT", "/root/reference")
 MODEL_FILE = os.path.join(REF_ROOT, "MPL/lib/models/multiview_mpl.py")
+# byte-for-byte copy of the model file made by oracle/stage_reference.py (git-ignored; travels to the GPU box)
+STAGE_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+STAGED_MODEL_FILE = os.path.join(STAGE_ROOT, "MPL/lib/models/multiview_mpl.py")
 
 
 def available() -> bool:
+    """The whole reference checkout is mounted (build container)."""
     return os.path.isfile(MODEL_FILE)
+
+
+def model_file() -> str | None:
+    """The unmodified reference model file: from the checkout, else the staged copy (GPU box), else None."""
+    for f in (MODEL_FILE, STAGED_MODEL_FILE):
+        if os.path.isfile(f):
+            return f
+    return None
 
 
 def _install_stubs():
@@ -79,10 +91,11 @@ def load_model_module():
     """The reference `multiview_mpl` python module, loaded from its file unmodified."""
     global _cached
     if _cached is None:
-        if not available():
+        f = model_file()
+        if f is None:
             raise FileNotFoundError(MODEL_FILE)
         _install_stubs()
-        spec = importlib.util.spec_from_file_location("ref_multiview_mpl", MODEL_FILE)
+        spec = importlib.util.spec_from_file_location("ref_multiview_mpl", f)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         _cached = mod

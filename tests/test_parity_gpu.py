@@ -194,6 +194,42 @@ def test_layernorm_fusion_on_and_off_agree_with_the_reference(name):
     assert rel_err(outs[1], outs[0].astype(np.float64)) <= TOL["bf16"]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_cuda_graph_small_batch_path_equals_the_plain_path(precision):
+    """Batches up to `graph_batch` poses (the reference runner's TEST.BATCH_SIZE = 256) are captured once per batch size as a
+    CUDA graph and replayed: same numbers as the kernel-by-kernel path, one capture, then replays -- also for fresh input
+    tensors at new addresses (the module stages them in persistent buffers), host tensors and the packed layout."""
+    case = CASES["flag_hm0flags_small"]
+    cfg = spec.make_config(**case["kw"])
+    weights = synth.named_weights(spec.param_spec(cfg), seed=3)
+    rig = synth.make_rig(cfg.V)
+    plain = build_module(case["kw"], weights, precision, graph_batch=0)
+    graph = build_module(case["kw"], weights, precision, graph_batch=512)
+    outs = []
+    for seed in (1, 2, 3):
+        batch = synth.make_batch(256, rig, seed=seed)
+        a = run_module(plain, batch)[0]
+        b = run_module(graph, batch)[0]
+        np.testing.assert_array_equal(a, b)
+        outs.append(b)
+    assert not np.array_equal(outs[0], outs[1])                       # the replays really consumed the new inputs
+    assert plain.graph_stats() == (0, 0)
+    assert graph.graph_stats() == (1, 2)
+    batch = synth.make_batch(256, rig, seed=4)
+    np.testing.assert_array_equal(run_module(graph, batch, packed=True)[0], run_module(plain, batch)[0])   # second layout: second graph
+    V = cfg.V
+    host = [[torch.from_numpy(np.ascontiguousarray(batch[k][:, v])) for v in range(V)] for k in ("poses", "rays", "centers")]
+    with torch.no_grad():
+        out = graph(host[0], rays=host[1], centers=host[2])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), run_module(plain, batch)[0])
+    big = synth.make_batch(600, rig, seed=5)                          # above graph_batch: plain path, no new capture
+    caps = graph.graph_stats()[0]
+    np.testing.assert_array_equal(run_module(graph, big)[0], run_module(plain, big)[0])
+    assert graph.graph_stats()[0] == caps
+    assert rel_err(outs[0], oracle_outputs(cfg, weights, synth.make_batch(256, rig, seed=1))[0]) <= TOL[precision]
+
+
 def test_native_library_is_what_ran():
     maps = open("/proc/self/maps").read()
     assert "libmpl_b200.so" in maps
