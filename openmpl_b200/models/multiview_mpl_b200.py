@@ -167,18 +167,37 @@ class MultiView_MPL(nn.Module):
         # getattr, not _parameters: in a DataParallel replica the parameters are plain tensor attributes
         return getattr(mod, parts[-1])
 
+    def _stamp(self):
+        """Cheap fingerprint of the ORIGINAL module's parameters (DataParallel re-broadcasts fresh copies to the replicas on
+        every call, which must not trigger a repack while the master's weights are unchanged): the invalidate() epoch, every
+        tensor's in-place version counter, and the storage addresses of a few sentinel tensors (a `.to()` / `.cuda()` moves
+        them all).  ~0.1 ms for the 800 tensors of `hm_0` -- it runs on every forward, including the 256-pose ones."""
+        origin = self._origin[0]
+        slots = origin.__dict__.get("_slots")
+        if slots is None:                                   # (container dict, key) of every tensor, resolved once
+            slots = []
+            for name in origin._names:
+                mod = origin
+                parts = name.split(".")
+                for p in parts[:-1]:
+                    mod = mod._modules[p]
+                d = mod._parameters if parts[-1] in mod._parameters else mod._buffers
+                slots.append((d, parts[-1]))
+            origin.__dict__["_slots"] = slots
+        ts = [d[k] for d, k in slots]
+        n = len(ts)
+        return (origin._epoch[0], tuple([t._version for t in ts]),
+                tuple(ts[i].data_ptr() for i in (0, n // 3, (2 * n) // 3, n - 1)), tuple(ts[i].device for i in (0, n - 1)))
+
     def _state(self, device):
-        """Per-device packed weights, repacked whenever a parameter's storage or version changes."""
+        """Per-device packed weights, repacked whenever the fingerprint of the parameters changes (see invalidate())."""
         L = _lib.lib()
         h = self._get_handle(device.index)
-        tensors = [self._tensor(n) for n in self._names]
-        # The stamp is taken on the parameters of the ORIGINAL module: DataParallel re-broadcasts fresh copies to the
-        # replicas on every call, which must not trigger a repack while the master's weights are unchanged.
-        origin = self._origin[0]
-        stamp = (origin._epoch[0],) + tuple((t.data_ptr(), t._version) for t in (origin._tensor(n) for n in self._names))
+        stamp = self._stamp()
         with self._lock:
             st = self._dev.get(device.index)
             if st is None or st["stamp"] != stamp:
+                tensors = [self._tensor(n) for n in self._names]
                 srcs = [t if (t.device == device and t.dtype in (torch.float32, torch.long) and t.is_contiguous())
                         else t.to(device=device, dtype=torch.long if t.dtype == torch.long else torch.float32).contiguous()
                         for t in tensors]
@@ -189,7 +208,12 @@ class MultiView_MPL(nn.Module):
                 _lib.check(L.mpl_pack_weights(h, ptrs, len(srcs), packed.data_ptr(), nbytes, stream))
                 for s in srcs:                      # temporaries must outlive the enqueued copies
                     s.record_stream(torch.cuda.current_stream(device))
-                st = {"packed": packed, "stamp": stamp, "workspace": st["workspace"] if st else None}
+                new = {"packed": packed, "stamp": stamp, "workspace": st["workspace"] if st else None}
+                if st is not None:
+                    for k in ("static", "copy_stream"):
+                        if k in st:
+                            new[k] = st[k]
+                st = new
                 self._dev[device.index] = st
             return st
 
@@ -198,8 +222,9 @@ class MultiView_MPL(nn.Module):
 
         The packed blob is refreshed automatically when a parameter is replaced or modified through autograd-visible
         in-place operations (`p.copy_()`, `load_state_dict`, optimizer steps: they bump `Tensor._version`).  Writes that
-        go through `p.data` (`p.data.copy_()`, `dist.broadcast(p.data)`, EMA updates on `.data`) bump nothing PyTorch
-        exposes -- call `invalidate()` after those.  `dist.broadcast_state` and `load_state_dict` already do."""
+        go through `p.data` (`p.data.copy_()`, `dist.broadcast(p.data)`, EMA updates on `.data`, `p.data = other`) bump
+        nothing PyTorch exposes, and neither does re-assigning a parameter object -- call `invalidate()` after those.
+        `dist.broadcast_state`, `load_state_dict` and moving the module (`.to()`, `.cuda()`) are detected."""
         self._origin[0]._epoch[0] += 1
         return self
 
@@ -242,6 +267,8 @@ class MultiView_MPL(nn.Module):
                 new.__dict__[k] = [new]
             elif k == "_epoch":
                 new.__dict__[k] = [0]
+            elif k == "_slots":
+                continue
             elif k == "_lock":
                 new.__dict__[k] = threading.Lock()
             else:
