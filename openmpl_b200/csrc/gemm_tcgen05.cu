@@ -347,11 +347,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0 && is_leader) {
+    // The whole warp walks the loops convergently (barrier waits, descriptor arithmetic on warp-uniform values -> uniform
+    // registers, no per-instruction ELECT / R2UR chains); one elected lane issues the tcgen05.mma / commit instructions.
+    // Operand descriptors advance by adding to the 14-bit (address >> 4) field: +2 per 32-byte UMMA K step.
+    if (is_leader) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint64_t desc0 = make_smem_desc(smem_base);
       for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int n_blk = (int)(tile % n_tiles);
         int nt0, n_size;
@@ -364,29 +368,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t b_src = a_src + C::OPS * C::A_BYTES;
+          const uint64_t adesc0 = desc0 + (uint64_t)((stage * C::STAGE_BYTES) >> 4);
+          const uint64_t bdesc0 = adesc0 + (uint64_t)((C::OPS * C::A_BYTES) >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < KB_BYTES / UMMA_K_BYTES; ++k) {
-            const uint64_t adesc = make_smem_desc(a_src + k * UMMA_K_BYTES);
-            const uint64_t bdesc = make_smem_desc(b_src + k * UMMA_K_BYTES);
-            if constexpr (SPLIT) {
-              // small cross terms first, the hi.hi product last (the lo.lo term, 2^-18 relative, is dropped)
-              const uint64_t adesc2 = make_smem_desc(a_src + C::A_BYTES + k * UMMA_K_BYTES);
-              const uint64_t bdesc2 = make_smem_desc(b_src + C::B_BYTES + k * UMMA_K_BYTES);
-              ptx::umma<CG, 0>(d_tmem, adesc, bdesc2, idesc, (kb | k) != 0 ? 1u : 0u);
-              ptx::umma<CG, 0>(d_tmem, adesc2, bdesc, idesc, 1u);
-              ptx::umma<CG, 0>(d_tmem, adesc, bdesc, idesc, 1u);
-            } else {
-              ptx::umma<CG, 0>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < KB_BYTES / UMMA_K_BYTES; ++k) {
+              const uint64_t adesc = adesc0 + (uint64_t)(k * (UMMA_K_BYTES >> 4));
+              const uint64_t bdesc = bdesc0 + (uint64_t)(k * (UMMA_K_BYTES >> 4));
+              if constexpr (SPLIT) {
+                // small cross terms first, the hi.hi product last (the lo.lo term, 2^-18 relative, is dropped)
+                const uint64_t adesc2 = adesc + (uint64_t)(C::A_BYTES >> 4);
+                const uint64_t bdesc2 = bdesc + (uint64_t)(C::B_BYTES >> 4);
+                ptx::umma<CG, 0>(d_tmem, adesc, bdesc2, idesc, (kb | k) != 0 ? 1u : 0u);
+                ptx::umma<CG, 0>(d_tmem, adesc2, bdesc, idesc, 1u);
+                ptx::umma<CG, 0>(d_tmem, adesc, bdesc, idesc, 1u);
+              } else {
+                ptx::umma<CG, 0>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
+            else ptx::umma_commit_pair(empty_bar(stage), 0x3);
+            if (kb == num_kb - 1) {
+              if constexpr (CG == 1) ptx::umma_commit(tfull_bar(acc));
+              else ptx::umma_commit_pair(tfull_bar(acc), 0x3);
             }
           }
-          if constexpr (CG == 1) ptx::umma_commit(empty_bar(stage));
-          else ptx::umma_commit_pair(empty_bar(stage), 0x3);
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        if constexpr (CG == 1) ptx::umma_commit(tfull_bar(acc));
-        else ptx::umma_commit_pair(tfull_bar(acc), 0x3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }

@@ -794,25 +794,39 @@ __global__ void __launch_bounds__(288) attention_views_kernel(const T* __restric
         for (int o = V / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(mask, sum, o);
         if (live) prob[idx] = e / sum;
       }
-    } else
-    // H * V query rows: sum the head's chunk partials, softmax over the V keys
-    for (int r = threadIdx.x; r < H * V; r += blockDim.x) {
-      const int h = r / V, i = r % V;
-      float sc[V];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
+    } else {
+      // V = 3, 5, 6, 7 (CMU Panoptic: 5 views): the same one-thread-per-(head, query, key) spread, the row's V scores
+      // exchanged through shared memory instead of shuffles (a separate compile-time path: the V = 4 kernel is untouched)
+      const int total = H * V * V;
+      for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int h = idx / (V * V), ij = idx % (V * V);
         float a = 0.f;
-        for (int cc = 0; cc < cph; ++cc) a += part[(h * cph + cc) * (V * V) + i * V + j];
-        sc[j] = a * scale;
-        mx = fmaxf(mx, sc[j]);
+        const float* pp = part + h * cph * (V * V) + ij;
+        if (CPH) {
+#pragma unroll
+          for (int cc = 0; cc < CPH; ++cc) a += pp[cc * (V * V)];
+        } else {
+          for (int cc = 0; cc < cph; ++cc) a += pp[cc * (V * V)];
+        }
+        prob[idx] = a * scale;
       }
-      float sum = 0.f;
+      __syncthreads();
+      float pr[V];  // this thread's probabilities: the launcher guarantees blockDim >= H * V, i.e. at most V rounds
+      int n_mine = 0;
+      for (int idx = threadIdx.x; idx < total; idx += blockDim.x, ++n_mine) {
+        const float* row = prob + (idx / V) * V;
+        float mx = row[0];
 #pragma unroll
-      for (int j = 0; j < V; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
-      const float inv = 1.0f / sum;
+        for (int j = 1; j < V; ++j) mx = fmaxf(mx, row[j]);
+        float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < V; ++j) prob[h * (V * V) + i * V + j] = sc[j] * inv;
+        for (int j = 0; j < V; ++j) sum += expf(row[j] - mx);
+        if (n_mine < (int)(sizeof(pr) / sizeof(float))) pr[n_mine] = expf(prob[idx] - mx) / sum;
+      }
+      __syncthreads();  // every score has been read
+      n_mine = 0;
+      for (int idx = threadIdx.x; idx < total; idx += blockDim.x, ++n_mine)
+        if (n_mine < (int)(sizeof(pr) / sizeof(float))) prob[idx] = pr[n_mine];
     }
     __syncthreads();
     const int h = c / cph;

@@ -1,9 +1,9 @@
-# usage: bash scripts/gpu_ab.sh TAG "ENV1=.. ENV2=.." "ENV..." ...   -- bench (no tests) under several env settings
+# usage: bash scripts/gpu_ab.sh TAG "ENV1=.. ENV2=.." "ENV..." ...   -- bench (no tests) under several env settings (same box: A/B)
 TAG=$1; shift
 mkdir -p gpurun_out
 i=0
 for envs in "$@"; do
-  env $envs timeout -k 5 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_$i.json 2> gpurun_out/${TAG}_$i.err
+  env $envs timeout -k 5 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras --parity-poses 64 > gpurun_out/${TAG}_$i.json 2> gpurun_out/${TAG}_$i.err
   python - <<PY
 import json
 try:
