@@ -92,6 +92,10 @@ typedef struct MplDesc {
                              the next GEMM's operand and per-row (sum, sum^2); the next GEMM multiplies the raw rows by
                              W diag(gamma) and applies (mean, rstd) in its epilogue */
   int32_t gemm_cta_group; /* 0 / 2: CTA pair per 256x256 tile (cta_group::2, cluster 2x1x1); 1: one CTA per 128x256 tile */
+  int32_t chunk_streams;  /* 0 / 1: one pose chunk at a time on the caller's stream (default).  2: batches of >= 16384 poses
+                             run as two interleaved pose chunks on two internal streams (forked from / joined to the
+                             caller's stream) so that kernels of one chunk may overlap those of the other; the
+                             workspace doubles.  Same results; measured neutral on B200 (profiles/r2_experiments.md) */
 } MplDesc;
 
 typedef struct MplModel MplModel;          /* opaque host-side handle */
@@ -156,7 +160,9 @@ int64_t mpl_last_launch_count(const MplModel* m);
 /* Optional per-launch timing with CUDA events on the caller's stream (the reference's only profiling hook is an
  * unsynchronised time.time() around the model call, core/function_mpl.py:346-351).  While enabled, every kernel
  * launch of mpl_forward is bracketed by two events; mpl_profile_collect waits for the last forward's events and
- * returns milliseconds and launch counts per kernel category (mpl_profile_category_name). */
+ * returns milliseconds and launch counts per kernel category (mpl_profile_category_name).  enabled = 1 profiles the
+ * production schedule (two chunks in flight: launches of the two streams overlap, so the per-category times sum to more
+ * than the step); enabled = 2 additionally runs one chunk at a time, so the times add up to the (slower) serial step. */
 int mpl_set_profile(MplModel* m, int enabled);
 int mpl_profile_categories(void);
 const char* mpl_profile_category_name(int category);

@@ -46,10 +46,10 @@ class MplDesc(ctypes.Structure):
                  ("depth", c_int32), ("num_heads", c_int32), ("num_views", c_int32), ("hidden_dim", c_int32),
                  ("mlp_ratio", c_float), ("qk_scale", c_float)]
                 + [(f, c_int32) for f in _DESC_FLAGS] + [("precision", c_int32), ("ln_fusion", c_int32),
-                                                         ("gemm_cta_group", c_int32)])
+                                                         ("gemm_cta_group", c_int32), ("chunk_streams", c_int32)])
 
 
-def make_desc(kw: dict, precision: str, ln_fusion: bool = True, gemm_cta_group: int = 2) -> MplDesc:
+def make_desc(kw: dict, precision: str, ln_fusion: bool = True, gemm_cta_group: int = 2, chunk_streams: int = 1) -> MplDesc:
     """Constructor kwargs of MultiView_MPL (multiview_mpl.py:95-117) -> MplDesc."""
     if precision not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
@@ -64,6 +64,7 @@ def make_desc(kw: dict, precision: str, ln_fusion: bool = True, gemm_cta_group: 
     d.precision = PRECISIONS[precision]
     d.ln_fusion = int(bool(ln_fusion))
     d.gemm_cta_group = int(gemm_cta_group)
+    d.chunk_streams = int(chunk_streams)
     return d
 
 

@@ -36,6 +36,18 @@ constexpr int BM = 128;          // accumulator rows per CTA (TMEM lanes)
 constexpr int BN = 256;          // accumulator columns per tile
 constexpr int KB_BYTES = 128;    // bytes of K per stage row = one 128B swizzle span
 constexpr int UMMA_K_BYTES = 32; // bytes of K per tcgen05.mma
+// Shared-memory budget of the LayerNorm-fused bf16 kernels (CTA pairs).  Defaults: all of shared memory.  The smaller settings
+// (5 / 1 / 4: ~193 KB, leaving room for CTAs of a light kernel of another stream beside the persistent GEMM CTA) were measured
+// together with two pose chunks in flight on two streams (MplDesc.chunk_streams = 2): no gain, see profiles/r2_experiments.md.
+#ifndef MPL_LN_STAGES
+#define MPL_LN_STAGES 6      // QKV / fc1 operand stages
+#endif
+#ifndef MPL_E6_SLOTS_EVEN
+#define MPL_E6_SLOTS_EVEN 2  // proj: residual slots of an even-group warp
+#endif
+#ifndef MPL_E7_STAGES
+#define MPL_E7_STAGES 5      // fc2 operand stages
+#endif
 constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter: even / odd 64-column groups
 constexpr int TMEM_COLS = 512;
 
@@ -56,12 +68,17 @@ struct Cfg {
   static constexpr bool RESID = (KIND == 0) && (EPI == 6 || EPI == 7);
   static constexpr int EPI_WARPS = NUM_EPI_WARPS;
   static constexpr int THREADS = (4 + EPI_WARPS) * 32;
-  static constexpr int SLOTS_EVEN = !RESID ? 0 : (EPI == 6 ? 2 : 1);  // slots of an even-group warp (odd-group warps: 1)
+  // Register cap.  The LayerNorm-fused bf16 kernels (the bench path) need no more than 112 registers (no spills): 42 k of the
+  // SM's 64 k, which leaves room for CTAs of a light kernel from another stream beside the persistent GEMM CTA; the other
+  // instantiations take what a single CTA per SM may use.
+  static constexpr int MAXREG = (KIND == 0 && EPI >= 4) ? 112 : 168;
+  static constexpr int SLOTS_EVEN = !RESID ? 0 : (EPI == 6 ? MPL_E6_SLOTS_EVEN : 1);  // slots of an even-group warp (odd-group warps: 1)
   static constexpr int RING_SLOTS = !RESID ? 0 : 4 * SLOTS_EVEN + 4;
   static constexpr int SLOT_BYTES = 8192;
   static constexpr int RING_BYTES = RING_SLOTS * SLOT_BYTES;
   static constexpr int STAGES = (KIND == 1) ? ((CG == 1) ? 2 : 3)
-                                : (EPI == 6) ? ((CG == 1) ? 2 : 4) : (EPI == 7) ? ((CG == 1) ? 3 : 5) : ((CG == 1) ? 4 : 6);
+                                : (EPI == 6) ? ((CG == 1) ? 2 : 4) : (EPI == 7) ? ((CG == 1) ? 3 : MPL_E7_STAGES)
+                                : ((CG == 1) ? 4 : (EPI >= 4 ? MPL_LN_STAGES : 6));
   static constexpr int STAGING_BYTES = RESID ? 0 : EPI_WARPS * 4096;  // per epilogue warp: one 32-row x 128-byte output box
   // slot and mbarrier phase of the n-th residual box (n = 0, 1, ...) of epilogue warp (lane quarter q, group parity `odd`)
   static constexpr uint32_t SE = SLOTS_EVEN ? SLOTS_EVEN : 1;
@@ -213,7 +230,7 @@ __device__ __forceinline__ void stage_row_f16(uint32_t box, int lane, int j0, co
 }
 
 template <int CG, int KIND, int EPI>
-__global__ void __launch_bounds__((Cfg<CG, EPI, KIND>::THREADS), 1)
+__global__ void __maxnreg__((Cfg<CG, EPI, KIND>::MAXREG))
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmY2,
@@ -572,6 +589,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       for (int c = half * 64; c < n_size; c += 128) {
+        if constexpr (OUT_BF16) {
+          // one 64-column bf16 box per step, filled in two 32-column halves (one accumulator chunk in registers at a time:
+          // ~100 registers per thread, which leaves room for CTAs of other kernels on the SM -- see mpl_forward)
+          constexpr bool GELU = (EPI == 1 || EPI == 5);
+          const bool f16_out = (ln.flags & 4) != 0;
+          if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has finished reading the box
+          __syncwarp();
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            uint32_t va[32];
+            ptx::tmem_ld_32x32(taddr + c + 32 * hb, va);
+            ptx::tmem_ld_wait();
+            float fa[32];
+            if (GELU && f16_out) {  // activation deferred to the packed-half2 stage
+              epilogue_math<KIND, EPI == 5 ? 4 : 0>(va, bias, ncol0 + c + 32 * hb, N, fa, ln.colsum, mu, rstd);
+              stage_row_f16<GELU>(box, lane, 4 * hb, fa);
+            } else {
+              epilogue_math<KIND, EPI>(va, bias, ncol0 + c + 32 * hb, N, fa, ln.colsum, mu, rstd);
+              if (f16_out) stage_row_f16<false>(box, lane, 4 * hb, fa);
+              else stage_row_bf16(box, lane, 4 * hb, fa);
+            }
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmY, box, ncol0 + c, row0);
+            ptx::bulk_commit();
+          }
+          continue;
+        }
         uint32_t va[32], vb[32];
         ptx::tmem_ld_32x32(taddr + c, va);
         ptx::tmem_ld_32x32(taddr + c + 32, vb);
@@ -593,33 +640,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ptx::tma_store_2d(plane ? &tmY2 : &tmY, box, ncol0 + c, row0);
               ptx::bulk_commit();
             }
-          }
-        } else if constexpr (OUT_BF16) {
-          // one 64-column bf16 box per step
-          float fa[32], fb[32];
-          constexpr bool GELU = (EPI == 1 || EPI == 5);
-          const bool f16_out = KIND == 0 && (ln.flags & 4);
-          if (GELU && f16_out) {  // activation deferred to the packed-half2 stage
-            epilogue_math<KIND, EPI == 5 ? 4 : 0>(va, bias, ncol0 + c, N, fa, ln.colsum, mu, rstd);
-            epilogue_math<KIND, EPI == 5 ? 4 : 0>(vb, bias, ncol0 + c + 32, N, fb, ln.colsum, mu, rstd);
-          } else {
-            epilogue_math<KIND, EPI>(va, bias, ncol0 + c, N, fa, ln.colsum, mu, rstd);
-            epilogue_math<KIND, EPI>(vb, bias, ncol0 + c + 32, N, fb, ln.colsum, mu, rstd);
-          }
-          if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has finished reading the box
-          __syncwarp();
-          if (f16_out) {
-            stage_row_f16<GELU>(box, lane, 0, fa);
-            stage_row_f16<GELU>(box, lane, 4, fb);
-          } else {
-            stage_row_bf16(box, lane, 0, fa);
-            stage_row_bf16(box, lane, 4, fb);
-          }
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            ptx::tma_store_2d(&tmY, box, ncol0 + c, row0);
-            ptx::bulk_commit();
           }
         } else {
           // two 32-column fp32 boxes per step, one after the other through the same staging box

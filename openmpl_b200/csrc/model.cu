@@ -87,6 +87,10 @@ struct MplModel {
     uint64_t last_used;
   };
   std::vector<GraphEntry> graphs;
+  // large batches: two pose chunks in flight on two internal streams (see plan_chunks)
+  int chunk_streams = 1;
+  cudaStream_t lane_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   int64_t graph_max_batch = 0;   // 0: off (mpl_set_graph_batch)
   cudaStream_t cap_stream = nullptr;
   uint64_t graph_clock = 0;
@@ -96,6 +100,7 @@ struct MplModel {
   std::vector<mpl::BlockW> fpt_blocks;
   // optional per-launch CUDA-event profiling (bench.py's roofline numbers come from here)
   bool profile = false;
+  bool profile_serial = false;  // profiling with one chunk at a time: per-launch times that add up to the step
   struct ProfRec { int cat; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -799,6 +804,7 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
   // LayerNorm fusion: the residual-emit epilogue works on whole 32-column chunks, launch_ln_prep on float4 rows
   m->ln_fused = m->fpt_tc && d.precision == MPL_PREC_BF16 && d.ln_fusion != 0 && m->fpt_dim % 32 == 0 && m->fpt_dim <= 32 * 4 * 17;
   m->cta_group = (d.gemm_cta_group == 1) ? 1 : 2;
+  m->chunk_streams = (d.chunk_streams == 2) ? 2 : 1;
   m->ln_slots = m->ln_fused ? gemm_ln_slots(m->fpt_dim) : 0;
   build_tables(m);
   *out = m;
@@ -810,6 +816,11 @@ void mpl_destroy(MplModel* m) {
   if (m == nullptr) return;
   for (auto& e : m->graphs) cudaGraphExecDestroy(e.exec);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  for (int k = 0; k < 2; ++k) {
+    if (m->lane_stream[k]) cudaStreamDestroy(m->lane_stream[k]);
+    if (m->ev_join[k]) cudaEventDestroy(m->ev_join[k]);
+  }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   for (cudaEvent_t e : m->ev_pool) cudaEventDestroy(e);
   delete m;
 }
@@ -820,6 +831,7 @@ int mpl_set_profile(MplModel* m, int enabled) {
     return MPL_ERR_INVALID_ARGUMENT;
   }
   m->profile = enabled != 0;
+  m->profile_serial = enabled == 2;  // 2: also run the chunks one after the other (times that add up); 1: as in production
   m->prof.clear();
   m->ev_used = 0;
   return MPL_OK;
@@ -992,10 +1004,30 @@ int mpl_set_chunk_poses(MplModel* m, int64_t chunk) {
   return MPL_OK;
 }
 
+// How a batch is cut into chunks.  Every pose is independent, so a batch may be processed in any number of chunks without
+// changing a result.  Large batches run as TWO interleaved chunk sequences on two internal streams: while one chunk is
+// inside a tensor-bound GEMM (one persistent CTA per SM, registers and shared memory capped so that more fits), the HBM-bound
+// kernels of the other chunk (view attention, ln_prep, head) become resident beside it, and the next GEMM's CTAs start on
+// SMs the previous one has already left -- the tail of every launch overlaps the head of the next.
+constexpr int64_t kDualMinBatch = 16384;
+struct ChunkPlan {
+  int64_t chunk;
+  int lanes;
+};
+static ChunkPlan plan_chunks(const MplModel* m, int64_t batch) {
+  ChunkPlan p{std::min<int64_t>(std::max<int64_t>(batch, 1), m->chunk), 1};
+  if (m->chunk_streams == 2 && batch >= kDualMinBatch && !m->profile_serial) {
+    if (batch <= m->chunk) p.chunk = (batch + 1) / 2;  // one chunk's worth of poses: two halves
+    p.lanes = 2;
+  }
+  return p;
+}
+
 size_t mpl_workspace_bytes(const MplModel* m, int64_t max_batch) {
   if (m == nullptr || max_batch < 0) return 0;
   const int64_t Bc = std::min<int64_t>(std::max<int64_t>(max_batch, 1), m->chunk);
-  return layout_workspace(m, Bc, nullptr).bytes;
+  const int lanes = (m->chunk_streams == 2 && max_batch >= kDualMinBatch) ? 2 : 1;  // an upper bound for every smaller batch
+  return lanes * layout_workspace(m, Bc, nullptr).bytes;
 }
 
 int mpl_forward(MplModel* m, const void* packed, const float* const* poses, const float* const* rays,
@@ -1033,13 +1065,16 @@ int mpl_forward(MplModel* m, const void* packed, const float* const* poses, cons
   m->launches = 0;
   if (m->profile) { m->prof.clear(); m->ev_used = 0; }
   if (batch == 0) return MPL_OK;
-  const int64_t Bc_max = std::min<int64_t>(batch, m->chunk);
-  const size_t need = layout_workspace(m, Bc_max, nullptr).bytes;
+  const ChunkPlan plan = plan_chunks(m, batch);
+  const int64_t Bc_max = plan.chunk;
+  const size_t lane_bytes = layout_workspace(m, Bc_max, nullptr).bytes;
+  const size_t need = plan.lanes * lane_bytes;
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("mpl_forward: workspace has %zu bytes, %zu needed for batch %lld", workspace_bytes, need, (long long)batch);
     return MPL_ERR_WORKSPACE;
   }
-  const Workspace w = layout_workspace(m, Bc_max, reinterpret_cast<uint8_t*>(workspace));
+  const Workspace wl[2] = {layout_workspace(m, Bc_max, reinterpret_cast<uint8_t*>(workspace)),
+                           layout_workspace(m, Bc_max, reinterpret_cast<uint8_t*>(workspace) + (plan.lanes == 2 ? lane_bytes : 0))};
   Packed P{m, reinterpret_cast<const uint8_t*>(packed)};
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int out_dim = 3 * m->J;
@@ -1093,8 +1128,29 @@ int mpl_forward(MplModel* m, const void* packed, const float* const* poses, cons
     MPL_CUDA(cudaGraphLaunch(exec, reinterpret_cast<cudaStream_t>(stream)));
     return MPL_OK;
   };
-  for (int64_t b0 = 0; b0 < batch; b0 += m->chunk) {
-    const int64_t Bc = std::min<int64_t>(m->chunk, batch - b0);
+  cudaStream_t lane_s[2] = {s, s};
+  if (plan.lanes == 2) {
+    // fork: both lane streams wait for everything enqueued on the caller's stream so far
+    for (int k = 0; k < 2; ++k) {
+      if (m->lane_stream[k] == nullptr) MPL_CUDA(cudaStreamCreateWithFlags(&m->lane_stream[k], cudaStreamNonBlocking));
+      if (m->ev_join[k] == nullptr) MPL_CUDA(cudaEventCreateWithFlags(&m->ev_join[k], cudaEventDisableTiming));
+      lane_s[k] = m->lane_stream[k];
+    }
+    if (m->ev_fork == nullptr) MPL_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    MPL_CUDA(cudaEventRecord(m->ev_fork, s));
+    for (int k = 0; k < 2; ++k) MPL_CUDA(cudaStreamWaitEvent(lane_s[k], m->ev_fork, 0));
+  }
+  auto join = [&]() -> int {  // the caller's stream continues after both lanes
+    if (plan.lanes == 2)
+      for (int k = 0; k < 2; ++k) {
+        MPL_CUDA(cudaEventRecord(m->ev_join[k], lane_s[k]));
+        MPL_CUDA(cudaStreamWaitEvent(s, m->ev_join[k], 0));
+      }
+    return MPL_OK;
+  };
+  int lane = 0;
+  for (int64_t b0 = 0; b0 < batch; b0 += plan.chunk, lane ^= 1) {
+    const int64_t Bc = std::min<int64_t>(plan.chunk, batch - b0);
     const float* pp[kMaxViews];
     const float* rp[kMaxViews];
     const float* cp[kMaxViews];
@@ -1105,9 +1161,14 @@ int mpl_forward(MplModel* m, const void* packed, const float* const* poses, cons
     }
     const int st = forward_chunk(m, P, pp, rays ? rp : nullptr, centers ? cp : nullptr, pose_stride, center_stride,
                                  out + b0 * out_dim, aux1 ? aux1 + b0 * out_dim : nullptr, aux2 ? aux2 + b0 * out_dim : nullptr, Bc,
-                                 w, s);
-    if (st != MPL_OK) return try_graph ? end_capture(st) : st;
+                                 wl[plan.lanes == 2 ? lane : 0], lane_s[plan.lanes == 2 ? lane : 0]);
+    if (st != MPL_OK) {
+      join();
+      return try_graph ? end_capture(st) : st;
+    }
   }
+  const int jst = join();
+  if (jst != MPL_OK) return try_graph ? end_capture(jst) : jst;
   return try_graph ? end_capture(MPL_OK) : MPL_OK;
   MPL_API_END
 }

@@ -108,7 +108,7 @@ class MultiView_MPL(nn.Module):
                  head_kadkhod=False,
                  hidden_dim=1024,
                  FPT_blocks_view_keypoint_tokens=False, *, precision=None, ln_fusion=True, gemm_cta_group=2,
-                 graph_batch=2048):
+                 graph_batch=2048, chunk_streams=1):
         super().__init__()
         kw = {k: v for k, v in locals().items() if k in CTOR_DEFAULTS}
         self.cfg = make_config(**kw)
@@ -119,6 +119,9 @@ class MultiView_MPL(nn.Module):
         # batches of at most `graph_batch` poses (the reference runner's 256, valid_mpl.py:205-210) replay one captured CUDA
         # graph per batch size instead of ~130 kernel launches (mpl_set_graph_batch); 0 = always launch kernel by kernel
         self.graph_batch = int(graph_batch)
+        # chunk_streams=2: batches of >= 16384 poses run as two interleaved pose chunks on two internal streams
+        # (MplDesc.chunk_streams; measured neutral on B200, profiles/r2_experiments.md, hence off by default)
+        self.chunk_streams = int(chunk_streams)
         self.num_joints, self.num_views, self.embed_dim_ratio = num_joints, num_views, embed_dim_ratio
         self._spec = param_spec(self.cfg)
         for name, (shape, kind, fan_in) in self._spec.items():
@@ -140,7 +143,7 @@ class MultiView_MPL(nn.Module):
             index = torch.cuda.current_device() if torch.cuda.is_available() else -1
         if index not in self._h.ptrs:
             L = _lib.lib()
-            desc = _lib.make_desc(self.cfg.kw, self.precision, self.ln_fusion, self.gemm_cta_group)
+            desc = _lib.make_desc(self.cfg.kw, self.precision, self.ln_fusion, self.gemm_cta_group, self.chunk_streams)
             h = ctypes.c_void_p()
             _lib.check(L.mpl_create(ctypes.byref(desc), ctypes.byref(h)))
             n = L.mpl_num_params(h)
@@ -237,9 +240,10 @@ class MultiView_MPL(nn.Module):
         """Poses per forward chunk (the workspace stops growing there)."""
         return int(_lib.lib().mpl_chunk_poses(self._get_handle()))
 
-    def set_profile(self, enabled: bool):
-        """Bracket every kernel launch of the next forwards with CUDA events (see `profile()`)."""
-        _lib.check(_lib.lib().mpl_set_profile(self._get_handle(), int(bool(enabled))))
+    def set_profile(self, enabled, serial: bool = False):
+        """Bracket every kernel launch of the next forwards with CUDA events (see `profile()`).  serial=True also runs the
+        pose chunks one after the other instead of two in flight, so that the per-category times add up."""
+        _lib.check(_lib.lib().mpl_set_profile(self._get_handle(), (2 if serial else 1) if enabled else 0))
 
     def profile(self) -> dict:
         """{category: (milliseconds, launches)} of the last forward run with profiling enabled."""
@@ -579,6 +583,7 @@ class MultiView_MPL_G(nn.Module):
             ln_fusion=kwargs.get("ln_fusion", True),
             gemm_cta_group=kwargs.get("gemm_cta_group", 2),
             graph_batch=kwargs.get("graph_batch", 2048),
+            chunk_streams=kwargs.get("chunk_streams", 1),
         )
 
     def forward(self, x, centers=None, rays=None):
