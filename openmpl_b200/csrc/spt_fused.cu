@@ -239,7 +239,17 @@ __device__ __forceinline__ __half2 ex2_h2(__half2 x) {
 // applications; keys are walked in two passes (max, then exp2 / sum / PV with the scores recomputed), fp16 partial
 // sums flushed into fp32 every 17 keys.  Rows come from and go back to the fp32 token buffer in place.
 template <bool PRECISE, bool GROUPED>
-__global__ void __launch_bounds__(THREADS, PRECISE ? 1 : 2) spt_fused_kernel(const SptArgs args) {
+__device__ __forceinline__ void spt_fused_body(const SptArgs& args);
+
+// packed-half2 forms: two CTAs per SM (96 registers); PRECISE: one CTA per SM.  168 registers is the ceiling for 288 threads
+// (the register file is handed out in units of four warps: 9 warps count as 12 -> 65536 / 384; a 224-register build
+// compiles without spills but cannot launch), so the split-operand form lives with ~740 bytes of spills
+template <bool GROUPED>
+__global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel_fast(const SptArgs args) { spt_fused_body<false, GROUPED>(args); }
+__global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel_precise(const SptArgs args) { spt_fused_body<true, false>(args); }
+
+template <bool PRECISE, bool GROUPED>
+__device__ __forceinline__ void spt_fused_body(const SptArgs& args) {
   static_assert(!(PRECISE && GROUPED), "the grouped (keypoint-token FPT) form exists for the packed-half2 arithmetic only");
   using SM = Smem<PRECISE>;
   constexpr int LW = SM::LAYER;
@@ -818,7 +828,7 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
   static std::atomic<unsigned char> attr_set[64][2];
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
-  auto kern = precise ? spt_fused_kernel<true, false> : spt_fused_kernel<false, false>;
+  auto kern = precise ? spt_fused_kernel_precise : spt_fused_kernel_fast<false>;
   const int smem_bytes = precise ? Smem<true>::TOTAL : Smem<false>::TOTAL;
   if (dev < 0 || dev >= 64 || !attr_set[dev][precise ? 1 : 0].load(std::memory_order_acquire)) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -851,7 +861,7 @@ int launch_fpt_kp_fused(float* tok, const void* wpack, int V, int64_t B, int dep
   static std::atomic<unsigned char> attr_set[64];
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
-  auto kern = spt_fused_kernel<false, true>;
+  auto kern = spt_fused_kernel_fast<true>;
   if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<false>::TOTAL));
     if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
