@@ -219,6 +219,8 @@ def run_ours(args):
         impl["gemm_cta_group"] = int(os.environ["MPL_GEMM_CTA_GROUP"])
     if os.environ.get("MPL_LN_FUSION"):
         impl["ln_fusion"] = bool(int(os.environ["MPL_LN_FUSION"]))
+    if os.environ.get("MPL_QKV_ATTN_FUSION"):
+        impl["qkv_attn_fusion"] = bool(int(os.environ["MPL_QKV_ATTN_FUSION"]))
     if os.environ.get("MPL_CHUNK_STREAMS"):
         impl["chunk_streams"] = int(os.environ["MPL_CHUNK_STREAMS"])
     model = MultiView_MPL(**kw, precision=args.precision, **impl)

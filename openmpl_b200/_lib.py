@@ -29,6 +29,7 @@ EXPORTS = [
     "mpl_forward", "mpl_last_launch_count", "mpl_mpjpe_accumulate", "mpl_build_inputs", "mpl_test_gemm",
     "mpl_set_profile", "mpl_profile_categories", "mpl_profile_category_name", "mpl_profile_collect", "mpl_synth_project",
     "mpl_pmpjpe_accumulate", "mpl_test_gemm_ln", "mpl_test_gemm_ln_slots", "mpl_set_graph_batch", "mpl_graph_stats",
+    "mpl_test_qkv_attn",
 ]
 
 _DESC_FLAGS = [
@@ -46,10 +47,12 @@ class MplDesc(ctypes.Structure):
                  ("depth", c_int32), ("num_heads", c_int32), ("num_views", c_int32), ("hidden_dim", c_int32),
                  ("mlp_ratio", c_float), ("qk_scale", c_float)]
                 + [(f, c_int32) for f in _DESC_FLAGS] + [("precision", c_int32), ("ln_fusion", c_int32),
-                                                         ("gemm_cta_group", c_int32), ("chunk_streams", c_int32)])
+                                                         ("gemm_cta_group", c_int32), ("qkv_attn_fusion", c_int32),
+                                                         ("chunk_streams", c_int32)])
 
 
-def make_desc(kw: dict, precision: str, ln_fusion: bool = True, gemm_cta_group: int = 2, chunk_streams: int = 1) -> MplDesc:
+def make_desc(kw: dict, precision: str, ln_fusion: bool = True, gemm_cta_group: int = 2, chunk_streams: int = 1,
+              qkv_attn_fusion: bool = True) -> MplDesc:
     """Constructor kwargs of MultiView_MPL (multiview_mpl.py:95-117) -> MplDesc."""
     if precision not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
@@ -65,6 +68,7 @@ def make_desc(kw: dict, precision: str, ln_fusion: bool = True, gemm_cta_group: 
     d.ln_fusion = int(bool(ln_fusion))
     d.gemm_cta_group = int(gemm_cta_group)
     d.chunk_streams = int(chunk_streams)
+    d.qkv_attn_fusion = int(bool(qkv_attn_fusion))
     return d
 
 
@@ -114,6 +118,8 @@ def lib():
         L.mpl_test_gemm_ln.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p]
         L.mpl_test_gemm_ln_slots.argtypes = [c_int]
+        L.mpl_test_qkv_attn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p,
+                                        c_int64, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         L.mpl_set_graph_batch.argtypes = [c_void_p, c_int64]
         L.mpl_graph_stats.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64)]
         L.mpl_set_profile.argtypes = [c_void_p, c_int]

@@ -21,6 +21,7 @@
 // the K tail is zero-filled by TMA, so no padding copies are needed.
 #include <cuda.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
@@ -681,6 +682,370 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+
+// =====================================================================================================================
+// QKV projection + cross-view attention in ONE kernel (bf16 mode, LayerNorm folded, view tokens with hd = 136, V = 2 / 4 / 8)
+// -- multiview_mpl.py:48-64.  The q|k|v tensor (6.5 KB per row, written and re-read once per block application: a quarter
+// of all DRAM traffic of the step) never exists: an output tile is one HEAD of 256 rows, 3 * 136 + 8 = 416 accumulator
+// columns [q | k | v | pad] (W rows permuted / zero-padded per head at pack time and stored so that each CTA of the pair
+// reads its 208 rows contiguously; two N = 208 UMMAs per K step).  The V views of a pose are V adjacent TMEM lanes = V
+// adjacent lanes of an epilogue warp.  Epilogue of a warp (lane quarter, half of the head dims):
+//   A  read q, k, v of its dims out of TMEM, apply the folded LayerNorm + bias, keep q in registers (bf16 pairs; the softmax
+//      scale * log2 e is folded into the q rows of W), park k and v in shared memory (bf16) -> the accumulator is RELEASED
+//      here, the next tile's MMAs run under everything below;
+//   B  partial scores of its dims: every lane reads the k rows of the V views of ITS pose (the V lanes of a pose read the
+//      same address: one broadcast wavefront per load), packed f32x2 FMAs; the two warps of a quarter exchange the partial
+//      sums through shared memory (64-thread named barrier); softmax over the V keys in registers;
+//   C  o = sum_j p_j v_j for its dims, bf16, into the (now free) k rows of the quarter;
+//   D  one TMA store of the quarter's 32 x 136 output box.
+// =====================================================================================================================
+constexpr int FA_HD = 136, FA_NT = 416, FA_UW = 208;         // head dim, padded q|k|v tile width, UMMA N
+constexpr int FA_B_ROWS = FA_NT / 2;                          // W rows per CTA and stage
+constexpr int FA_A_BYTES = BM * KB_BYTES, FA_B_BYTES = FA_B_ROWS * KB_BYTES;
+constexpr int FA_STAGE_BYTES = FA_A_BYTES + FA_B_BYTES;       // 43 008
+constexpr int FA_STAGES = 3;
+constexpr int FA_PITCH = FA_HD * 2;                           // bytes per row of the k / v / output exchange buffers (272)
+constexpr int FA_KV_BYTES = 2 * BM * FA_PITCH;                // k rows then v rows of the CTA's 128 rows
+constexpr int FA_D0 = 72;                                     // dims of epilogue half 0 ([0, 72)); half 1 takes [72, 136)
+constexpr int FA_PART_BYTES = 2 * BM * 8 * 4;                 // partial scores [half][row][<= 8 views]
+constexpr int FA_BC_WARP_BYTES = 3 * FA_D0 * 8;               // per epilogue warp: (bias, colsum) of its 3 x 72 columns of the head
+constexpr int FA_BC_BYTES = NUM_EPI_WARPS * FA_BC_WARP_BYTES;
+constexpr int FA_SMEM_BYTES = 1024 + FA_STAGES * FA_STAGE_BYTES + FA_KV_BYTES + FA_PART_BYTES + FA_BC_BYTES + 256;
+static_assert(FA_STAGE_BYTES % 1024 == 0 && FA_SMEM_BYTES <= 232448, "fused QKV + attention kernel: shared-memory budget");
+
+struct FusedAttnArgs {
+  const float* bias;       // [H * 416] folded bias, logical column order [q | k | v | pad] per head
+  const float* colsum;     // [H * 416]
+  const float2* stats;     // [slots][stats_ld]
+  int64_t stats_ld;
+  int slots;
+  float inv_k, eps;
+  int64_t M;
+  int K, H;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int V>
+__global__ void __launch_bounds__(NUM_EPI_WARPS * 32 + 128, 1)
+qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const FusedAttnArgs a) {
+  static_assert(V == 2 || V == 4 || V == 8, "the views of a pose must be adjacent lanes of one warp");
+  constexpr int BK = KB_BYTES / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kv_base = smem_base + FA_STAGES * FA_STAGE_BYTES;  // k rows [128][272 B], then v rows
+  const uint32_t part_base = kv_base + FA_KV_BYTES;
+  const uint32_t bc_base = part_base + FA_PART_BYTES;
+  const uint32_t bar_base = bc_base + FA_BC_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (FA_STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * FA_STAGES);
+  const uint32_t tempty_bar = bar_base + 8u * (2 * FA_STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * FA_STAGES + 2);
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + FA_STAGES * FA_STAGE_BYTES + FA_KV_BYTES + FA_PART_BYTES + FA_BC_BYTES + 8 * (2 * FA_STAGES + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool is_leader = cta_rank == 0;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    ptx::prefetch_tensormap(&tmO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < FA_STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tfull_bar, 1);
+    ptx::mbar_init(tempty_bar, NUM_EPI_WARPS * 2);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<2>(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish<2>();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int64_t m_tiles = (a.M + 2 * BM - 1) / (2 * BM);
+  const int64_t total_tiles = m_tiles * a.H;
+  const int64_t first_tile = blockIdx.x / 2, tile_stride = gridDim.x / 2;
+  const int num_kb = (a.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ---- TMA producer: A rows of this CTA (128 x 64 K elements) + its 208 W rows of the head ----
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t leader_full0 = ptx::mapa(full_bar(0), 0);
+      for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        const int64_t m_blk = tile / a.H;
+        const int head = (int)(tile % a.H);
+        const int32_t m0 = (int32_t)(m_blk * 2 * BM + cta_rank * BM);
+        const int32_t n0 = head * FA_NT + (int32_t)cta_rank * FA_B_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * FA_STAGE_BYTES, b_dst = a_dst + FA_A_BYTES;
+          const uint32_t lbar = leader_full0 + 8u * stage;
+          if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * FA_STAGE_BYTES);
+          ptx::tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
+          ptx::tma_load_2d_pair(b_dst, &tmB, lbar, kb * BK, n0);
+          if (++stage == FA_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---- MMA issuer: two N = 208 UMMAs per K step into the single 416-column accumulator ----
+    if (is_leader) {
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint64_t desc0 = make_smem_desc(smem_base);
+      const uint32_t idesc = make_idesc(2 * BM, FA_UW);
+      for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        ptx::mbar_wait(tempty_bar, acc_phase ^ 1u);  // the epilogue warps have read the previous tile out of TMEM
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc0 = desc0 + (uint64_t)((stage * FA_STAGE_BYTES) >> 4);
+          const uint64_t bdesc0 = adesc0 + (uint64_t)(FA_A_BYTES >> 4);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < KB_BYTES / UMMA_K_BYTES; ++k) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u)  // W rows [104 u, 104 u + 104) of both CTAs = accumulator columns [208 u, 208 u + 208)
+                ptx::umma<2, 0>(tmem_base + (uint32_t)(u * FA_UW), adesc0 + (uint64_t)(k * (UMMA_K_BYTES >> 4)),
+                                bdesc0 + (uint64_t)(k * (UMMA_K_BYTES >> 4) + u * ((FA_UW / 2 * KB_BYTES) >> 4)), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit_pair(empty_bar(stage), 0x3);
+            if (kb == num_kb - 1) ptx::umma_commit_pair(tfull_bar, 0x3);
+          }
+          __syncwarp();
+          if (++stage == FA_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---- epilogue ----
+    const int q4 = warp & 3, half = (warp - 4) >> 2;
+    const int d_lo = half ? FA_D0 : 0, nchunks = half ? (FA_HD - FA_D0) / 8 : FA_D0 / 8;  // 8-dim chunks of this warp
+    const int lrow = q4 * 32 + lane;                       // CTA-local row of this lane
+    const int prow0 = q4 * 32 + (lane / V) * V;            // first row (view 0) of this lane's pose
+    const uint32_t k_row = kv_base + (uint32_t)lrow * FA_PITCH, v_row = k_row + BM * FA_PITCH;
+    const uint32_t k_pose = kv_base + (uint32_t)prow0 * FA_PITCH, v_pose = k_pose + BM * FA_PITCH;
+    const uint32_t leader_tempty = ptx::mapa(tempty_bar, 0);
+    uint32_t acc_phase = 0;
+    for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
+      const int64_t m_blk = tile / a.H;
+      const int head = (int)(tile % a.H);
+      const int32_t row0 = (int32_t)(m_blk * 2 * BM + cta_rank * BM + q4 * 32);
+      const int64_t my_row = (int64_t)row0 + lane;
+      float mu = 0.f, rstd = 1.f;
+      {
+        float s1 = 0.f, s2 = 0.f;
+        if (my_row < a.M) {
+          const float2* sp = a.stats + my_row;
+          for (int i = 0; i < a.slots; ++i) { const float2 t = sp[i * a.stats_ld]; s1 += t.x; s2 += t.y; }
+        }
+        mu = s1 * a.inv_k;
+        rstd = rsqrtf(fmaxf(fmaf(-mu, mu, s2 * a.inv_k), 0.f) + a.eps);
+      }
+      // (bias, colsum) of this warp's 3 x nd columns of the head -> its shared-memory scratch, while the MMAs of the tile run
+      // (the accumulator is single-buffered: everything between its completion and its release is serial time)
+      const int nd = 8 * nchunks;
+      const uint32_t bc = bc_base + (uint32_t)(warp - 4) * FA_BC_WARP_BYTES;
+      for (int idx = lane; idx < 3 * nd / 2; idx += 32) {  // per pair of dims: (bias d, bias d+1, colsum d, colsum d+1)
+        const int part = idx / (nd / 2), d = 2 * (idx - part * (nd / 2));
+        const int n = head * FA_NT + part * FA_HD + d_lo + d;
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.bias + n)), c2 = __ldg(reinterpret_cast<const float2*>(a.colsum + n));
+        ptx::st_shared_v4(bc + (uint32_t)idx * 16u, __float_as_uint(b2.x), __float_as_uint(b2.y), __float_as_uint(c2.x), __float_as_uint(c2.y));
+      }
+      // the previous tile's output box (it lives in the k rows of this quarter) has left shared memory
+      if (half == 0 && lane == 0) ptx::bulk_wait_read<0>();
+      named_bar_sync(1 + q4, 64);
+      ptx::mbar_wait(tfull_bar, acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+      // ---- A: TMEM -> folded LayerNorm + bias -> q in registers, k / v rows in shared memory (bf16) ----
+      const float2 rstd2 = make_float2(rstd, rstd), nmu2 = make_float2(-mu, -mu);
+      uint32_t qreg[FA_D0 / 2];
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        uint32_t r0[32], r1[32], r2[8];
+        const uint32_t col0 = (uint32_t)(part * FA_HD + d_lo);
+        ptx::tmem_ld_32x32(taddr + col0, r0);
+        ptx::tmem_ld_32x32(taddr + col0 + 32, r1);
+        if (half == 0) ptx::tmem_ld_32x8(taddr + col0 + 64, r2);
+        ptx::tmem_ld_wait();
+        auto chunk = [&](const uint32_t* r, int c) {  // 8 dims: LayerNorm-apply, bias, bf16 pairs (packed f32x2 arithmetic)
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 t;  // (bias d, bias d+1, colsum d, colsum d+1) of dims d = 2i, 2i + 1 of the chunk
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                         : "r"(bc + (uint32_t)((part * nd + 8 * c + 2 * i) * 8)));
+            const float2 acc2 = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            const float2 f2v = __ffma2_rn(rstd2, __ffma2_rn(nmu2, make_float2(t.z, t.w), acc2), make_float2(t.x, t.y));
+            const __nv_bfloat162 p = __float22bfloat162_rn(f2v);
+            w[i] = *reinterpret_cast<const uint32_t*>(&p);
+          }
+          if (part == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qreg[4 * c + i] = w[i];
+          } else {
+            ptx::st_shared_v4((part == 1 ? k_row : v_row) + (uint32_t)(d_lo + 8 * c) * 2u, w[0], w[1], w[2], w[3]);
+          }
+        };
+#pragma unroll
+        for (int c = 0; c < 4; ++c) chunk(&r0[8 * c], c);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) chunk(&r1[8 * c], 4 + c);
+        if (half == 0) chunk(r2, 8);
+      }
+      // the accumulator is free: the next tile's MMAs run under the rest of this epilogue
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(leader_tempty);
+      acc_phase ^= 1u;
+      // ---- B: partial scores over this warp's dims ----
+      float2 s2[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) s2[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < FA_D0 / 8; ++c) {
+        if (c < nchunks) {
+          float2 q2[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) q2[i] = make_float2(__uint_as_float(qreg[4 * c + i] << 16), __uint_as_float(qreg[4 * c + i] & 0xffff0000u));
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            uint32_t kw[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(kw[0]), "=r"(kw[1]), "=r"(kw[2]), "=r"(kw[3])
+                         : "r"(k_pose + (uint32_t)j * FA_PITCH + (uint32_t)(d_lo + 8 * c) * 2u));
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              s2[j] = __ffma2_rn(q2[i], make_float2(__uint_as_float(kw[i] << 16), __uint_as_float(kw[i] & 0xffff0000u)), s2[j]);
+          }
+        }
+      }
+      {
+        const uint32_t mine = part_base + (uint32_t)((half * BM + lrow) * 8) * 4u;
+#pragma unroll
+        for (int j = 0; j < V; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(mine + 4u * j), "f"(s2[j].x + s2[j].y) : "memory");
+      }
+      named_bar_sync(1 + q4, 64);  // both halves' partial sums are in place (and both are done reading the k rows)
+      float p[V];
+      {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float s0, s1;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s0) : "r"(part_base + (uint32_t)((lrow) * 8 + j) * 4u));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s1) : "r"(part_base + (uint32_t)((BM + lrow) * 8 + j) * 4u));
+          p[j] = s0 + s1;  // fixed order: bitwise the same in both warps
+          mx = fmaxf(mx, p[j]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) { p[j] = exp2f(p[j] - mx); sum += p[j]; }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int j = 0; j < V; ++j) p[j] *= inv;
+      }
+      // ---- C: o = sum_j p_j v_j over this warp's dims, into the k row of this lane (free since the barrier above) ----
+#pragma unroll
+      for (int c = 0; c < FA_D0 / 8; ++c) {
+        if (c < nchunks) {
+          float2 o2[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            uint32_t vw[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(vw[0]), "=r"(vw[1]), "=r"(vw[2]), "=r"(vw[3])
+                         : "r"(v_pose + (uint32_t)j * FA_PITCH + (uint32_t)(d_lo + 8 * c) * 2u));
+            const float2 pj = make_float2(p[j], p[j]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o2[i] = __ffma2_rn(pj, make_float2(__uint_as_float(vw[i] << 16), __uint_as_float(vw[i] & 0xffff0000u)), o2[i]);
+          }
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 t = __float22bfloat162_rn(o2[i]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          ptx::st_shared_v4(k_row + (uint32_t)(d_lo + 8 * c) * 2u, w[0], w[1], w[2], w[3]);
+        }
+      }
+      // ---- D: the quarter's 32 x 136 output box leaves by TMA ----
+      ptx::fence_proxy_async();
+      named_bar_sync(1 + q4, 64);
+      if (half == 0 && lane == 0) {
+        ptx::tma_store_2d(&tmO, kv_base + (uint32_t)(q4 * 32) * FA_PITCH, head * FA_HD, row0);
+        ptx::bulk_commit();
+      }
+    }
+    if (half == 0 && lane == 0) ptx::bulk_wait_all();
+    __syncwarp();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<2>(tmem_base, TMEM_COLS);
+  }
+}
+
+// pack: W [3D, D] fp32, LayerNorm gamma / beta folded, q rows scaled by qscale -> W'' [H * 416, D] bf16 in the PHYSICAL row
+// order of the kernel (per head: CTA 0 rows {[0,104) | [208,312)}, CTA 1 rows {[104,208) | [312,416)} of the logical
+// [q | k | v | pad] order), colsum / bias [H * 416] fp32 in LOGICAL order
+__global__ void __launch_bounds__(256) qkv_attn_pack_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           __nv_bfloat16* __restrict__ Wp, float* __restrict__ colsum,
+                                                           float* __restrict__ bias_f, int H, int D, float qscale) {
+  const int pr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // physical row
+  if (pr >= H * FA_NT) return;
+  const int lane = threadIdx.x & 31;
+  const int head = pr / FA_NT, within = pr % FA_NT;
+  const int r = within / (FA_NT / 2), rem = within % (FA_NT / 2);
+  const int u = rem / (FA_UW / 2), i = rem % (FA_UW / 2);
+  const int logical = u * FA_UW + r * (FA_UW / 2) + i;
+  const int part = logical / FA_HD, d = logical % FA_HD;
+  const bool live = part < 3;
+  const int src = part * D + head * FA_HD + d;
+  const float sc = (part == 0) ? qscale : 1.0f;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float w = live ? W[(int64_t)src * D + k] : 0.f;
+    const __nv_bfloat16 rw = __float2bfloat16_rn(w * gamma[k] * sc);
+    Wp[(int64_t)pr * D + k] = rw;
+    cs += __bfloat162float(rw);
+    bb = fmaf(w, beta[k], bb);
+  }
+  cs = warp_sum(cs);
+  bb = warp_sum(bb);
+  if (lane == 0) {
+    colsum[head * FA_NT + logical] = cs;
+    bias_f[head * FA_NT + logical] = live ? ((b != nullptr ? b[src] : 0.f) + bb) * sc : 0.f;
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -700,7 +1065,7 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // [rows, K] row-major matrix, box = 128 bytes of K x box_rows rows, 128B swizzle, out-of-bounds -> zeros
-int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, int box_rows, int box_cols = 0) {
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, int box_rows, int box_cols = 0, bool swizzle = true) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -712,7 +1077,7 @@ int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, i
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%d esz=%d box_rows=%d ptr=%p)", (int)r,
               (long long)rows, K, esz, box_rows, ptr);
@@ -794,6 +1159,72 @@ TileSplit split_tiles(int N) {
 }
 
 }  // namespace
+
+bool qkv_attn_supports(int D, int H, int tokens) {
+  return H >= 1 && D == H * FA_HD && (tokens == 2 || tokens == 4 || tokens == 8) && ((int64_t)D * 2) % 16 == 0;
+}
+size_t qkv_attn_weight_elems(int D, int H) { return (size_t)H * FA_NT * D; }
+int qkv_attn_vec_len(int H) { return H * FA_NT; }
+
+int launch_qkv_attn_pack(const float* W, const float* b, const float* gamma, const float* beta, void* Wp, float* colsum,
+                         float* bias_f, int H, int D, float scale, cudaStream_t s) {
+  const int rows = H * FA_NT;
+  qkv_attn_pack_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, s>>>(W, b, gamma, beta, reinterpret_cast<__nv_bfloat16*>(Wp), colsum,
+                                                                 bias_f, H, D, scale * 1.4426950408889634f);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+
+int launch_qkv_attn(const void* xb, const void* Wp, const float* bias_f, const float* colsum, const void* stats, int slots,
+                    float eps, void* att, int64_t M, int D, int H, int V, cudaStream_t s) {
+  if (M == 0) return MPL_OK;
+  if (!qkv_attn_supports(D, H, V) || M % V != 0) {
+    set_error("launch_qkv_attn: needs D = H * 136 and V in {2, 4, 8} (D=%d H=%d V=%d)", D, H, V);
+    return MPL_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmA, tmB, tmO;
+  MPL_TRY(make_tmap(&tmA, xb, M, D, 2, BM));
+  MPL_TRY(make_tmap(&tmB, Wp, (int64_t)H * FA_NT, D, 2, FA_B_ROWS));
+  MPL_TRY(make_tmap(&tmO, att, M, D, 2, 32, FA_HD, /*swizzle=*/false));
+  FusedAttnArgs a{};
+  a.bias = bias_f;
+  a.colsum = colsum;
+  a.stats = reinterpret_cast<const float2*>(stats);
+  a.stats_ld = (int64_t)align_up((size_t)M, 256);
+  a.slots = slots;
+  a.inv_k = 1.0f / (float)D;
+  a.eps = eps;
+  a.M = M;
+  a.K = D;
+  a.H = H;
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, FusedAttnArgs) =
+      V == 2 ? qkv_attn_kernel<2> : (V == 4 ? qkv_attn_kernel<4> : qkv_attn_kernel<8>);
+  static std::atomic<unsigned char> attr_set[64][3];
+  const int vi = V == 2 ? 0 : (V == 4 ? 1 : 2);
+  int dev = 0;
+  MPL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev][vi].load(std::memory_order_acquire)) {
+    MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    if (dev >= 0 && dev < 64) attr_set[dev][vi].store(1, std::memory_order_release);
+  }
+  const int64_t total = ceil_div(M, (int64_t)2 * BM) * H;
+  const unsigned groups = (unsigned)std::min<int64_t>(total, kNumSMs / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * 2);
+  cfg.blockDim = dim3(NUM_EPI_WARPS * 32 + 128);
+  cfg.dynamicSmemBytes = FA_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MPL_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, a));
+  return MPL_OK;
+}
+
 
 bool gemm_tcgen05_supports(int N, int K, int dtype) {
   (void)dtype;  // both tensor-core modes stage bf16 planes

@@ -46,6 +46,8 @@ struct BlockW {
   const float *n1w, *n1b, *qkvw, *qkvb, *projw, *projb, *n2w, *n2b, *fc1w, *fc1b, *fc2w, *fc2b;
   const void *qkvw_tc, *projw_tc, *fc1w_tc, *fc2w_tc;  // tensor-core operand copies (FPT, bf16 / tf32 modes)
   const float *qkv_cs, *qkv_bf, *fc1_cs, *fc1_bf;      // LayerNorm-fused mode: column sums of W' and folded biases
+  const void* qa_w;                                    // fused QKV + attention: head-tiled W'' and its column sums / biases
+  const float *qa_cs, *qa_b;
 };
 
 }  // namespace mpl
@@ -62,6 +64,7 @@ struct MplModel {
   bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
   bool spt_fused;  // the SPT stack runs as the single fused fp16-mma kernel (bf16 / tf32 modes, d=32, H=8, J=17)
   bool ln_fused;   // bf16 mode: the FPT LayerNorms are folded into the projection GEMMs (no LayerNorm kernel)
+  bool qkv_attn;      // bf16 LN-fused mode, view tokens, D = H * 136, V in {2, 4, 8}: QKV GEMM + cross-view attention are one kernel
   bool fpt_kp_fused;  // bf16 mode, keypoint-token FPT (width 32, 8 heads, J = 17): the whole FPT stack is one kernel launch
   int ln_slots;    // statistics slots per row written by the residual-emit GEMMs
   int cta_group;   // 1: one CTA per 128 x 256 GEMM tile, 2: CTA pairs per 256 x 256 tile (default)
@@ -273,9 +276,15 @@ static void build_tables(MplModel* m) {
       const std::string p = "blocks." + std::to_string(l) + ".";
       const int64_t D = m->fpt_dim, Hf = m->fpt_hidden;
       if (m->ln_fused) {
-        add_derived(m, "lnw:" + p + "attn.qkv", 3 * D * D, 2);
-        add_derived(m, "lncs:" + p + "attn.qkv", 3 * D, 4);
-        add_derived(m, "lnb:" + p + "attn.qkv", 3 * D, 4);
+        if (m->qkv_attn) {
+          add_derived(m, "qaw:" + p + "attn.qkv", (int64_t)qkv_attn_weight_elems((int)D, m->H), 2);
+          add_derived(m, "qacs:" + p + "attn.qkv", qkv_attn_vec_len(m->H), 4);
+          add_derived(m, "qab:" + p + "attn.qkv", qkv_attn_vec_len(m->H), 4);
+        } else {
+          add_derived(m, "lnw:" + p + "attn.qkv", 3 * D * D, 2);
+          add_derived(m, "lncs:" + p + "attn.qkv", 3 * D, 4);
+          add_derived(m, "lnb:" + p + "attn.qkv", 3 * D, 4);
+        }
         add_derived(m, "lnw:" + p + "mlp.fc1", Hf * D, 2);
         add_derived(m, "lncs:" + p + "mlp.fc1", Hf, 4);
         add_derived(m, "lnb:" + p + "mlp.fc1", Hf, 4);
@@ -351,7 +360,7 @@ static Workspace layout_workspace(const MplModel* m, int64_t Bc, uint8_t* base) 
     const int esz = (m->fpt_tc && m->d.precision == MPL_PREC_BF16) ? 2 : 4;
     w.fxn = take(Rf * D * esz);
     if (m->ln_fused) w.fxl = take(Rf * D * 2);
-    w.fqkv = take(Rf * 3 * D * esz);
+    if (!m->qkv_attn) w.fqkv = take(Rf * 3 * D * esz);
     w.fatt = take(Rf * D * esz);
     w.fhid = take(Rf * Hf * esz);
     if (m->ln_fused) w.fstats = take(Rf * (size_t)m->ln_slots * 8);
@@ -421,9 +430,15 @@ static BlockW block_weights(const MplModel* m, const Packed& P, const std::strin
   if (tc) {
     const std::string tag = (m->d.precision == MPL_PREC_BF16) ? "bf16:" : "split:";
     if (m->ln_fused) {
-      b.qkvw_tc = P.dv("lnw:" + p + "attn.qkv");
-      b.qkv_cs = P.df("lncs:" + p + "attn.qkv");
-      b.qkv_bf = P.df("lnb:" + p + "attn.qkv");
+      if (m->qkv_attn) {
+        b.qa_w = P.dv("qaw:" + p + "attn.qkv");
+        b.qa_cs = P.df("qacs:" + p + "attn.qkv");
+        b.qa_b = P.df("qab:" + p + "attn.qkv");
+      } else {
+        b.qkvw_tc = P.dv("lnw:" + p + "attn.qkv");
+        b.qkv_cs = P.df("lncs:" + p + "attn.qkv");
+        b.qkv_bf = P.df("lnb:" + p + "attn.qkv");
+      }
       b.fc1w_tc = P.dv("lnw:" + p + "mlp.fc1");
       b.fc1_cs = P.df("lncs:" + p + "mlp.fc1");
       b.fc1_bf = P.df("lnb:" + p + "mlp.fc1");
@@ -472,9 +487,14 @@ static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_
     GemmLnArgs emit{};  // residual-emit side (proj, fc2)
     emit.stats_out = stats;
     emit.x_lo = xl;
-    app.colsum = w.qkv_cs;
-    LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkv_bf, qkv, rows, 3 * C, C, prec, EPI_LN_BIAS, 0, s, &app, cg));
-    LC(CAT_FPT_ATTN, launch_attention_bf16((const __nv_bfloat16*)qkv, (__nv_bfloat16*)att, sets, N, m->H, hd, scale, s));
+    if (m->qkv_attn) {
+      // QKV projection and cross-view attention in one kernel: the q|k|v tensor never exists
+      LC(CAT_FPT_QKV, launch_qkv_attn(xn, w.qa_w, w.qa_b, w.qa_cs, stats, m->ln_slots, 1e-6f, att, rows, C, m->H, N, s));
+    } else {
+      app.colsum = w.qkv_cs;
+      LC(CAT_FPT_QKV, launch_gemm_tcgen05(xn, w.qkvw_tc, w.qkv_bf, qkv, rows, 3 * C, C, prec, EPI_LN_BIAS, 0, s, &app, cg));
+      LC(CAT_FPT_ATTN, launch_attention_bf16((const __nv_bfloat16*)qkv, (__nv_bfloat16*)att, sets, N, m->H, hd, scale, s));
+    }
     LC(CAT_FPT_PROJ, launch_gemm_tcgen05(att, w.projw_tc, w.projb, xn, rows, C, C, prec, EPI_RESIDUAL_EMIT, 0, s, &emit, cg));
     app.colsum = w.fc1_cs;
     app.out_fp16 = 1;   // hidden activations in fp16 (GELU in packed half2), fc2 runs kind::f16 on fp16 operands
@@ -806,6 +826,7 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
   m->cta_group = (d.gemm_cta_group == 1) ? 1 : 2;
   m->chunk_streams = (d.chunk_streams == 2) ? 2 : 1;
   m->ln_slots = m->ln_fused ? gemm_ln_slots(m->fpt_dim) : 0;
+  m->qkv_attn = m->ln_fused && d.qkv_attn_fusion != 0 && m->cta_group == 2 && qkv_attn_supports(m->fpt_dim, m->H, m->fpt_tokens);
   build_tables(m);
   *out = m;
   return MPL_OK;
@@ -969,10 +990,18 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
       if (m->ln_fused) {
         const int D = m->fpt_dim, Hf = m->fpt_hidden;
         auto mut = [&](const std::string& name) { return base + m->derived[m->dindex.at(name)].offset; };
-        MPL_TRY(launch_ln_fold(P.f(p + "attn.qkv.weight"), m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr, P.f(p + "norm1.weight"),
-                               P.f(p + "norm1.bias"), reinterpret_cast<__nv_bfloat16*>(mut("lnw:" + p + "attn.qkv")),
-                               reinterpret_cast<float*>(mut("lncs:" + p + "attn.qkv")),
-                               reinterpret_cast<float*>(mut("lnb:" + p + "attn.qkv")), 3 * D, D, s));
+        if (m->qkv_attn) {
+          const float fscale = m->d.qk_scale != 0.f ? m->d.qk_scale : 1.0f / sqrtf((float)(D / m->H));
+          MPL_TRY(launch_qkv_attn_pack(P.f(p + "attn.qkv.weight"), m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr,
+                                       P.f(p + "norm1.weight"), P.f(p + "norm1.bias"), mut("qaw:" + p + "attn.qkv"),
+                                       reinterpret_cast<float*>(mut("qacs:" + p + "attn.qkv")),
+                                       reinterpret_cast<float*>(mut("qab:" + p + "attn.qkv")), m->H, D, fscale, s));
+        } else {
+          MPL_TRY(launch_ln_fold(P.f(p + "attn.qkv.weight"), m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr, P.f(p + "norm1.weight"),
+                                 P.f(p + "norm1.bias"), reinterpret_cast<__nv_bfloat16*>(mut("lnw:" + p + "attn.qkv")),
+                                 reinterpret_cast<float*>(mut("lncs:" + p + "attn.qkv")),
+                                 reinterpret_cast<float*>(mut("lnb:" + p + "attn.qkv")), 3 * D, D, s));
+        }
         MPL_TRY(launch_ln_fold(P.f(p + "mlp.fc1.weight"), P.f(p + "mlp.fc1.bias"), P.f(p + "norm2.weight"), P.f(p + "norm2.bias"),
                                reinterpret_cast<__nv_bfloat16*>(mut("lnw:" + p + "mlp.fc1")),
                                reinterpret_cast<float*>(mut("lncs:" + p + "mlp.fc1")),
@@ -1266,5 +1295,28 @@ int mpl_test_gemm_ln(const void* A, const void* W, const float* bias, void* Y, i
   MPL_API_END
 }
 int mpl_test_gemm_ln_slots(int N) { return gemm_ln_slots(N); }
+
+/* The fused QKV + cross-view attention kernel in isolation.  scratch: (H * 416 * D) bf16 + 2 * (H * 416) floats, 256-aligned. */
+int mpl_test_qkv_attn(const void* xb, const float* W, const float* bias, const float* gamma, const float* beta,
+                      const void* stats, int slots, float eps, float scale, void* att, int64_t M, int D, int H, int V,
+                      void* scratch, size_t scratch_bytes, mpl_stream_t stream) {
+  MPL_API_BEGIN
+  if (!qkv_attn_supports(D, H, V)) {
+    set_error("mpl_test_qkv_attn: unsupported shape (D=%d H=%d V=%d)", D, H, V);
+    return MPL_ERR_UNSUPPORTED;
+  }
+  const size_t wbytes = align_up(qkv_attn_weight_elems(D, H) * 2, 256), vbytes = align_up((size_t)qkv_attn_vec_len(H) * 4, 256);
+  if (scratch == nullptr || scratch_bytes < wbytes + 2 * vbytes) {
+    set_error("mpl_test_qkv_attn: scratch has %zu bytes, %zu needed", scratch_bytes, wbytes + 2 * vbytes);
+    return MPL_ERR_WORKSPACE;
+  }
+  uint8_t* sb = reinterpret_cast<uint8_t*>(scratch);
+  float* cs = reinterpret_cast<float*>(sb + wbytes);
+  float* bf = reinterpret_cast<float*>(sb + wbytes + vbytes);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  MPL_TRY(launch_qkv_attn_pack(W, bias, gamma, beta, sb, cs, bf, H, D, scale, s));
+  return launch_qkv_attn(xb, sb, bf, cs, stats, slots, eps, att, M, D, H, V, s);
+  MPL_API_END
+}
 
 }  // extern "C"

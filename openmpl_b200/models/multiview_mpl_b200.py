@@ -108,7 +108,7 @@ class MultiView_MPL(nn.Module):
                  head_kadkhod=False,
                  hidden_dim=1024,
                  FPT_blocks_view_keypoint_tokens=False, *, precision=None, ln_fusion=True, gemm_cta_group=2,
-                 graph_batch=2048, chunk_streams=1):
+                 graph_batch=2048, chunk_streams=1, qkv_attn_fusion=True):
         super().__init__()
         kw = {k: v for k, v in locals().items() if k in CTOR_DEFAULTS}
         self.cfg = make_config(**kw)
@@ -122,6 +122,8 @@ class MultiView_MPL(nn.Module):
         # chunk_streams=2: batches of >= 16384 poses run as two interleaved pose chunks on two internal streams
         # (MplDesc.chunk_streams; measured neutral on B200, profiles/r2_experiments.md, hence off by default)
         self.chunk_streams = int(chunk_streams)
+        # bf16 mode: QKV projection + cross-view attention as one kernel where the shape allows (MplDesc.qkv_attn_fusion)
+        self.qkv_attn_fusion = bool(qkv_attn_fusion)
         self.num_joints, self.num_views, self.embed_dim_ratio = num_joints, num_views, embed_dim_ratio
         self._spec = param_spec(self.cfg)
         for name, (shape, kind, fan_in) in self._spec.items():
@@ -143,7 +145,8 @@ class MultiView_MPL(nn.Module):
             index = torch.cuda.current_device() if torch.cuda.is_available() else -1
         if index not in self._h.ptrs:
             L = _lib.lib()
-            desc = _lib.make_desc(self.cfg.kw, self.precision, self.ln_fusion, self.gemm_cta_group, self.chunk_streams)
+            desc = _lib.make_desc(self.cfg.kw, self.precision, self.ln_fusion, self.gemm_cta_group, self.chunk_streams,
+                                  self.qkv_attn_fusion)
             h = ctypes.c_void_p()
             _lib.check(L.mpl_create(ctypes.byref(desc), ctypes.byref(h)))
             n = L.mpl_num_params(h)
@@ -584,6 +587,7 @@ class MultiView_MPL_G(nn.Module):
             gemm_cta_group=kwargs.get("gemm_cta_group", 2),
             graph_batch=kwargs.get("graph_batch", 2048),
             chunk_streams=kwargs.get("chunk_streams", 1),
+            qkv_attn_fusion=kwargs.get("qkv_attn_fusion", True),
         )
 
     def forward(self, x, centers=None, rays=None):

@@ -230,6 +230,26 @@ def test_cuda_graph_small_batch_path_equals_the_plain_path(precision):
     assert rel_err(outs[0], oracle_outputs(cfg, weights, synth.make_batch(256, rig, seed=1))[0]) <= TOL[precision]
 
 
+@pytest.mark.parametrize("name", ["hm0_v4_d12", "cmu0_v2_d2", "sweep_viewtok_v8", "sweep_viewtok_v2"])
+def test_fused_qkv_attention_on_and_off_agree_with_the_reference(name):
+    """bf16 mode runs the QKV projection and the cross-view attention as ONE kernel for 2 / 4 / 8 views of 136-wide heads (no
+    q|k|v tensor); the two-kernel form stays selectable (`qkv_attn_fusion=False`) and serves every other shape.  Both must
+    meet the bf16 bound against the reference goldens and agree with each other; a large batch covers many tiles per CTA."""
+    case = CASES[name]
+    g = load_golden(name)
+    cfg, weights, batch = make_inputs(case)
+    outs = {}
+    for fused in (True, False):
+        m = build_module(case["kw"], weights, "bf16", qkv_attn_fusion=fused)
+        outs[fused] = run_module(m, batch)[0]
+        assert rel_err(outs[fused], g["out64_0"]) <= TOL["bf16"]
+    assert rel_err(outs[True], outs[False].astype(np.float64)) <= TOL["bf16"]
+    big = synth.make_batch(3000, synth.make_rig(cfg.V, case["rig"]), seed=77)
+    a = run_module(build_module(case["kw"], weights, "bf16", qkv_attn_fusion=True), big, packed=True)[0]
+    b = run_module(build_module(case["kw"], weights, "bf16", qkv_attn_fusion=False), big, packed=True)[0]
+    assert np.isfinite(a).all() and rel_err(a, b.astype(np.float64)) <= TOL["bf16"]
+
+
 def test_native_library_is_what_ran():
     maps = open("/proc/self/maps").read()
     assert "libmpl_b200.so" in maps
