@@ -337,7 +337,10 @@ def run_ours(args):
         achieved = g_flops / (g_ms / 1000.0) / 1e12
         # tf32-named mode = split bf16 operands: three bf16 MMAs per algorithmic product
         peak = pk.get("bf16_tflops_sustained", 1400.0) / (3.0 if args.precision == "tf32" else 1.0)
-        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV/proj/fc1/fc2 of the FPT)", "achieved": achieved,
+        fused_attn = "fpt_attention" not in agg
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel / qkv_attn_kernel (QKV/proj/fc1/fc2 of the FPT)"
+                    + ("; the QKV launches are the fused QKV + cross-view-attention kernel: their time includes the attention, "
+                       "their FLOPs count the projection only" if fused_attn else ""), "achieved": achieved,
                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic.get("gemm_tcgen05_kernel", {}).get("bytes_per_launch"),
                     "traffic_note": traffic.get("gemm_tcgen05_kernel", {}).get("note"),

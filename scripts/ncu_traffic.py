@@ -31,10 +31,13 @@ def main():
     per, tens = {}, {}
     for r in rows[2:]:
         name = r[ix["Kernel Name"]]
-        if "gemm_tcgen05_kernel" not in name:
+        if "qkv_attn_kernel" in name:
+            key = "qkv_attention_fused"
+        elif "gemm_tcgen05_kernel" in name:
+            epi = name.split("gemm_tcgen05_kernel<")[1].split(">")[0].replace("(int)", "").split(",")[2].strip()
+            key = NAMES.get(epi, "epi" + epi)
+        else:
             continue
-        epi = name.split("gemm_tcgen05_kernel<")[1].split(">")[0].replace("(int)", "").split(",")[2].strip()
-        key = NAMES.get(epi, "epi" + epi)
         per[key] = (val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")) / 1e6
         tens[key] = float(r[ix["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])
     lib = os.path.join(ROOT, "openmpl_b200", "libmpl_b200.so")
