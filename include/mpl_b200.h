@@ -92,6 +92,8 @@ typedef struct MplDesc {
                              the next GEMM's operand and per-row (sum, sum^2); the next GEMM multiplies the raw rows by
                              W diag(gamma) and applies (mean, rstd) in its epilogue */
   int32_t gemm_cta_group; /* 0 / 2: CTA pair per 256x256 tile (cta_group::2, cluster 2x1x1); 1: one CTA per 128x256 tile */
+  int32_t spt_hidden, fpt_hidden; /* int(width * mlp_ratio) of the SPT / FPT Mlp as the reference's float64 arithmetic gives it
+                                     (0 = derive from the float mlp_ratio above) */
   int32_t qkv_attn_fusion; /* bf16 LayerNorm-fused mode, view tokens, D = 8 x 136-wide heads, 2 / 4 / 8 views: QKV projection and
                               cross-view attention run as ONE kernel (no q|k|v tensor).  0 = two kernels, non-zero (make_desc
                               default: 1) = fused where the shape allows */

@@ -47,7 +47,8 @@ class MplDesc(ctypes.Structure):
                  ("depth", c_int32), ("num_heads", c_int32), ("num_views", c_int32), ("hidden_dim", c_int32),
                  ("mlp_ratio", c_float), ("qk_scale", c_float)]
                 + [(f, c_int32) for f in _DESC_FLAGS] + [("precision", c_int32), ("ln_fusion", c_int32),
-                                                         ("gemm_cta_group", c_int32), ("qkv_attn_fusion", c_int32),
+                                                         ("gemm_cta_group", c_int32), ("spt_hidden", c_int32), ("fpt_hidden", c_int32),
+                                                         ("qkv_attn_fusion", c_int32),
                                                          ("chunk_streams", c_int32)])
 
 
@@ -69,6 +70,11 @@ def make_desc(kw: dict, precision: str, ln_fusion: bool = True, gemm_cta_group: 
     d.gemm_cta_group = int(gemm_cta_group)
     d.chunk_streams = int(chunk_streams)
     d.qkv_attn_fusion = int(bool(qkv_attn_fusion))
+    # the Mlp widths as Python's float64 int(dim * ratio) gives them (the float32 ratio in the struct can round differently)
+    from .spec import make_config
+    from .spec import CTOR_DEFAULTS
+    cfg = make_config(**{k: v for k, v in kw.items() if k in CTOR_DEFAULTS})
+    d.spt_hidden, d.fpt_hidden = int(cfg.spt_hidden), int(cfg.fpt_hidden)
     return d
 
 

@@ -158,7 +158,7 @@ static int validate(const MplModel* m) {
     set_error("in_chans must be 2: the forward slices pose[:, :, 0:2|0:3] (multiview_mpl.py:359-364)");
     return MPL_ERR_CONFIG_RUNTIME;
   }
-  if (m->dim % m->H != 0 && !d.no_transformer_spt) {
+  if (m->dim % m->H != 0 && !d.no_transformer_spt && d.depth > 0) {
     set_error("embed_dim_ratio must be divisible by num_heads (reshape at multiview_mpl.py:55)");
     return MPL_ERR_CONFIG_RUNTIME;
   }
@@ -181,7 +181,7 @@ static int validate(const MplModel* m) {
               "(multiview_mpl.py:75,497)", m->dim, m->dim, 2 * m->dim);
     return MPL_ERR_CONFIG_RUNTIME;
   }
-  if (!d.no_transformer_fpt && m->fpt_dim % m->H != 0) {
+  if (!d.no_transformer_fpt && m->fpt_dim % m->H != 0 && d.depth > 0) {
     set_error("FPT width must be divisible by num_heads (reshape at multiview_mpl.py:55)");
     return MPL_ERR_CONFIG_RUNTIME;
   }
@@ -794,8 +794,10 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
   else { m->fpt_dim = m->tok_w; m->fpt_tokens = m->V; }
   m->pos3d_lin_out = (d.add_3D_pos_encoding_to_rays && !d.add_3D_pos_encoding_in_Spatial) ? 2 * m->dim : m->dim;
   m->pos3d_w = d.add_3D_pos_encoding_to_rays ? 2 * m->dim : m->dim;
-  m->spt_hidden = (int)((double)m->dim * (double)d.mlp_ratio);
-  m->fpt_hidden = (int)((double)m->fpt_dim * (double)d.mlp_ratio);
+  // int(dim * mlp_ratio) as the reference computes it in float64 (multiview_mpl.py:25-26,78): the host passes the two integers,
+  // because the ratio itself crosses the ABI as a float (0.7 * 10 = 7 in float64, 6 in float32)
+  m->spt_hidden = d.spt_hidden > 0 ? d.spt_hidden : (int)((double)m->dim * (double)d.mlp_ratio);
+  m->fpt_hidden = d.fpt_hidden > 0 ? d.fpt_hidden : (int)((double)m->fpt_dim * (double)d.mlp_ratio);
   m->n_out = d.head_kadkhod ? 3 : 1;
   const int st = validate(m);
   if (st != MPL_OK) {

@@ -96,7 +96,8 @@ def _first_forward_error(c: MplConfig):
     kw = c.kw
     if kw["in_chans"] != 2:
         return ("RuntimeError", "in_chans must be 2: the forward slices pose[:, :, 0:2|0:3] (multiview_mpl.py:359-364)")
-    if c.d % c.H != 0 and not kw["no_transformer_spt"]:
+    # (with depth 0 the reference builds no blocks, so nothing reshapes: multiview_mpl.py:236-259)
+    if c.d % c.H != 0 and not kw["no_transformer_spt"] and c.depth > 0:
         return ("RuntimeError", "embed_dim_ratio must be divisible by num_heads (reshape at multiview_mpl.py:55)")
     if kw["no_transformer_spt"] and kw["multiple_spatial_blocks"]:
         return ("IndexError", "index 0 is out of range (Spatial_blocks is empty, multiview_mpl.py:401)")
@@ -110,7 +111,7 @@ def _first_forward_error(c: MplConfig):
     if kw["input_rays_as_token"] and kw["FPT_blocks_view_keypoint_tokens"] and not kw["no_transformer_fpt"]:
         return ("RuntimeError", f"Given normalized_shape=[{c.d}], expected input with shape [*, {c.d}], but got "
                                 f"input of width {2 * c.d} (multiview_mpl.py:75,497)")
-    if not kw["no_transformer_fpt"] and c.fpt_dim % c.H != 0:
+    if not kw["no_transformer_fpt"] and c.fpt_dim % c.H != 0 and c.depth > 0:
         return ("RuntimeError", "FPT width must be divisible by num_heads (reshape at multiview_mpl.py:55)")
     return None
 

@@ -283,3 +283,28 @@ def test_missing_library_fails_loudly_without_fallback(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0
     assert "is missing" in r.stderr and "no fallback" in r.stderr
+
+
+def test_mlp_hidden_width_follows_float64_like_the_reference():
+    """int(dim * mlp_ratio) in float64 (multiview_mpl.py:25-26,78): ratio 0.7 with width 10 gives 7; the float32 ratio of the
+    struct alone would give 6 and the parameter tables would disagree."""
+    L = _lib.lib()
+    kw = dict(spec.CTOR_DEFAULTS, num_joints=5, embed_dim_ratio=10, num_heads=2, depth=1, num_views=2, mlp_ratio=0.7)
+    desc = _lib.make_desc(kw, "fp32")
+    h = ctypes.c_void_p()
+    assert L.mpl_create(ctypes.byref(desc), ctypes.byref(h)) == 0, L.mpl_last_error()
+    assert L.mpl_dim(h, 4) == int(10 * 0.7) == 7 and L.mpl_dim(h, 5) == int(50 * 0.7)
+    L.mpl_destroy(h)
+    m = mb.MultiView_MPL(**{k: v for k, v in kw.items()})
+    assert m.state_dict()["Spatial_blocks.0.mlp.fc1.weight"].shape == (7, 10)
+
+
+def test_depth_zero_skips_the_head_divisibility_checks():
+    """With depth 0 the reference builds no blocks, so a width that is not divisible by the head count is legal."""
+    cfg = spec.make_config(num_joints=5, embed_dim_ratio=10, num_heads=4, depth=0, num_views=2)
+    assert cfg.error is None
+    L = _lib.lib()
+    desc = _lib.make_desc(dict(spec.CTOR_DEFAULTS, num_joints=5, embed_dim_ratio=10, num_heads=4, depth=0, num_views=2), "fp32")
+    h = ctypes.c_void_p()
+    assert L.mpl_create(ctypes.byref(desc), ctypes.byref(h)) == 0, L.mpl_last_error()
+    L.mpl_destroy(h)
