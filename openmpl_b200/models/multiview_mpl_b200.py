@@ -124,6 +124,9 @@ class MultiView_MPL(nn.Module):
         self.chunk_streams = int(chunk_streams)
         # bf16 mode: QKV projection + cross-view attention as one kernel where the shape allows (MplDesc.qkv_attn_fusion)
         self.qkv_attn_fusion = bool(qkv_attn_fusion)
+        # host inputs spanning more than one forward chunk are copied piece by piece on a side stream under the kernels of
+        # the previous piece; the first piece (the only exposed copy) is this many poses
+        self.pipeline_first_poses = int(os.environ.get("MPL_PIPE_FIRST", 4096))
         self.num_joints, self.num_views, self.embed_dim_ratio = num_joints, num_views, embed_dim_ratio
         self._spec = param_spec(self.cfg)
         for name, (shape, kind, fan_in) in self._spec.items():
@@ -490,11 +493,14 @@ class MultiView_MPL(nn.Module):
             dev = {k: ([torch.empty(t.shape, dtype=torch.float32, device=device) for t in v[0]] if v is not None else None)
                    for k, v in plan.items()}
             side.wait_stream(main)                       # the fresh buffers may still be in use on the main stream
-            starts = list(range(0, B, chunk))
+            # the first piece is small: its copy is the only one the forward has to wait for, every later piece arrives under
+            # the kernels of the one before it
+            first = min(chunk, max(1, self.pipeline_first_poses))
+            bounds = [0] + list(range(first, B, chunk)) + [B]
+            pieces = list(zip(bounds[:-1], bounds[1:]))
             events = []
             with torch.cuda.stream(side):
-                for b0 in starts:
-                    b1 = min(B, b0 + chunk)
+                for b0, b1 in pieces:
                     for k, v in plan.items():
                         if v is not None:
                             for d, t in zip(dev[k], v[0]):
@@ -521,8 +527,7 @@ class MultiView_MPL(nn.Module):
             r_list, _ = views("rays", J * 3)
             c_list, c_stride = views("centers", 3)
             launches = 0
-            for ev, b0 in zip(events, starts):
-                b1 = min(B, b0 + chunk)
+            for ev, (b0, b1) in zip(events, pieces):
                 main.wait_event(ev)
                 arr = lambda ts: (ctypes.c_void_p * V)(*[t[b0:].data_ptr() for t in ts]) if ts is not None else None
                 _lib.check(L.mpl_forward(h, st["packed"].data_ptr(), arr(p_list), arr(r_list), arr(c_list), p_stride, c_stride,

@@ -8,7 +8,7 @@ for envs in "$@"; do
 import json
 try:
     d=json.loads(open("gpurun_out/${TAG}_$i.json").read().strip().splitlines()[-1])
-    print("[$envs]", "value", round(d["value"]), "ms", round(d["ms_per_step"],2), "roof", round(d["roofline"]["frac"],3), "err", round(d["parity"]["max_abs_err_over_scale"],5))
+    print("[$envs]", "value", round(d["value"]), "ms", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"]), "e2e_ms", round(d["e2e"]["ms_per_step"],2), "roof", round(d["roofline"]["frac"],3), "err", round(d["parity"]["max_abs_err_over_scale"],5))
     print("   ", {k: round(v["ms_per_step"],2) for k,v in d["breakdown"].items()})
 except Exception as e:
     print("[$envs] ERR", e); print(open("gpurun_out/${TAG}_$i.err").read()[-600:])

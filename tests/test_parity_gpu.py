@@ -276,8 +276,8 @@ def test_data_parallel_replicas_like_the_reference_runner(precision):
     np.testing.assert_array_equal(out.cpu().numpy(), single)
 
 
-@pytest.mark.parametrize("packed", [False, True])
-def test_pipelined_host_staging_equals_device_resident_inputs(packed):
+@pytest.mark.parametrize("packed,first", [(False, None), (True, None), (True, 100), (False, 7)])
+def test_pipelined_host_staging_equals_device_resident_inputs(packed, first):
     """Host inputs spanning several forward chunks take the pipelined path (copy of chunk i+1 overlapped with the compute
     of chunk i on a side stream); the result must be bitwise the result of the same call on device-resident inputs."""
     case = CASES["cmu0_v2_d2"]
@@ -285,6 +285,8 @@ def test_pipelined_host_staging_equals_device_resident_inputs(packed):
     batch = synth.make_batch(1000, synth.make_rig(cfg.V, "cmu"), seed=12)
     m = build_module(case["kw"], weights, "bf16")
     m.set_chunk_poses(256)                                           # 1000 = 3 * 256 + 232
+    if first is not None:
+        m.pipeline_first_poses = first                               # a short, unaligned first piece: 1000 = 100 + 3 * 256 + 132
     ref = run_module(m, batch, packed=packed)[0]                     # device-resident inputs
     V = cfg.V
     if packed:
