@@ -684,7 +684,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 
 // =====================================================================================================================
-// QKV projection + cross-view attention in ONE kernel (bf16 mode, LayerNorm folded, view tokens with hd = 136, V = 2 / 4 / 8)
+// QKV projection + cross-view attention in ONE kernel (bf16 mode, LayerNorm folded, view tokens with hd = 136, V = 2 .. 8)
 // -- multiview_mpl.py:48-64.  The q|k|v tensor (6.5 KB per row, written and re-read once per block application: a quarter
 // of all DRAM traffic of the step) never exists: an output tile is one HEAD of 256 rows, 3 * 136 + 8 = 416 accumulator
 // columns [q | k | v | pad] (W rows permuted / zero-padded per head at pack time and stored so that each CTA of the pair
@@ -732,7 +732,12 @@ template <int V>
 __global__ void __launch_bounds__(NUM_EPI_WARPS * 32 + 128, 1)
 qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const FusedAttnArgs a) {
-  static_assert(V == 2 || V == 4 || V == 8, "the views of a pose must be adjacent lanes of one warp");
+  // The views of a pose are adjacent lanes of one warp (= 32 TMEM lanes = one quarter of the CTA's rows): a quarter holds
+  // PQ whole poses = RQ rows.  V = 2, 4, 8 fill it; for the other view counts the row tiling is pose aligned instead of
+  // 128 aligned: every quarter is its own 32-row TMA box starting RQ rows after the previous one, its last 32 - RQ rows
+  // (and lanes) are the first rows of the next quarter again and are ignored.
+  static_assert(V >= 2 && V <= 8, "2 to 8 views");
+  constexpr int PQ = 32 / V, RQ = PQ * V;
   constexpr int BK = KB_BYTES / 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -775,13 +780,13 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int64_t m_tiles = (a.M + 2 * BM - 1) / (2 * BM);
+  const int64_t m_tiles = (a.M + 8 * RQ - 1) / (8 * RQ);
   const int64_t total_tiles = m_tiles * a.H;
   const int64_t first_tile = blockIdx.x / 2, tile_stride = gridDim.x / 2;
   const int num_kb = (a.K + BK - 1) / BK;
 
   if (warp == 0) {
-    // ---- TMA producer: A rows of this CTA (128 x 64 K elements) + its 208 W rows of the head ----
+    // ---- TMA producer: A rows of this CTA (4 quarters x 32 rows x 64 K elements) + its 208 W rows of the head ----
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -789,14 +794,20 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int64_t m_blk = tile / a.H;
         const int head = (int)(tile % a.H);
-        const int32_t m0 = (int32_t)(m_blk * 2 * BM + cta_rank * BM);
+        const int32_t m0 = (int32_t)((m_blk * 2 + cta_rank) * 4 * RQ);
         const int32_t n0 = head * FA_NT + (int32_t)cta_rank * FA_B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * FA_STAGE_BYTES, b_dst = a_dst + FA_A_BYTES;
           const uint32_t lbar = leader_full0 + 8u * stage;
           if (is_leader) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * FA_STAGE_BYTES);
-          ptx::tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
+          if constexpr (RQ == 32) {
+            ptx::tma_load_2d_pair(a_dst, &tmA, lbar, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)  // 32-row boxes: whole swizzle atoms of 8 rows, the same layout as one 128-row box
+              ptx::tma_load_2d_pair(a_dst + (uint32_t)(q * 32 * KB_BYTES), &tmA, lbar, kb * BK, m0 + q * RQ);
+          }
           ptx::tma_load_2d_pair(b_dst, &tmB, lbar, kb * BK, n0);
           if (++stage == FA_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -842,7 +853,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q4 = warp & 3, half = (warp - 4) >> 2;
     const int d_lo = half ? FA_D0 : 0, nchunks = half ? (FA_HD - FA_D0) / 8 : FA_D0 / 8;  // 8-dim chunks of this warp
     const int lrow = q4 * 32 + lane;                       // CTA-local row of this lane
-    const int prow0 = q4 * 32 + (lane / V) * V;            // first row (view 0) of this lane's pose
+    const int prow0 = q4 * 32 + min(lane / V, PQ - 1) * V;  // first row (view 0) of this lane's pose (lanes >= RQ: idle)
     const uint32_t k_row = kv_base + (uint32_t)lrow * FA_PITCH, v_row = k_row + BM * FA_PITCH;
     const uint32_t k_pose = kv_base + (uint32_t)prow0 * FA_PITCH, v_pose = k_pose + BM * FA_PITCH;
     const uint32_t leader_tempty = ptx::mapa(tempty_bar, 0);
@@ -850,12 +861,12 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const int64_t m_blk = tile / a.H;
       const int head = (int)(tile % a.H);
-      const int32_t row0 = (int32_t)(m_blk * 2 * BM + cta_rank * BM + q4 * 32);
+      const int32_t row0 = (int32_t)(((m_blk * 2 + cta_rank) * 4 + q4) * RQ);
       const int64_t my_row = (int64_t)row0 + lane;
       float mu = 0.f, rstd = 1.f;
       {
         float s1 = 0.f, s2 = 0.f;
-        if (my_row < a.M) {
+        if (lane < RQ && my_row < a.M) {
           const float2* sp = a.stats + my_row;
           for (int i = 0; i < a.slots; ++i) { const float2 t = sp[i * a.stats_ld]; s1 += t.x; s2 += t.y; }
         }
@@ -993,7 +1004,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::st_shared_v4(k_row + (uint32_t)(d_lo + 8 * c) * 2u, w[0], w[1], w[2], w[3]);
         }
       }
-      // ---- D: the quarter's 32 x 136 output box leaves by TMA ----
+      // ---- D: the quarter's RQ x 136 output box leaves by TMA ----
       ptx::fence_proxy_async();
       named_bar_sync(1 + q4, 64);
       if (half == 0 && lane == 0) {
@@ -1161,7 +1172,7 @@ TileSplit split_tiles(int N) {
 }  // namespace
 
 bool qkv_attn_supports(int D, int H, int tokens) {
-  return H >= 1 && D == H * FA_HD && (tokens == 2 || tokens == 4 || tokens == 8) && ((int64_t)D * 2) % 16 == 0;
+  return H >= 1 && D == H * FA_HD && tokens >= 2 && tokens <= 8 && ((int64_t)D * 2) % 16 == 0;
 }
 size_t qkv_attn_weight_elems(int D, int H) { return (size_t)H * FA_NT * D; }
 int qkv_attn_vec_len(int H) { return H * FA_NT; }
@@ -1179,13 +1190,14 @@ int launch_qkv_attn(const void* xb, const void* Wp, const float* bias_f, const f
                     float eps, void* att, int64_t M, int D, int H, int V, cudaStream_t s) {
   if (M == 0) return MPL_OK;
   if (!qkv_attn_supports(D, H, V) || M % V != 0) {
-    set_error("launch_qkv_attn: needs D = H * 136 and V in {2, 4, 8} (D=%d H=%d V=%d)", D, H, V);
+    set_error("launch_qkv_attn: needs D = H * 136, 2 <= V <= 8 and whole poses (D=%d H=%d V=%d)", D, H, V);
     return MPL_ERR_UNSUPPORTED;
   }
   CUtensorMap tmA, tmB, tmO;
-  MPL_TRY(make_tmap(&tmA, xb, M, D, 2, BM));
+  const int rq = (32 / V) * V;  // rows of a lane quarter: whole poses
+  MPL_TRY(make_tmap(&tmA, xb, M, D, 2, rq == 32 ? BM : 32));
   MPL_TRY(make_tmap(&tmB, Wp, (int64_t)H * FA_NT, D, 2, FA_B_ROWS));
-  MPL_TRY(make_tmap(&tmO, att, M, D, 2, 32, FA_HD, /*swizzle=*/false));
+  MPL_TRY(make_tmap(&tmO, att, M, D, 2, rq, FA_HD, /*swizzle=*/false));
   FusedAttnArgs a{};
   a.bias = bias_f;
   a.colsum = colsum;
@@ -1197,17 +1209,19 @@ int launch_qkv_attn(const void* xb, const void* Wp, const float* bias_f, const f
   a.M = M;
   a.K = D;
   a.H = H;
-  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, FusedAttnArgs) =
-      V == 2 ? qkv_attn_kernel<2> : (V == 4 ? qkv_attn_kernel<4> : qkv_attn_kernel<8>);
-  static std::atomic<unsigned char> attr_set[64][3];
-  const int vi = V == 2 ? 0 : (V == 4 ? 1 : 2);
+  void (*const kerns[7])(CUtensorMap, CUtensorMap, CUtensorMap, FusedAttnArgs) = {
+      qkv_attn_kernel<2>, qkv_attn_kernel<3>, qkv_attn_kernel<4>, qkv_attn_kernel<5>,
+      qkv_attn_kernel<6>, qkv_attn_kernel<7>, qkv_attn_kernel<8>};
+  const int vi = V - 2;
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, FusedAttnArgs) = kerns[vi];
+  static std::atomic<unsigned char> attr_set[64][7];
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev][vi].load(std::memory_order_acquire)) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
     if (dev >= 0 && dev < 64) attr_set[dev][vi].store(1, std::memory_order_release);
   }
-  const int64_t total = ceil_div(M, (int64_t)2 * BM) * H;
+  const int64_t total = ceil_div(M, (int64_t)8 * rq) * H;
   const unsigned groups = (unsigned)std::min<int64_t>(total, kNumSMs / 2);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * 2);

@@ -147,7 +147,7 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
                         int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* ln = nullptr, int cta_group = 2);
 bool gemm_tcgen05_supports(int N, int K, int dtype);
 
-// QKV projection + cross-view attention fused (bf16 mode, LayerNorm folded; D = H * 136, V in {2, 4, 8}): att [M, D] bf16 straight
+// QKV projection + cross-view attention fused (bf16 mode, LayerNorm folded; D = H * 136, 2 <= V <= 8): att [M, D] bf16 straight
 // from the raw residual rows xb [M, D] bf16 + their statistics -- no q|k|v tensor.  Wp / colsum / bias_f come from
 // launch_qkv_attn_pack (W [3D, D], b [3D] or null, LayerNorm gamma / beta, softmax scale).
 bool qkv_attn_supports(int D, int H, int tokens);

@@ -64,7 +64,7 @@ struct MplModel {
   bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
   bool spt_fused;  // the SPT stack runs as the single fused fp16-mma kernel (bf16 / tf32 modes, d=32, H=8, J=17)
   bool ln_fused;   // bf16 mode: the FPT LayerNorms are folded into the projection GEMMs (no LayerNorm kernel)
-  bool qkv_attn;      // bf16 LN-fused mode, view tokens, D = H * 136, V in {2, 4, 8}: QKV GEMM + cross-view attention are one kernel
+  bool qkv_attn;      // bf16 LN-fused mode, view tokens, D = H * 136, 2 <= V <= 8: QKV GEMM + cross-view attention are one kernel
   bool fpt_kp_fused;  // bf16 mode, keypoint-token FPT (width 32, 8 heads, J = 17): the whole FPT stack is one kernel launch
   int ln_slots;    // statistics slots per row written by the residual-emit GEMMs
   int cta_group;   // 1: one CTA per 128 x 256 GEMM tile, 2: CTA pairs per 256 x 256 tile (default)

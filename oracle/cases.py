@@ -25,7 +25,7 @@ CASES["cmu0_v2_d2"] = _case(dict(_COMMON, depth=2, num_views=2, **HM0_FLAGS), ri
 CASES["cmu_v5_d2_hm0flags"] = _case(dict(_COMMON, depth=2, num_views=5, **HM0_FLAGS), rig="cmu", batch=8)
 CASES["cmu_v5_d2_chosen"] = _case(dict(_COMMON, depth=2, num_views=5, **CHOSEN_FLAGS), rig="cmu", batch=8)
 # --- view-count sweep (config 4): view tokens and view x keypoint tokens -------------------------------
-for _v in (2, 3, 6, 8):
+for _v in (2, 3, 5, 6, 7, 8):
     CASES[f"sweep_viewtok_v{_v}"] = _case(dict(_COMMON, depth=2, num_views=_v, **HM0_FLAGS), batch=5, iseed=10 + _v)
     CASES[f"sweep_kptok_v{_v}"] = _case(dict(_COMMON, depth=2, num_views=_v, pose_3d_emb_learnable=True,
                                              FPT_blocks_view_keypoint_tokens=True), batch=5, iseed=20 + _v)

@@ -83,7 +83,10 @@ def main():
     if "--only-procrustes" in sys.argv:
         return
     torch.set_num_threads(os.cpu_count())
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]       # --only=name,name: just these cases
     for name, case in CASES.items():
+        if only and name not in only[0]:
+            continue
         cfg, weights, batch = make_inputs(case)
         out32 = run_reference(case["kw"], weights, batch, torch.float32)
         out64 = run_reference(case["kw"], weights, batch, torch.float64)
@@ -96,6 +99,8 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **arrays)
         print(f"{name}: out {out64[0].shape} scale {np.abs(out64[0]).max():.3f} "
               f"fp32-vs-fp64 {np.abs(out32[0] - out64[0]).max():.2e}")
+    if only:
+        return
     # validity grid: does the reference's constructor + first forward succeed?
     m = ref_loader.load_model_module()
     ok = np.zeros(1 << len(GRID_FLAGS), dtype=np.uint8)

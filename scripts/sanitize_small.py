@@ -23,7 +23,8 @@ for kw in CASES:
     for B in (1, 37, 300):
         batch = synth.make_batch(B, synth.make_rig(cfg.V), seed=2)
         for prec in ("fp32", "tf32", "bf16"):
-            m = MultiView_MPL(**kw, precision=prec)
+            # batches up to graph_batch replay a captured CUDA graph; B = 300 runs kernel by kernel
+            m = MultiView_MPL(**kw, precision=prec, graph_batch=64)
             m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
             m = m.cuda().eval()
             a = [torch.from_numpy(batch[k]).cuda() for k in ("poses", "rays", "centers")]
@@ -31,6 +32,14 @@ for kw in CASES:
                 out = m(a[0], rays=a[1], centers=a[2])
             torch.cuda.synchronize()
             assert torch.isfinite(out).all()
+            if B == 300 and prec == "bf16":                  # pipelined host staging: pinned host inputs over several chunks
+                m.set_chunk_poses(128)
+                m.pipeline_first_poses = 50
+                h = [torch.from_numpy(batch[k]).pin_memory() for k in ("poses", "rays", "centers")]
+                with torch.no_grad():
+                    out2 = m(h[0], rays=h[1], centers=h[2])
+                torch.cuda.synchronize()
+                assert torch.equal(out, out2)
 print("eval loop")
 evaluate.run(arch="cmu0", views=2, poses=700, micro_batch=256, precision="bf16")
 print("sanitize_small: done")

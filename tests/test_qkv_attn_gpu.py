@@ -20,7 +20,9 @@ def _al(n):
     return (n + 255) // 256 * 256
 
 
-@pytest.mark.parametrize("V,poses", [(4, 64), (4, 77), (2, 300), (8, 40), (4, 5000), (2, 9000), (8, 3000)])
+@pytest.mark.parametrize("V,poses", [(4, 64), (4, 77), (2, 300), (8, 40), (4, 5000), (2, 9000), (8, 3000),
+                                     # pose-aligned row tiling: 30 (V = 3, 5, 6) or 28 (V = 7) rows per 32-lane quarter
+                                     (3, 50), (5, 77), (6, 41), (7, 33), (5, 1), (3, 7001), (5, 4000), (6, 3000), (7, 2500)])
 def test_fused_qkv_attention_against_fp64(V, poses):
     L = _lib.lib()
     M = poses * V
@@ -73,4 +75,5 @@ def test_fused_qkv_attention_rejects_other_shapes():
     x = torch.zeros(1024, device="cuda")
     args = (x.data_ptr(),) * 6
     assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 12, 544, 8, 4, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
-    assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 12, 1088, 8, 3, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
+    assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 18, 1088, 8, 9, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
+    assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 12, 1088, 8, 1, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
