@@ -94,7 +94,7 @@ typedef struct MplDesc {
   int32_t gemm_cta_group; /* 0 / 2: CTA pair per 256x256 tile (cta_group::2, cluster 2x1x1); 1: one CTA per 128x256 tile */
   int32_t spt_hidden, fpt_hidden; /* int(width * mlp_ratio) of the SPT / FPT Mlp as the reference's float64 arithmetic gives it
                                      (0 = derive from the float mlp_ratio above) */
-  int32_t qkv_attn_fusion; /* bf16 LayerNorm-fused mode, view tokens, D = 8 x 136-wide heads, 2 to 8 views: QKV projection and
+  int32_t qkv_attn_fusion; /* bf16 LayerNorm-fused mode, view tokens, 136-wide heads (or an even number of 68-wide ones), 2 to 8 views: QKV projection and
                               cross-view attention run as ONE kernel (no q|k|v tensor).  0 = two kernels, non-zero (make_desc
                               default: 1) = fused where the shape allows */
   int32_t chunk_streams;  /* 0 / 1: one pose chunk at a time on the caller's stream (default).  2: batches of >= 16384 poses
@@ -233,7 +233,7 @@ int mpl_test_gemm_ln(const void* A, const void* W, const float* bias, void* Y, i
 int mpl_test_gemm_ln_slots(int N);
 /* The fused QKV projection + cross-view attention kernel (multiview_mpl.py:48-64 behind the folded norm1) in isolation:
  *   xb [M, D] bf16 raw residual rows, W [3D, D] / bias [3D] (or NULL) / gamma, beta [D] fp32 on the device, stats as above,
- *   att [M, D] bf16 out; M = poses * V rows, D = H * 136, 2 <= V <= 8.
+ *   att [M, D] bf16 out; M = poses * V rows, D = H * 136 (or H * 68, H even), 2 <= V <= 8.
  *   scratch: device buffer of at least align256(H*416*D*2) + 2 * align256(H*416*4) bytes for the packed operands. */
 int mpl_test_qkv_attn(const void* xb, const float* W, const float* bias, const float* gamma, const float* beta,
                       const void* stats, int slots, float eps, float scale, void* att, int64_t M, int D, int H, int V,

@@ -25,6 +25,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -704,8 +705,9 @@ constexpr int FA_B_ROWS = FA_NT / 2;                          // W rows per CTA 
 constexpr int FA_A_BYTES = BM * KB_BYTES, FA_B_BYTES = FA_B_ROWS * KB_BYTES;
 constexpr int FA_STAGE_BYTES = FA_A_BYTES + FA_B_BYTES;       // 43 008
 constexpr int FA_STAGES = 3;
-constexpr int FA_PITCH = FA_HD * 2;                           // bytes per row of the k / v / output exchange buffers (272)
-constexpr int FA_KV_BYTES = 2 * BM * FA_PITCH;                // k rows then v rows of the CTA's 128 rows
+constexpr int FA_PITCH = FA_HD * 2;                           // bytes per row of the output box, and of the k / v rows for hd = 136 (272)
+constexpr int FA_PITCH2 = 288;                                // k / v row pitch for hd = 68: two heads at byte offsets 0 and 144
+constexpr int FA_KV_BYTES = 2 * BM * FA_PITCH2;               // k rows then v rows of the CTA's 128 rows
 constexpr int FA_D0 = 72;                                     // dims of epilogue half 0 ([0, 72)); half 1 takes [72, 136)
 constexpr int FA_PART_BYTES = 2 * BM * 8 * 4;                 // partial scores [half][row][<= 8 views]
 constexpr int FA_BC_WARP_BYTES = 3 * FA_D0 * 8;               // per epilogue warp: (bias, colsum) of its 3 x 72 columns of the head
@@ -728,7 +730,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int V>
+// HD = 136: a tile is one head, the two epilogue warps of a lane quarter split its dims 72 / 64 and exchange partial scores.
+// HD = 68 (the "chosen" architecture, D = 544): a tile is a PAIR of heads -- accumulator columns [208 e, 208 e + 204) = q | k | v
+// of head 2 t + e, one N = 208 UMMA each -- and the two epilogue warps of a quarter take one head each, all 68 dims.
+template <int V, int HD>
 __global__ void __launch_bounds__(NUM_EPI_WARPS * 32 + 128, 1)
 qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const FusedAttnArgs a) {
@@ -737,7 +742,10 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // 128 aligned: every quarter is its own 32-row TMA box starting RQ rows after the previous one, its last 32 - RQ rows
   // (and lanes) are the first rows of the next quarter again and are ignored.
   static_assert(V >= 2 && V <= 8, "2 to 8 views");
+  static_assert(HD == 136 || HD == 68, "136-wide heads, or pairs of 68-wide heads");
   constexpr int PQ = 32 / V, RQ = PQ * V;
+  constexpr bool PAIR = HD == 68;
+  constexpr int KVP = PAIR ? FA_PITCH2 : FA_PITCH;  // bytes per k / v row
   constexpr int BK = KB_BYTES / 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -851,11 +859,18 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= 4) {
     // ---- epilogue ----
     const int q4 = warp & 3, half = (warp - 4) >> 2;
-    const int d_lo = half ? FA_D0 : 0, nchunks = half ? (FA_HD - FA_D0) / 8 : FA_D0 / 8;  // 8-dim chunks of this warp
+    // dims [d_lo, d_lo + nd) of the head this warp works on: nchunks whole 8-dim chunks (+ a 4-dim tail for 68-wide heads)
+    const int d_lo = (!PAIR && half) ? FA_D0 : 0;
+    const int nd = PAIR ? 68 : (half ? FA_HD - FA_D0 : FA_D0), nchunks = nd / 8;
+    const uint32_t cbase = PAIR ? (uint32_t)(half * FA_UW) : 0u;  // accumulator column of the head
+    const uint32_t hoff = PAIR ? (uint32_t)(half * (FA_PITCH2 / 2)) : 0u;  // byte offset of the head inside a k / v row
     const int lrow = q4 * 32 + lane;                       // CTA-local row of this lane
     const int prow0 = q4 * 32 + min(lane / V, PQ - 1) * V;  // first row (view 0) of this lane's pose (lanes >= RQ: idle)
-    const uint32_t k_row = kv_base + (uint32_t)lrow * FA_PITCH, v_row = k_row + BM * FA_PITCH;
-    const uint32_t k_pose = kv_base + (uint32_t)prow0 * FA_PITCH, v_pose = k_pose + BM * FA_PITCH;
+    const uint32_t k_row = kv_base + (uint32_t)lrow * KVP + hoff, v_row = k_row + BM * KVP;
+    const uint32_t k_pose = kv_base + (uint32_t)prow0 * KVP + hoff, v_pose = k_pose + BM * KVP;
+    // the quarter's dense output box (RQ rows of 272 B) takes the place of its k rows once the scores are done
+    const uint32_t o_box = kv_base + (uint32_t)(q4 * 32) * KVP;
+    const uint32_t o_row = o_box + (uint32_t)lane * FA_PITCH + (PAIR ? (uint32_t)(half * HD * 2) : 0u);
     const uint32_t leader_tempty = ptx::mapa(tempty_bar, 0);
     uint32_t acc_phase = 0;
     for (int64_t tile = first_tile; tile < total_tiles; tile += tile_stride) {
@@ -875,11 +890,10 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       // (bias, colsum) of this warp's 3 x nd columns of the head -> its shared-memory scratch, while the MMAs of the tile run
       // (the accumulator is single-buffered: everything between its completion and its release is serial time)
-      const int nd = 8 * nchunks;
       const uint32_t bc = bc_base + (uint32_t)(warp - 4) * FA_BC_WARP_BYTES;
       for (int idx = lane; idx < 3 * nd / 2; idx += 32) {  // per pair of dims: (bias d, bias d+1, colsum d, colsum d+1)
         const int part = idx / (nd / 2), d = 2 * (idx - part * (nd / 2));
-        const int n = head * FA_NT + part * FA_HD + d_lo + d;
+        const int n = head * FA_NT + (int)cbase + part * HD + d_lo + d;
         const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.bias + n)), c2 = __ldg(reinterpret_cast<const float2*>(a.colsum + n));
         ptx::st_shared_v4(bc + (uint32_t)idx * 16u, __float_as_uint(b2.x), __float_as_uint(b2.y), __float_as_uint(c2.x), __float_as_uint(c2.y));
       }
@@ -895,15 +909,21 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int part = 0; part < 3; ++part) {
         uint32_t r0[32], r1[32], r2[8];
-        const uint32_t col0 = (uint32_t)(part * FA_HD + d_lo);
+        const uint32_t col0 = cbase + (uint32_t)(part * HD + d_lo);
         ptx::tmem_ld_32x32(taddr + col0, r0);
         ptx::tmem_ld_32x32(taddr + col0 + 32, r1);
-        if (half == 0) ptx::tmem_ld_32x8(taddr + col0 + 64, r2);
+        if constexpr (PAIR) {
+          ptx::tmem_ld_32x4(taddr + col0 + 64, r2);
+        } else {
+          if (half == 0) ptx::tmem_ld_32x8(taddr + col0 + 64, r2);
+        }
         ptx::tmem_ld_wait();
-        auto chunk = [&](const uint32_t* r, int c) {  // 8 dims: LayerNorm-apply, bias, bf16 pairs (packed f32x2 arithmetic)
-          uint32_t w[4];
+        // NP dim pairs starting at dim 8 c: LayerNorm-apply, bias, bf16 pairs (packed f32x2 arithmetic)
+        auto chunk = [&](const uint32_t* r, int c, auto np) {
+          constexpr int NP = decltype(np)::value;
+          uint32_t w[NP];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < NP; ++i) {
             float4 t;  // (bias d, bias d+1, colsum d, colsum d+1) of dims d = 2i, 2i + 1 of the chunk
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
@@ -915,59 +935,82 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (part == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) qreg[4 * c + i] = w[i];
+            for (int i = 0; i < NP; ++i) qreg[4 * c + i] = w[i];
           } else {
-            ptx::st_shared_v4((part == 1 ? k_row : v_row) + (uint32_t)(d_lo + 8 * c) * 2u, w[0], w[1], w[2], w[3]);
+            const uint32_t dst = (part == 1 ? k_row : v_row) + (uint32_t)(d_lo + 8 * c) * 2u;
+            if constexpr (NP == 4) ptx::st_shared_v4(dst, w[0], w[1], w[2], w[3]);
+            else ptx::st_shared_v2(dst, w[0], w[1]);
           }
         };
 #pragma unroll
-        for (int c = 0; c < 4; ++c) chunk(&r0[8 * c], c);
+        for (int c = 0; c < 4; ++c) chunk(&r0[8 * c], c, std::integral_constant<int, 4>{});
 #pragma unroll
-        for (int c = 0; c < 4; ++c) chunk(&r1[8 * c], 4 + c);
-        if (half == 0) chunk(r2, 8);
+        for (int c = 0; c < 4; ++c) chunk(&r1[8 * c], 4 + c, std::integral_constant<int, 4>{});
+        if constexpr (PAIR) {
+          chunk(r2, 8, std::integral_constant<int, 2>{});
+        } else {
+          if (half == 0) chunk(r2, 8, std::integral_constant<int, 4>{});
+        }
       }
       // the accumulator is free: the next tile's MMAs run under the rest of this epilogue
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(leader_tempty);
       acc_phase ^= 1u;
-      // ---- B: partial scores over this warp's dims ----
+      // ---- B: (partial) scores over this warp's dims ----
       float2 s2[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) s2[j] = make_float2(0.f, 0.f);
+      auto bf_lo = [](uint32_t w) { return __uint_as_float(w << 16); };
+      auto bf_hi = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
 #pragma unroll
       for (int c = 0; c < FA_D0 / 8; ++c) {
         if (c < nchunks) {
           float2 q2[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) q2[i] = make_float2(__uint_as_float(qreg[4 * c + i] << 16), __uint_as_float(qreg[4 * c + i] & 0xffff0000u));
+          for (int i = 0; i < 4; ++i) q2[i] = make_float2(bf_lo(qreg[4 * c + i]), bf_hi(qreg[4 * c + i]));
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             uint32_t kw[4];
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(kw[0]), "=r"(kw[1]), "=r"(kw[2]), "=r"(kw[3])
-                         : "r"(k_pose + (uint32_t)j * FA_PITCH + (uint32_t)(d_lo + 8 * c) * 2u));
+                         : "r"(k_pose + (uint32_t)j * KVP + (uint32_t)(d_lo + 8 * c) * 2u));
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              s2[j] = __ffma2_rn(q2[i], make_float2(__uint_as_float(kw[i] << 16), __uint_as_float(kw[i] & 0xffff0000u)), s2[j]);
+            for (int i = 0; i < 4; ++i) s2[j] = __ffma2_rn(q2[i], make_float2(bf_lo(kw[i]), bf_hi(kw[i])), s2[j]);
           }
         }
       }
-      {
+      if constexpr (PAIR) {  // dims 64 .. 67
+        float2 q2[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) q2[i] = make_float2(bf_lo(qreg[32 + i]), bf_hi(qreg[32 + i]));
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          uint32_t kw[2];
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(kw[0]), "=r"(kw[1]) : "r"(k_pose + (uint32_t)j * KVP + 128u));
+#pragma unroll
+          for (int i = 0; i < 2; ++i) s2[j] = __ffma2_rn(q2[i], make_float2(bf_lo(kw[i]), bf_hi(kw[i])), s2[j]);
+        }
+      }
+      float p[V];
+      if constexpr (!PAIR) {
         const uint32_t mine = part_base + (uint32_t)((half * BM + lrow) * 8) * 4u;
 #pragma unroll
         for (int j = 0; j < V; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(mine + 4u * j), "f"(s2[j].x + s2[j].y) : "memory");
       }
-      named_bar_sync(1 + q4, 64);  // both halves' partial sums are in place (and both are done reading the k rows)
-      float p[V];
+      named_bar_sync(1 + q4, 64);  // both warps of the quarter are done reading its k rows (and the partial sums are in place)
       {
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          float s0, s1;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s0) : "r"(part_base + (uint32_t)((lrow) * 8 + j) * 4u));
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s1) : "r"(part_base + (uint32_t)((BM + lrow) * 8 + j) * 4u));
-          p[j] = s0 + s1;  // fixed order: bitwise the same in both warps
+          if constexpr (PAIR) {
+            p[j] = s2[j].x + s2[j].y;
+          } else {
+            float s0, s1;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s0) : "r"(part_base + (uint32_t)((lrow) * 8 + j) * 4u));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s1) : "r"(part_base + (uint32_t)((BM + lrow) * 8 + j) * 4u));
+            p[j] = s0 + s1;  // fixed order: bitwise the same in both warps
+          }
           mx = fmaxf(mx, p[j]);
         }
         float sum = 0.f;
@@ -977,7 +1020,7 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < V; ++j) p[j] *= inv;
       }
-      // ---- C: o = sum_j p_j v_j over this warp's dims, into the k row of this lane (free since the barrier above) ----
+      // ---- C: o = sum_j p_j v_j over this warp's dims, into the quarter's output box (its k rows: free since the barrier) ----
 #pragma unroll
       for (int c = 0; c < FA_D0 / 8; ++c) {
         if (c < nchunks) {
@@ -989,11 +1032,10 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t vw[4];
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(vw[0]), "=r"(vw[1]), "=r"(vw[2]), "=r"(vw[3])
-                         : "r"(v_pose + (uint32_t)j * FA_PITCH + (uint32_t)(d_lo + 8 * c) * 2u));
+                         : "r"(v_pose + (uint32_t)j * KVP + (uint32_t)(d_lo + 8 * c) * 2u));
             const float2 pj = make_float2(p[j], p[j]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o2[i] = __ffma2_rn(pj, make_float2(__uint_as_float(vw[i] << 16), __uint_as_float(vw[i] & 0xffff0000u)), o2[i]);
+            for (int i = 0; i < 4; ++i) o2[i] = __ffma2_rn(pj, make_float2(bf_lo(vw[i]), bf_hi(vw[i])), o2[i]);
           }
           uint32_t w[4];
 #pragma unroll
@@ -1001,14 +1043,33 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const __nv_bfloat162 t = __float22bfloat162_rn(o2[i]);
             w[i] = *reinterpret_cast<const uint32_t*>(&t);
           }
-          ptx::st_shared_v4(k_row + (uint32_t)(d_lo + 8 * c) * 2u, w[0], w[1], w[2], w[3]);
+          const uint32_t dst = o_row + (uint32_t)(d_lo + 8 * c) * 2u;
+          if constexpr (PAIR) {  // head 1 starts 136 B into the row: 8-byte aligned only
+            ptx::st_shared_v2(dst, w[0], w[1]);
+            ptx::st_shared_v2(dst + 8u, w[2], w[3]);
+          } else {
+            ptx::st_shared_v4(dst, w[0], w[1], w[2], w[3]);
+          }
         }
+      }
+      if constexpr (PAIR) {  // dims 64 .. 67
+        float2 o2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          uint32_t vw[2];
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(vw[0]), "=r"(vw[1]) : "r"(v_pose + (uint32_t)j * KVP + 128u));
+          const float2 pj = make_float2(p[j], p[j]);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) o2[i] = __ffma2_rn(pj, make_float2(bf_lo(vw[i]), bf_hi(vw[i])), o2[i]);
+        }
+        const __nv_bfloat162 t0 = __float22bfloat162_rn(o2[0]), t1 = __float22bfloat162_rn(o2[1]);
+        ptx::st_shared_v2(o_row + 128u, *reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1));
       }
       // ---- D: the quarter's RQ x 136 output box leaves by TMA ----
       ptx::fence_proxy_async();
       named_bar_sync(1 + q4, 64);
       if (half == 0 && lane == 0) {
-        ptx::tma_store_2d(&tmO, kv_base + (uint32_t)(q4 * 32) * FA_PITCH, head * FA_HD, row0);
+        ptx::tma_store_2d(&tmO, o_box, head * FA_HD, row0);
         ptx::bulk_commit();
       }
     }
@@ -1023,23 +1084,30 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-// pack: W [3D, D] fp32, LayerNorm gamma / beta folded, q rows scaled by qscale -> W'' [H * 416, D] bf16 in the PHYSICAL row
-// order of the kernel (per head: CTA 0 rows {[0,104) | [208,312)}, CTA 1 rows {[104,208) | [312,416)} of the logical
-// [q | k | v | pad] order), colsum / bias [H * 416] fp32 in LOGICAL order
+// pack: W [3D, D] fp32, LayerNorm gamma / beta folded, q rows scaled by qscale -> W'' [tiles * 416, D] bf16 in the PHYSICAL row
+// order of the kernel (per tile: CTA 0 rows {[0,104) | [208,312)}, CTA 1 rows {[104,208) | [312,416)} of the logical column
+// order), colsum / bias [tiles * 416] fp32 in LOGICAL order.  Logical columns of a tile: hd = 136: [q | k | v | 8 pad] of head
+// t; hd = 68: [q | k | v | 4 pad] of head 2 t, then the same of head 2 t + 1.
 __global__ void __launch_bounds__(256) qkv_attn_pack_kernel(const float* __restrict__ W, const float* __restrict__ b,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            __nv_bfloat16* __restrict__ Wp, float* __restrict__ colsum,
-                                                           float* __restrict__ bias_f, int H, int D, float qscale) {
+                                                           float* __restrict__ bias_f, int tiles, int HD, int D, float qscale) {
   const int pr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // physical row
-  if (pr >= H * FA_NT) return;
+  if (pr >= tiles * FA_NT) return;
   const int lane = threadIdx.x & 31;
-  const int head = pr / FA_NT, within = pr % FA_NT;
+  const int tile = pr / FA_NT, within = pr % FA_NT;
   const int r = within / (FA_NT / 2), rem = within % (FA_NT / 2);
   const int u = rem / (FA_UW / 2), i = rem % (FA_UW / 2);
   const int logical = u * FA_UW + r * (FA_UW / 2) + i;
-  const int part = logical / FA_HD, d = logical % FA_HD;
+  int part, d, head;
+  if (HD == FA_HD) {
+    part = logical / FA_HD, d = logical % FA_HD, head = tile;
+  } else {
+    const int e = logical / FA_UW, l2 = logical % FA_UW;
+    part = l2 / HD, d = l2 % HD, head = 2 * tile + e;
+  }
   const bool live = part < 3;
-  const int src = part * D + head * FA_HD + d;
+  const int src = part * D + head * HD + d;
   const float sc = (part == 0) ? qscale : 1.0f;
   float cs = 0.f, bb = 0.f;
   for (int k = lane; k < D; k += 32) {
@@ -1052,8 +1120,8 @@ __global__ void __launch_bounds__(256) qkv_attn_pack_kernel(const float* __restr
   cs = warp_sum(cs);
   bb = warp_sum(bb);
   if (lane == 0) {
-    colsum[head * FA_NT + logical] = cs;
-    bias_f[head * FA_NT + logical] = live ? ((b != nullptr ? b[src] : 0.f) + bb) * sc : 0.f;
+    colsum[tile * FA_NT + logical] = cs;
+    bias_f[tile * FA_NT + logical] = live ? ((b != nullptr ? b[src] : 0.f) + bb) * sc : 0.f;
   }
 }
 
@@ -1171,17 +1239,20 @@ TileSplit split_tiles(int N) {
 
 }  // namespace
 
+static int qkv_attn_tiles(int D, int H) { return D == H * FA_HD ? H : H / 2; }  // head tiles: one 136-wide head or two 68-wide ones
+
 bool qkv_attn_supports(int D, int H, int tokens) {
-  return H >= 1 && D == H * FA_HD && tokens >= 2 && tokens <= 8 && ((int64_t)D * 2) % 16 == 0;
+  const bool shape = H >= 1 && (D == H * FA_HD || (D == H * (FA_HD / 2) && H % 2 == 0));
+  return shape && tokens >= 2 && tokens <= 8 && ((int64_t)D * 2) % 16 == 0;
 }
-size_t qkv_attn_weight_elems(int D, int H) { return (size_t)H * FA_NT * D; }
-int qkv_attn_vec_len(int H) { return H * FA_NT; }
+size_t qkv_attn_weight_elems(int D, int H) { return (size_t)qkv_attn_tiles(D, H) * FA_NT * D; }
+int qkv_attn_vec_len(int D, int H) { return qkv_attn_tiles(D, H) * FA_NT; }
 
 int launch_qkv_attn_pack(const float* W, const float* b, const float* gamma, const float* beta, void* Wp, float* colsum,
                          float* bias_f, int H, int D, float scale, cudaStream_t s) {
-  const int rows = H * FA_NT;
+  const int tiles = qkv_attn_tiles(D, H), rows = tiles * FA_NT;
   qkv_attn_pack_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, s>>>(W, b, gamma, beta, reinterpret_cast<__nv_bfloat16*>(Wp), colsum,
-                                                                 bias_f, H, D, scale * 1.4426950408889634f);
+                                                                 bias_f, tiles, D / H, D, scale * 1.4426950408889634f);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
@@ -1190,13 +1261,15 @@ int launch_qkv_attn(const void* xb, const void* Wp, const float* bias_f, const f
                     float eps, void* att, int64_t M, int D, int H, int V, cudaStream_t s) {
   if (M == 0) return MPL_OK;
   if (!qkv_attn_supports(D, H, V) || M % V != 0) {
-    set_error("launch_qkv_attn: needs D = H * 136, 2 <= V <= 8 and whole poses (D=%d H=%d V=%d)", D, H, V);
+    set_error("launch_qkv_attn: needs D = H * 136 (or H * 68, H even), 2 <= V <= 8 and whole poses (D=%d H=%d V=%d)", D, H, V);
     return MPL_ERR_UNSUPPORTED;
   }
+  const int tiles = qkv_attn_tiles(D, H);
+  const bool pair = tiles != H;
   CUtensorMap tmA, tmB, tmO;
   const int rq = (32 / V) * V;  // rows of a lane quarter: whole poses
   MPL_TRY(make_tmap(&tmA, xb, M, D, 2, rq == 32 ? BM : 32));
-  MPL_TRY(make_tmap(&tmB, Wp, (int64_t)H * FA_NT, D, 2, FA_B_ROWS));
+  MPL_TRY(make_tmap(&tmB, Wp, (int64_t)tiles * FA_NT, D, 2, FA_B_ROWS));
   MPL_TRY(make_tmap(&tmO, att, M, D, 2, rq, FA_HD, /*swizzle=*/false));
   FusedAttnArgs a{};
   a.bias = bias_f;
@@ -1208,20 +1281,23 @@ int launch_qkv_attn(const void* xb, const void* Wp, const float* bias_f, const f
   a.eps = eps;
   a.M = M;
   a.K = D;
-  a.H = H;
-  void (*const kerns[7])(CUtensorMap, CUtensorMap, CUtensorMap, FusedAttnArgs) = {
-      qkv_attn_kernel<2>, qkv_attn_kernel<3>, qkv_attn_kernel<4>, qkv_attn_kernel<5>,
-      qkv_attn_kernel<6>, qkv_attn_kernel<7>, qkv_attn_kernel<8>};
-  const int vi = V - 2;
-  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, FusedAttnArgs) = kerns[vi];
-  static std::atomic<unsigned char> attr_set[64][7];
+  a.H = tiles;
+  typedef void (*Kern)(CUtensorMap, CUtensorMap, CUtensorMap, FusedAttnArgs);
+  static const Kern kerns[2][7] = {
+      {qkv_attn_kernel<2, 136>, qkv_attn_kernel<3, 136>, qkv_attn_kernel<4, 136>, qkv_attn_kernel<5, 136>, qkv_attn_kernel<6, 136>,
+       qkv_attn_kernel<7, 136>, qkv_attn_kernel<8, 136>},
+      {qkv_attn_kernel<2, 68>, qkv_attn_kernel<3, 68>, qkv_attn_kernel<4, 68>, qkv_attn_kernel<5, 68>, qkv_attn_kernel<6, 68>,
+       qkv_attn_kernel<7, 68>, qkv_attn_kernel<8, 68>}};
+  const int vi = V - 2, hi = pair ? 1 : 0;
+  const Kern kern = kerns[hi][vi];
+  static std::atomic<unsigned char> attr_set[64][2][7];
   int dev = 0;
   MPL_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_set[dev][vi].load(std::memory_order_acquire)) {
+  if (dev < 0 || dev >= 64 || !attr_set[dev][hi][vi].load(std::memory_order_acquire)) {
     MPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    if (dev >= 0 && dev < 64) attr_set[dev][vi].store(1, std::memory_order_release);
+    if (dev >= 0 && dev < 64) attr_set[dev][hi][vi].store(1, std::memory_order_release);
   }
-  const int64_t total = ceil_div(M, (int64_t)8 * rq) * H;
+  const int64_t total = ceil_div(M, (int64_t)8 * rq) * tiles;
   const unsigned groups = (unsigned)std::min<int64_t>(total, kNumSMs / 2);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * 2);

@@ -147,12 +147,12 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
                         int epilogue, int out_fp32, cudaStream_t s, const GemmLnArgs* ln = nullptr, int cta_group = 2);
 bool gemm_tcgen05_supports(int N, int K, int dtype);
 
-// QKV projection + cross-view attention fused (bf16 mode, LayerNorm folded; D = H * 136, 2 <= V <= 8): att [M, D] bf16 straight
+// QKV projection + cross-view attention fused (bf16 mode, LayerNorm folded; D = H * 136 or H * 68 with H even, 2 <= V <= 8): att [M, D] bf16 straight
 // from the raw residual rows xb [M, D] bf16 + their statistics -- no q|k|v tensor.  Wp / colsum / bias_f come from
 // launch_qkv_attn_pack (W [3D, D], b [3D] or null, LayerNorm gamma / beta, softmax scale).
 bool qkv_attn_supports(int D, int H, int tokens);
 size_t qkv_attn_weight_elems(int D, int H);  // bf16 elements of Wp
-int qkv_attn_vec_len(int H);                 // floats of colsum / bias_f
+int qkv_attn_vec_len(int D, int H);          // floats of colsum / bias_f
 int launch_qkv_attn_pack(const float* W, const float* b, const float* gamma, const float* beta, void* Wp, float* colsum,
                          float* bias_f, int H, int D, float scale, cudaStream_t s);
 int launch_qkv_attn(const void* xb, const void* Wp, const float* bias_f, const float* colsum, const void* stats, int slots,

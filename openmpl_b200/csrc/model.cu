@@ -64,7 +64,7 @@ struct MplModel {
   bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
   bool spt_fused;  // the SPT stack runs as the single fused fp16-mma kernel (bf16 / tf32 modes, d=32, H=8, J=17)
   bool ln_fused;   // bf16 mode: the FPT LayerNorms are folded into the projection GEMMs (no LayerNorm kernel)
-  bool qkv_attn;      // bf16 LN-fused mode, view tokens, D = H * 136, 2 <= V <= 8: QKV GEMM + cross-view attention are one kernel
+  bool qkv_attn;      // bf16 LN-fused mode, view tokens, D = H * 136 (or H * 68), 2 <= V <= 8: QKV GEMM + cross-view attention are one kernel
   bool fpt_kp_fused;  // bf16 mode, keypoint-token FPT (width 32, 8 heads, J = 17): the whole FPT stack is one kernel launch
   int ln_slots;    // statistics slots per row written by the residual-emit GEMMs
   int cta_group;   // 1: one CTA per 128 x 256 GEMM tile, 2: CTA pairs per 256 x 256 tile (default)
@@ -278,8 +278,8 @@ static void build_tables(MplModel* m) {
       if (m->ln_fused) {
         if (m->qkv_attn) {
           add_derived(m, "qaw:" + p + "attn.qkv", (int64_t)qkv_attn_weight_elems((int)D, m->H), 2);
-          add_derived(m, "qacs:" + p + "attn.qkv", qkv_attn_vec_len(m->H), 4);
-          add_derived(m, "qab:" + p + "attn.qkv", qkv_attn_vec_len(m->H), 4);
+          add_derived(m, "qacs:" + p + "attn.qkv", qkv_attn_vec_len((int)D, m->H), 4);
+          add_derived(m, "qab:" + p + "attn.qkv", qkv_attn_vec_len((int)D, m->H), 4);
         } else {
           add_derived(m, "lnw:" + p + "attn.qkv", 3 * D * D, 2);
           add_derived(m, "lncs:" + p + "attn.qkv", 3 * D, 4);
@@ -1307,7 +1307,7 @@ int mpl_test_qkv_attn(const void* xb, const float* W, const float* bias, const f
     set_error("mpl_test_qkv_attn: unsupported shape (D=%d H=%d V=%d)", D, H, V);
     return MPL_ERR_UNSUPPORTED;
   }
-  const size_t wbytes = align_up(qkv_attn_weight_elems(D, H) * 2, 256), vbytes = align_up((size_t)qkv_attn_vec_len(H) * 4, 256);
+  const size_t wbytes = align_up(qkv_attn_weight_elems(D, H) * 2, 256), vbytes = align_up((size_t)qkv_attn_vec_len(D, H) * 4, 256);
   if (scratch == nullptr || scratch_bytes < wbytes + 2 * vbytes) {
     set_error("mpl_test_qkv_attn: scratch has %zu bytes, %zu needed", scratch_bytes, wbytes + 2 * vbytes);
     return MPL_ERR_WORKSPACE;

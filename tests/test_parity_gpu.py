@@ -231,9 +231,10 @@ def test_cuda_graph_small_batch_path_equals_the_plain_path(precision):
 
 
 @pytest.mark.parametrize("name", ["hm0_v4_d12", "cmu0_v2_d2", "sweep_viewtok_v8", "sweep_viewtok_v2", "cmu_v5_d2_hm0flags",
-                                  "sweep_viewtok_v3", "sweep_viewtok_v5", "sweep_viewtok_v6", "sweep_viewtok_v7"])
+                                  "sweep_viewtok_v3", "sweep_viewtok_v5", "sweep_viewtok_v6", "sweep_viewtok_v7",
+                                  "chosen_v4_d12", "cmu_v5_d2_chosen"])
 def test_fused_qkv_attention_on_and_off_agree_with_the_reference(name):
-    """bf16 mode runs the QKV projection and the cross-view attention as ONE kernel for 2 to 8 views of 136-wide heads (no
+    """bf16 mode runs the QKV projection and the cross-view attention as ONE kernel for 2 to 8 views of 136- or 68-wide heads (no
     q|k|v tensor); the two-kernel form stays selectable (`qkv_attn_fusion=False`) and serves every other shape.  Both must
     meet the bf16 bound against the reference goldens and agree with each other; a large batch covers many tiles per CTA."""
     case = CASES[name]

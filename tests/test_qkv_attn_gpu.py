@@ -8,8 +8,7 @@ import torch
 from openmpl_b200 import _lib
 
 pytestmark = pytest.mark.gpu
-H, HD = 8, 136
-D = H * HD
+H = 8
 
 
 def _pad256(m):
@@ -23,10 +22,15 @@ def _al(n):
 @pytest.mark.parametrize("V,poses", [(4, 64), (4, 77), (2, 300), (8, 40), (4, 5000), (2, 9000), (8, 3000),
                                      # pose-aligned row tiling: 30 (V = 3, 5, 6) or 28 (V = 7) rows per 32-lane quarter
                                      (3, 50), (5, 77), (6, 41), (7, 33), (5, 1), (3, 7001), (5, 4000), (6, 3000), (7, 2500)])
-def test_fused_qkv_attention_against_fp64(V, poses):
+@pytest.mark.parametrize("HD", [136, 68])
+def test_fused_qkv_attention_against_fp64(V, poses, HD):
+    """HD = 136: one head per 416-column tile (hm_0, D = 1088); HD = 68: two heads per tile (the "chosen" architecture, D = 544,
+    whose K = 544 ends in half a K block that TMA zero-fills)."""
     L = _lib.lib()
+    D = H * HD
+    tiles = H if HD == 136 else H // 2
     M = poses * V
-    g = torch.Generator(device="cuda").manual_seed(V * 1000 + poses)
+    g = torch.Generator(device="cuda").manual_seed(V * 1000 + poses + HD)
     x = torch.randn(M, D, device="cuda", generator=g) * 0.8 + 0.05 * torch.randn(M, 1, device="cuda", generator=g)
     gamma = 1.0 + 0.1 * torch.randn(D, device="cuda", generator=g)
     beta = 0.1 * torch.randn(D, device="cuda", generator=g)
@@ -41,7 +45,7 @@ def test_fused_qkv_attention_against_fp64(V, poses):
     stats[3, :M, 0] = x[:, h:].sum(1); stats[3, :M, 1] = (x[:, h:] ** 2).sum(1)
     eps, scale = 1e-6, HD ** -0.5
     att = torch.full((M, D), float("nan"), device="cuda", dtype=torch.bfloat16)
-    scratch = torch.empty(_al(H * 416 * D * 2) + 2 * _al(H * 416 * 4), dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(_al(tiles * 416 * D * 2) + 2 * _al(tiles * 416 * 4), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     _lib.check(L.mpl_test_qkv_attn(xb.data_ptr(), W.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
                                    slots, eps, scale, att.data_ptr(), M, D, H, V, scratch.data_ptr(), scratch.numel(), stream))
@@ -74,6 +78,7 @@ def test_fused_qkv_attention_rejects_other_shapes():
     L = _lib.lib()
     x = torch.zeros(1024, device="cuda")
     args = (x.data_ptr(),) * 6
-    assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 12, 544, 8, 4, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
+    assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 12, 600, 8, 4, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
+    assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 12, 476, 7, 4, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
     assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 18, 1088, 8, 9, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
     assert L.mpl_test_qkv_attn(*args, 2, 1e-6, 0.1, x.data_ptr(), 12, 1088, 8, 1, x.data_ptr(), 4096, None) == _lib.MPL_ERR_UNSUPPORTED
