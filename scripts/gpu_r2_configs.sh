@@ -8,7 +8,7 @@ run --arch chosen
 run --arch cmu0 --views 5
 run --arch cmu0 --views 2
 run --arch chosen --views 5 --depth 2
-for v in 2 3 5 6 8; do run --arch hm0 --views $v --batch 32768; done
+for v in 2 3 5 6 7 8; do run --arch hm0 --views $v --batch 32768; done
 for v in 2 4 8; do run --arch kptok --views $v --batch 32768; done
 run --arch hm0 --precision tf32 --batch 32768
 python - <<PY
