@@ -47,6 +47,13 @@ struct TokenArgs {
   int ray_layout;  // 0 none, 1 interleave (cat dim=2), 2 append (cat dim=1)
   int V, J, d, tok_w;
   float* tok;           // [B, V, tok_w] fp32
+  // LayerNorm-fused bf16 mode behind the single-kernel SPT: the token rows leave as the two bf16 planes of the FPT residual
+  // stream (hi, lo) together with their per-row (sum, sum^2) in statistics slot 0 -- what launch_ln_prep would make of `tok`
+  __nv_bfloat16* tok_hi;
+  __nv_bfloat16* tok_lo;
+  float2* stats;        // [slots][stats_ld]
+  int stat_slots;
+  int64_t stats_ld;
 };
 int launch_token_build(const TokenArgs& a, cudaStream_t s);
 int try_launch_token_build_vec(const TokenArgs& a, cudaStream_t s);

@@ -606,6 +606,17 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   // the single-kernel SPT computes the embedding in its prologue and writes the FPT tokens from its epilogue
   const bool fuse_embed = m->spt_fused && ea.spatial_pos_mode != 2;
   const bool fuse_token = m->spt_fused;
+  // LayerNorm-fused mode: the FPT residual stream lives in two bf16 planes (+ per-row statistics).  The single-kernel SPT
+  // writes them from its epilogue; any other producer leaves fp32 tokens and launch_ln_prep converts them.
+  const bool planes = m->ln_fused && !d.no_transformer_fpt && m->depth > 0 && !m->fpt_kp_fused;
+  const bool spt_planes = planes && fuse_token;
+  if (spt_planes) {
+    ta.tok_hi = (__nv_bfloat16*)w.fxn;
+    ta.tok_lo = (__nv_bfloat16*)w.fxl;
+    ta.stats = reinterpret_cast<float2*>(w.fstats);
+    ta.stat_slots = m->ln_slots;
+    ta.stats_ld = (int64_t)align_up((size_t)(Bc * m->fpt_tokens), 256);
+  }
   if (!fuse_embed) LC(CAT_EMBED, launch_embed(ea, s));
   // ---- SPT blocks (multiview_mpl.py:400-410): conf-weighted pass, last block twice; then Spatial_norm (:412) ----
   const int64_t Rs = (int64_t)V * Bc * J;
@@ -648,7 +659,7 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
     const int hd = D / m->H;
     const float scale = d.qk_scale != 0.f ? d.qk_scale : 1.0f / sqrtf((float)hd);
     const int64_t rows = Bc * N;
-    if (m->ln_fused)
+    if (m->ln_fused && !spt_planes)
       LC(CAT_FPT_LN, launch_ln_prep(w.tok, D, (__nv_bfloat16*)w.fxn, (__nv_bfloat16*)w.fxl, D, w.fstats, m->ln_slots, rows, D, s));
     if (m->resolved_for != P.base) {  // once per packed blob: no string lookups on the launch path afterwards
       m->fpt_blocks.clear();
@@ -673,7 +684,6 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   const bool fused_head = !d.linear_weighted_mean && !d.deep_head && !d.head_kadkhod;
   // LayerNorm-fused mode: the FPT left the residual stream in two bf16 planes.  The K5 head kernel reads them directly; every
   // other head takes the fp32 token buffer, refilled from the planes first.
-  const bool planes = m->ln_fused && !d.no_transformer_fpt && m->depth > 0 && !m->fpt_kp_fused;
   bool head_planes = false;
   if (planes) {
     HeadArgs probe{};

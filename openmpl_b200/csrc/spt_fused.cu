@@ -625,6 +625,11 @@ __device__ __forceinline__ void spt_fused_body(const SptArgs& args) {
     }
   }
 
+  // planes out (TokenArgs::tok_hi): per-row (sum, sum^2) of everything this CTA writes, reduced per set in a fixed order
+  // through the weight buffer no layer is using any more
+  const bool planes_out = args.x_out == nullptr && args.io.token.tok_hi != nullptr;
+  float2* rowstat = reinterpret_cast<float2*>(wbuf + ((args.depth == 0 ? 1 : args.depth) & 1) * LW);
+
   // ---- Spatial_norm (multiview_mpl.py:412), fp32 out ----
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
@@ -667,50 +672,84 @@ __device__ __forceinline__ void spt_fused_body(const SptArgs& args) {
     const int V = gridDim.y;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (!ok[mt][h]) continue;
-      const int64_t gr = h ? gr1 : gr0;
-      const int64_t b = gr / J;
-      const int j = (int)(gr - b * J);
-      float* trow = k.tok + (b * V + view) * (int64_t)k.tok_w;
-      const bool need_dir = k.ray_layout != 0 || k.pos_table == nullptr;
-      float dx = 0.f, dy = 0.f, dz = 0.f, inv = 0.f;
-      if (need_dir) {
-        const float* r = k.rays[view] + b * k.pose_stride + j * 3;
-        const float* ce = k.centers[view] + b * k.center_stride;
-        dx = __ldg(r) - __ldg(ce); dy = __ldg(r + 1) - __ldg(ce + 1); dz = __ldg(r + 2) - __ldg(ce + 2);
-        inv = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);  // F.normalize eps
-      }
-      const float pc = (k.Wcf != nullptr) ? __ldg(k.poses[view] + b * k.pose_stride + j * 3 + 2) : 0.f;
-      auto pos_at = [&](int pos_c) {  // 3D position code of channel pos_c of this joint
-        if (k.pos_table != nullptr) return __ldg(k.pos_table + j * k.pos_w + pos_c);
-        const float* wl = k.Wl + pos_c * 3;
-        return fmaf(__ldg(wl + 2), dz * inv, fmaf(__ldg(wl + 1), dy * inv, fmaf(__ldg(wl), dx * inv, __ldg(k.bl + pos_c))));
-      };
-      const int slot = (k.ray_layout == 1) ? 2 * D : D;  // channels per joint slot of the pose part
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int c = 8 * nt + 2 * t;
-        float v0 = y[nt][2 * h], v1 = y[nt][2 * h + 1];
-        if (k.Wcf != nullptr) {
-          v0 += fmaf(__ldg(k.Wcf + c), pc, __ldg(k.bcf + c));
-          v1 += fmaf(__ldg(k.Wcf + c + 1), pc, __ldg(k.bcf + c + 1));
+      float rs = 0.f, rq = 0.f;  // this lane's share of the row's (sum, sum^2)
+      auto emit = [&](int64_t off, float v0, float v1) {
+        if (planes_out) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(&hh);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - __uint_as_float(u << 16), v1 - __uint_as_float(u & 0xffff0000u));
+          *reinterpret_cast<uint32_t*>(k.tok_hi + off) = u;
+          *reinterpret_cast<__nv_bfloat162*>(k.tok_lo + off) = ll;
+          rs += v0 + v1;
+          rq = fmaf(v0, v0, fmaf(v1, v1, rq));
+        } else {
+          *reinterpret_cast<float2*>(k.tok + off) = make_float2(v0, v1);
         }
-        v0 += pos_at(c);
-        v1 += pos_at(c + 1);
-        *reinterpret_cast<float2*>(trow + j * slot + c) = make_float2(v0, v1);
-        if (k.ray_layout != 0) {
-          const float* w0 = k.Wr + c * 3;
-          float r0 = fmaf(__ldg(w0 + 2), dz, fmaf(__ldg(w0 + 1), dy, fmaf(__ldg(w0), dx, __ldg(k.br + c))));
-          float r1 = fmaf(__ldg(w0 + 5), dz, fmaf(__ldg(w0 + 4), dy, fmaf(__ldg(w0 + 3), dx, __ldg(k.br + c + 1))));
-          if (k.ray_layout == 1) {  // [x | ray] per joint, the position code spans both halves
-            r0 += pos_at(D + c);
-            r1 += pos_at(D + c + 1);
-            *reinterpret_cast<float2*>(trow + j * slot + D + c) = make_float2(r0, r1);
-          } else {                  // J pose tokens then J ray tokens (no position code on the ray tokens)
-            *reinterpret_cast<float2*>(trow + (J + j) * D + c) = make_float2(r0, r1);
+      };
+      if (ok[mt][h]) {  // (the quad reduction below is executed by every lane of the warp, valid row or not)
+        const int64_t gr = h ? gr1 : gr0;
+        const int64_t b = gr / J;
+        const int j = (int)(gr - b * J);
+        const int64_t trow = (b * V + view) * (int64_t)k.tok_w;
+        const bool need_dir = k.ray_layout != 0 || k.pos_table == nullptr;
+        float dx = 0.f, dy = 0.f, dz = 0.f, inv = 0.f;
+        if (need_dir) {
+          const float* r = k.rays[view] + b * k.pose_stride + j * 3;
+          const float* ce = k.centers[view] + b * k.center_stride;
+          dx = __ldg(r) - __ldg(ce); dy = __ldg(r + 1) - __ldg(ce + 1); dz = __ldg(r + 2) - __ldg(ce + 2);
+          inv = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);  // F.normalize eps
+        }
+        const float pc = (k.Wcf != nullptr) ? __ldg(k.poses[view] + b * k.pose_stride + j * 3 + 2) : 0.f;
+        auto pos_at = [&](int pos_c) {  // 3D position code of channel pos_c of this joint
+          if (k.pos_table != nullptr) return __ldg(k.pos_table + j * k.pos_w + pos_c);
+          const float* wl = k.Wl + pos_c * 3;
+          return fmaf(__ldg(wl + 2), dz * inv, fmaf(__ldg(wl + 1), dy * inv, fmaf(__ldg(wl), dx * inv, __ldg(k.bl + pos_c))));
+        };
+        const int slot = (k.ray_layout == 1) ? 2 * D : D;  // channels per joint slot of the pose part
+  #pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int c = 8 * nt + 2 * t;
+          float v0 = y[nt][2 * h], v1 = y[nt][2 * h + 1];
+          if (k.Wcf != nullptr) {
+            v0 += fmaf(__ldg(k.Wcf + c), pc, __ldg(k.bcf + c));
+            v1 += fmaf(__ldg(k.Wcf + c + 1), pc, __ldg(k.bcf + c + 1));
+          }
+          v0 += pos_at(c);
+          v1 += pos_at(c + 1);
+          emit(trow + j * slot + c, v0, v1);
+          if (k.ray_layout != 0) {
+            const float* w0 = k.Wr + c * 3;
+            float r0 = fmaf(__ldg(w0 + 2), dz, fmaf(__ldg(w0 + 1), dy, fmaf(__ldg(w0), dx, __ldg(k.br + c))));
+            float r1 = fmaf(__ldg(w0 + 5), dz, fmaf(__ldg(w0 + 4), dy, fmaf(__ldg(w0 + 3), dx, __ldg(k.br + c + 1))));
+            if (k.ray_layout == 1) {  // [x | ray] per joint, the position code spans both halves
+              r0 += pos_at(D + c);
+              r1 += pos_at(D + c + 1);
+              emit(trow + j * slot + D + c, r0, r1);
+            } else {                  // J pose tokens then J ray tokens (no position code on the ray tokens)
+              emit(trow + (J + j) * D + c, r0, r1);
+            }
           }
         }
       }
+      if (planes_out) {
+        rs = quad_sum(rs);
+        rq = quad_sum(rq);
+        if (t == 0) rowstat[lr[mt] + 8 * h] = make_float2(rs, rq);
+      }
+    }
+  }
+  if (planes_out) {
+    __syncthreads();
+    // one thread per set: its J rows in order (bitwise reproducible), then slot 0 of the row's statistics; other slots zero
+    const TokenArgs& k = args.io.token;
+    const int set = threadIdx.x;
+    const int64_t gr = tile * args.rows_used + (int64_t)set * J;
+    if (set * J < args.rows_used && gr < rows_in_view) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int j = 0; j < J; ++j) { const float2 v = rowstat[set * J + j]; s1 += v.x; s2 += v.y; }
+      const int64_t row = (gr / J) * gridDim.y + view;
+      k.stats[row] = make_float2(s1, s2);
+      for (int i = 1; i < k.stat_slots; ++i) k.stats[i * k.stats_ld + row] = make_float2(0.f, 0.f);
     }
   }
 }
