@@ -373,6 +373,14 @@ def run_ours(args):
             gbs = nbytes / (ms_l * 1e-3) / 1e9
             memory_kernels[k] = {"avg_launch_ms": ms_l, "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": gbs,
                                  "frac_of_hbm_peak": gbs / pk.get("hbm_gbs", 6650.0)}
+            cap = traffic.get("head_block_kernel") if k == "head" else None
+            if cap and Bc == 32768 and args.precision == "bf16":
+                # what DRAM really moves for this launch (ncu capture of the same chunk size, profiles/ncu_traffic.json): the head
+                # uses the pose half of every 128-byte line of the residual planes and DRAM delivers whole lines
+                dgbs = cap["bytes_per_launch"] / (ms_l * 1e-3) / 1e9
+                memory_kernels[k].update({"dram_bytes_per_launch_ncu": cap["bytes_per_launch"], "dram_gbs": dgbs,
+                                          "dram_frac_of_hbm_peak": dgbs / pk.get("hbm_gbs", 6650.0),
+                                          "ncu_alone": {"launch_ms": cap["ncu_launch_s"] * 1e3, "dram_gbs": cap["ncu_dram_gbs"]}})
 
     # ---- the collectives: MPJPE / P-MPJPE accumulators all-reduced over ranks (NCCL) ----
     acc = metric.MpjpeAccumulator(cfg.J, output_in_meter=True, device=dev)

@@ -2,7 +2,10 @@
 """Regenerate profiles/ncu_traffic.json (what bench.py reports as roofline.traffic) from an `ncu --set full` capture of the
 four FPT GEMM launches of one block, stamped with the build it was taken from.
 
-    python scripts/ncu_traffic.py gpurun_out/<capture>.ncu-rep [arch] [profiles/<summary>.md]
+    python scripts/ncu_traffic.py gpurun_out/<capture>.ncu-rep [arch] [profiles/<summary>.md] [gpurun_out/<head capture>.ncu-rep]
+
+The optional fourth argument is a capture of head_block_kernel: its DRAM bytes per launch are recorded next to the GEMMs'
+(the head reads the non-ray half of every 128-byte line; DRAM delivers whole lines, i.e. twice the algorithmic bytes).
 """
 import csv
 import hashlib
@@ -38,6 +41,10 @@ def main():
             key = NAMES.get(epi, "epi" + epi)
         else:
             continue
+        n = 2
+        while key in per:                      # two launches of one instantiation (D = 544: proj and fc2 share an epilogue)
+            key = key.split("#")[0] + f"#{n}"
+            n += 1
         per[key] = (val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")) / 1e6
         tens[key] = float(r[ix["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])
     lib = os.path.join(ROOT, "openmpl_b200", "libmpl_b200.so")
@@ -54,6 +61,22 @@ def main():
         "per_instantiation_mb": per, "tensor_pipe_pct_ncu": tens,
         "capture": os.path.basename(rep), "git_rev_at_capture": rev,
         "lib_sha256_16": hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16] if os.path.isfile(lib) else None}}
+    if len(sys.argv) > 4:
+        out2 = subprocess.run(["ncu", "-i", sys.argv[4], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows2 = list(csv.reader(io.StringIO(out2)))
+        ix2 = {h: i for i, h in enumerate(rows2[0])}
+
+        def val2(r, k):
+            v, u = float(r[ix2[k]].replace(",", "")), rows2[1][ix2[k]].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "nsecond": 1e-9, "ms": 1e-3, "msecond": 1e-3}.get(u, 1)
+        heads = [r for r in rows2[2:] if "head_block_kernel" in r[ix2["Kernel Name"]]]
+        if heads:
+            b = sum(val2(r, "dram__bytes_read.sum") + val2(r, "dram__bytes_write.sum") for r in heads) / len(heads)
+            t = sum(val2(r, "gpu__time_duration.sum") for r in heads) / len(heads)
+            data[arch]["head_block_kernel"] = {"bytes_per_launch": b, "ncu_launch_s": t, "ncu_dram_gbs": b / t / 1e9,
+                                               "capture": os.path.basename(sys.argv[4]),
+                                               "note": "DRAM bytes of one head launch (32768 poses): the kernel uses the pose half (64 B) of "
+                                                       "every 128-byte line of the two residual planes, DRAM delivers the whole line"}
     json.dump(data, open(path, "w"), indent=1)
     print(json.dumps(data[arch], indent=1))
 
