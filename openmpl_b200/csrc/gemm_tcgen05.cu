@@ -1091,7 +1091,8 @@ qkv_attn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 __global__ void __launch_bounds__(256) qkv_attn_pack_kernel(const float* __restrict__ W, const float* __restrict__ b,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            __nv_bfloat16* __restrict__ Wp, float* __restrict__ colsum,
-                                                           float* __restrict__ bias_f, int tiles, int HD, int D, float qscale) {
+                                                           float* __restrict__ bias_f, int tiles, int HD, int D, float qscale,
+                                                           const int* __restrict__ kperm) {
   const int pr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // physical row
   if (pr >= tiles * FA_NT) return;
   const int lane = threadIdx.x & 31;
@@ -1111,11 +1112,12 @@ __global__ void __launch_bounds__(256) qkv_attn_pack_kernel(const float* __restr
   const float sc = (part == 0) ? qscale : 1.0f;
   float cs = 0.f, bb = 0.f;
   for (int k = lane; k < D; k += 32) {
-    const float w = live ? W[(int64_t)src * D + k] : 0.f;
-    const __nv_bfloat16 rw = __float2bfloat16_rn(w * gamma[k] * sc);
+    const int ks = kperm ? kperm[k] : k;  // source channel of packed input channel k
+    const float w = live ? W[(int64_t)src * D + ks] : 0.f;
+    const __nv_bfloat16 rw = __float2bfloat16_rn(w * gamma[ks] * sc);
     Wp[(int64_t)pr * D + k] = rw;
     cs += __bfloat162float(rw);
-    bb = fmaf(w, beta[k], bb);
+    bb = fmaf(w, beta[ks], bb);
   }
   cs = warp_sum(cs);
   bb = warp_sum(bb);
@@ -1144,14 +1146,15 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // [rows, K] row-major matrix, box = 128 bytes of K x box_rows rows, 128B swizzle, out-of-bounds -> zeros
-int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, int box_rows, int box_cols = 0, bool swizzle = true) {
+int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int K, int esz, int box_rows, int box_cols = 0, bool swizzle = true,
+              int64_t pitch = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return MPL_ERR_CUDA;
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)K * esz};
+  const cuuint64_t gstride[1] = {(cuuint64_t)(pitch ? pitch : K) * esz};  // pitch: a [rows, K] window of wider rows
   const cuuint32_t box[2] = {(cuuint32_t)(box_cols ? box_cols : KB_BYTES / esz), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
@@ -1249,10 +1252,10 @@ size_t qkv_attn_weight_elems(int D, int H) { return (size_t)qkv_attn_tiles(D, H)
 int qkv_attn_vec_len(int D, int H) { return qkv_attn_tiles(D, H) * FA_NT; }
 
 int launch_qkv_attn_pack(const float* W, const float* b, const float* gamma, const float* beta, void* Wp, float* colsum,
-                         float* bias_f, int H, int D, float scale, cudaStream_t s) {
+                         float* bias_f, int H, int D, float scale, cudaStream_t s, const int* kperm) {
   const int tiles = qkv_attn_tiles(D, H), rows = tiles * FA_NT;
   qkv_attn_pack_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, s>>>(W, b, gamma, beta, reinterpret_cast<__nv_bfloat16*>(Wp), colsum,
-                                                                 bias_f, tiles, D / H, D, scale * 1.4426950408889634f);
+                                                                 bias_f, tiles, D / H, D, scale * 1.4426950408889634f, kperm);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
@@ -1377,7 +1380,12 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
   GemmMaps tm;
   MPL_TRY(make_tmap(&tm.a, A, M, K, 2, BM));
   MPL_TRY(make_tmap(&tm.b, W, N, K, 2, wide_rows));
-  MPL_TRY(make_tmap(&tm.y, Y, M, N, out_bf16 ? 2 : 4, 32, out_bf16 ? 64 : 32));
+  const int64_t ldy = (resid && lnargs->ldy > 0) ? lnargs->ldy : 0;  // residual planes wider than the N columns updated
+  if (ldy != 0 && (ldy < N || (ldy * 2) % 16 != 0)) {
+    set_error("launch_gemm_tcgen05: residual row pitch %lld does not fit N=%d", (long long)ldy, N);
+    return MPL_ERR_INVALID_ARGUMENT;
+  }
+  MPL_TRY(make_tmap(&tm.y, Y, M, N, out_bf16 ? 2 : 4, 32, out_bf16 ? 64 : 32, true, ldy));
   tm.a2 = tm.a;
   tm.y2 = tm.y;
   if (split) {
@@ -1386,7 +1394,7 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* Y
     if (out_bf16) MPL_TRY(make_tmap(&tm.y2, reinterpret_cast<__nv_bfloat16*>(Y) + M * (int64_t)N, M, N, 2, 32, 64));
   } else {
     MPL_TRY(make_tmap(&tm.b2, W, N, K, 2, narrow_rows));  // the W box of the narrow tiles
-    if (resid) MPL_TRY(make_tmap(&tm.y2, lnargs->x_lo, M, N, 2, 32, 64));  // Y = the hi plane, x_lo = the lo plane
+    if (resid) MPL_TRY(make_tmap(&tm.y2, lnargs->x_lo, M, N, 2, 32, 64, true, ldy));  // Y = the hi plane, x_lo = the lo plane
   }
   if (cg == 1) {
     return split ? launch_epi<1, 1>(epi, tm, bias, M, N, K, ts, ln, s) : launch_epi<1, 0>(epi, tm, bias, M, N, K, ts, ln, s);

@@ -47,6 +47,7 @@ struct TokenArgs {
   int ray_layout;  // 0 none, 1 interleave (cat dim=2), 2 append (cat dim=1)
   int V, J, d, tok_w;
   float* tok;           // [B, V, tok_w] fp32
+  int perm_layout;      // ray_layout 1 written as [J pose parts | J ray parts] (channel-permuted residual stream, model.cu)
   // LayerNorm-fused bf16 mode behind the single-kernel SPT: the token rows leave as the two bf16 planes of the FPT residual
   // stream (hi, lo) together with their per-row (sum, sum^2) in statistics slot 0 -- what launch_ln_prep would make of `tok`
   __nv_bfloat16* tok_hi;
@@ -76,7 +77,7 @@ int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* x_hi, __nv_bfloat
 int launch_join_planes(const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* out, int64_t n, cudaStream_t s);
 // pack time: W' = bf16(W diag(gamma)), colsum = row sums of W', bias' = b + W beta
 int launch_ln_fold(const float* W, const float* b, const float* gamma, const float* beta, __nv_bfloat16* Wf, float* colsum,
-                   float* bias_f, int N, int K, cudaStream_t s);
+                   float* bias_f, int N, int K, cudaStream_t s, const int* kperm = nullptr);
 
 // ---- fp32 CUDA-core Linear: Y = act(X W^T + bias) (+ R) ------------------------------------------------------------
 int launch_linear_f32(const float* X, int64_t lda, const float* W, const float* bias, const float* R, int64_t ldr,
@@ -124,6 +125,10 @@ int launch_fold_bn(const float* W, const float* b, const float* g, const float* 
                    float eps, float* Wf, float* bf, int N, int K, cudaStream_t s);
 int launch_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t s);
 int launch_to_f16(const float* src, void* dst, int64_t n, cudaStream_t s);
+// Channel-permuted residual stream (model.cu, MplModel::perm): dst row n = src row perm[n] of a [N, K] matrix, as bf16 or
+// fp16; dst[i] = src[perm[i]] for a vector
+int launch_to_half_rows(const float* src, void* dst, int N, int K, const int* perm, int fp16, cudaStream_t s);
+int launch_gather_f32(const float* src, float* dst, int n, const int* perm, cudaStream_t s);
 int launch_to_split(const float* src, __nv_bfloat16* dst, int64_t n, int64_t plane, cudaStream_t s);  // hi at dst, lo at dst + plane
 
 // ---- tcgen05 projection GEMM (gemm_tcgen05.cu) ----------------------------------------------------------------------
@@ -143,6 +148,8 @@ struct GemmLnArgs {
   float eps;
   int ab_fp16;   // A and W hold fp16 (not bf16) values
   int out_fp16;  // EPI_LN_BIAS(_GELU): write fp16 (not bf16); the GELU then runs in packed half2 arithmetic
+  int ldy;       // residual-emit: row pitch (elements) of the two residual planes when only their first N columns are
+                 // updated (0 = N)
 };
 int gemm_ln_slots(int N);
 // A [M,K] row-major (lda = K), W [N,K] row-major.  dtype MPL_PREC_BF16: bf16 matrices.  dtype MPL_PREC_TF32 (the fp32-grade
@@ -160,8 +167,9 @@ bool gemm_tcgen05_supports(int N, int K, int dtype);
 bool qkv_attn_supports(int D, int H, int tokens);
 size_t qkv_attn_weight_elems(int D, int H);  // bf16 elements of Wp
 int qkv_attn_vec_len(int D, int H);          // floats of colsum / bias_f
+// kperm (or null): input channel k of the packed matrix is channel kperm[k] of W / gamma / beta
 int launch_qkv_attn_pack(const float* W, const float* b, const float* gamma, const float* beta, void* Wp, float* colsum,
-                         float* bias_f, int H, int D, float scale, cudaStream_t s);
+                         float* bias_f, int H, int D, float scale, cudaStream_t s, const int* kperm = nullptr);
 int launch_qkv_attn(const void* xb, const void* Wp, const float* bias_f, const float* colsum, const void* stats, int slots,
                     float eps, void* att, int64_t M, int D, int H, int V, cudaStream_t s);
 

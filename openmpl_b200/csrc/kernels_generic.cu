@@ -342,17 +342,18 @@ int launch_ln_prep(const float* x, int64_t ldx, __nv_bfloat16* xb, __nv_bfloat16
 __global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ W, const float* __restrict__ b,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       __nv_bfloat16* __restrict__ Wf, float* __restrict__ colsum,
-                                                      float* __restrict__ bias_f, int N, int K) {
+                                                      float* __restrict__ bias_f, int N, int K, const int* __restrict__ kperm) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
   const int lane = threadIdx.x & 31;
   float cs = 0.f, bb = 0.f;
   for (int k = lane; k < K; k += 32) {
-    const float w = W[(int64_t)n * K + k];
-    const __nv_bfloat16 r = __float2bfloat16_rn(w * gamma[k]);
+    const int ks = kperm ? kperm[k] : k;  // source channel of packed input channel k
+    const float w = W[(int64_t)n * K + ks];
+    const __nv_bfloat16 r = __float2bfloat16_rn(w * gamma[ks]);
     Wf[(int64_t)n * K + k] = r;
     cs += __bfloat162float(r);
-    bb = fmaf(w, beta[k], bb);
+    bb = fmaf(w, beta[ks], bb);
   }
   cs = warp_sum(cs);
   bb = warp_sum(bb);
@@ -363,9 +364,9 @@ __global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ 
 }
 
 int launch_ln_fold(const float* W, const float* b, const float* gamma, const float* beta, __nv_bfloat16* Wf, float* colsum,
-                   float* bias_f, int N, int K, cudaStream_t s) {
+                   float* bias_f, int N, int K, cudaStream_t s, const int* kperm) {
   if (N == 0) return MPL_OK;
-  ln_fold_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, s>>>(W, b, gamma, beta, Wf, colsum, bias_f, N, K);
+  ln_fold_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, s>>>(W, b, gamma, beta, Wf, colsum, bias_f, N, K, kperm);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }
@@ -1107,6 +1108,33 @@ __global__ void to_f16_kernel(const float* src, __half* dst, int64_t n) {
 int launch_to_f16(const float* src, void* dst, int64_t n, cudaStream_t s) {
   if (n == 0) return MPL_OK;
   to_f16_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, reinterpret_cast<__half*>(dst), n);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+template <typename T>
+__global__ void to_half_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int K, const int* __restrict__ perm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * K) return;
+  const int n = (int)(i / K), k = (int)(i - (int64_t)n * K);
+  const float v = src[(int64_t)perm[n] * K + k];
+  if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) dst[i] = __float2half_rn(v);
+  else dst[i] = __float2bfloat16_rn(v);
+}
+int launch_to_half_rows(const float* src, void* dst, int N, int K, const int* perm, int fp16, cudaStream_t s) {
+  const int64_t n = (int64_t)N * K;
+  if (n == 0) return MPL_OK;
+  if (fp16) to_half_rows_kernel<__half><<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, reinterpret_cast<__half*>(dst), N, K, perm);
+  else to_half_rows_kernel<__nv_bfloat16><<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), N, K, perm);
+  MPL_LAUNCH_CHECK();
+  return MPL_OK;
+}
+__global__ void gather_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, const int* __restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
+}
+int launch_gather_f32(const float* src, float* dst, int n, const int* perm, cudaStream_t s) {
+  if (n == 0) return MPL_OK;
+  gather_f32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(src, dst, n, perm);
   MPL_LAUNCH_CHECK();
   return MPL_OK;
 }

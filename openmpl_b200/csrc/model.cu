@@ -64,6 +64,14 @@ struct MplModel {
   bool fpt_tc;     // FPT projections run on tcgen05 (precision != fp32 and shapes fit)
   bool spt_fused;  // the SPT stack runs as the single fused fp16-mma kernel (bf16 / tf32 modes, d=32, H=8, J=17)
   bool ln_fused;   // bf16 mode: the FPT LayerNorms are folded into the projection GEMMs (no LayerNorm kernel)
+  // LN-fused planes behind the single-kernel SPT with interleaved ray tokens ([x_j | ray_j] per joint, ray_layout 1) and the K5
+  // head: the residual stream is kept CHANNEL-PERMUTED as [all pose parts | all ray parts].  Every consumer is permutation
+  // equivariant once its weights are permuted at pack time (LayerNorm gamma / beta and W columns of QKV / fc1, W rows and
+  // biases of proj / fc2), so nothing changes at run time except that (1) the head reads one contiguous half row instead of
+  // the pose half of every 128-byte line and (2) the LAST fc2 of the stack computes the pose half only: the head never
+  // reads the ray channels of the final residual (multiview_mpl.py:425-433 strips them).
+  bool perm;
+  std::vector<int> perm_host;  // packed channel c holds reference channel perm_host[c]
   bool qkv_attn;      // bf16 LN-fused mode, view tokens, D = H * 136 (or H * 68), 2 <= V <= 8: QKV GEMM + cross-view attention are one kernel
   bool fpt_kp_fused;  // bf16 mode, keypoint-token FPT (width 32, 8 heads, J = 17): the whole FPT stack is one kernel launch
   int ln_slots;    // statistics slots per row written by the residual-emit GEMMs
@@ -268,6 +276,7 @@ static void build_tables(MplModel* m) {
     for (int st = 0; st < stacks; ++st) add_derived(m, "sptpack:" + std::to_string(st), (int64_t)m->depth * spt_fused_layer_bytes(), 1);
   }
   if (m->fpt_kp_fused) add_derived(m, "fptpack", (int64_t)m->depth * spt_fused_layer_bytes(), 1);
+  if (m->perm) add_derived(m, "perm", m->fpt_dim, 4);
   if (m->fpt_tc) {
     // bf16 mode: one bf16 (fp16 for fc2 under LayerNorm fusion) copy; split mode: two bf16 planes (hi, lo) per matrix
     const int esz = (d.precision == MPL_PREC_BF16) ? 2 : 4;
@@ -288,6 +297,10 @@ static void build_tables(MplModel* m) {
         add_derived(m, "lnw:" + p + "mlp.fc1", Hf * D, 2);
         add_derived(m, "lncs:" + p + "mlp.fc1", Hf, 4);
         add_derived(m, "lnb:" + p + "mlp.fc1", Hf, 4);
+        if (m->perm) {  // biases of the two residual-emit GEMMs in the permuted channel order
+          add_derived(m, "pb:" + p + "attn.proj.bias", D, 4);
+          add_derived(m, "pb:" + p + "mlp.fc2.bias", D, 4);
+        }
       } else {
         add_derived(m, tag + p + "attn.qkv.weight", 3 * D * D, esz);
         add_derived(m, tag + p + "mlp.fc1.weight", Hf * D, esz);
@@ -448,6 +461,10 @@ static BlockW block_weights(const MplModel* m, const Packed& P, const std::strin
     }
     b.projw_tc = P.dv(tag + p + "attn.proj.weight");
     b.fc2w_tc = P.dv(tag + p + "mlp.fc2.weight");
+    if (m->perm) {
+      b.projb = P.df("pb:" + p + "attn.proj.bias");
+      b.fc2b = P.df("pb:" + p + "mlp.fc2.bias");
+    }
   }
   return b;
 }
@@ -472,7 +489,7 @@ static int block_f32(MplModel* m, bool fpt, const BlockW& w, float* x, int64_t r
 // MMA per k-step).  tf32-named mode = fp32-grade "split" arithmetic: every GEMM operand is a pair of bf16 planes (hi, lo) and
 // the tensor cores accumulate hi.hi + hi.lo + lo.hi (the producers -- LayerNorm, attention, the fc1 epilogue -- write planes).
 static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_t sets, int N, int C, int hidden, float scale,
-                    void* xn, void* xl, void* qkv, void* att, void* hid, void* stats, cudaStream_t s) {
+                    void* xn, void* xl, void* qkv, void* att, void* hid, void* stats, bool last, cudaStream_t s) {
   const int prec = m->d.precision;
   const int hd = C / m->H;
   const int cg = m->cta_group;
@@ -500,7 +517,11 @@ static int block_tc(MplModel* m, const BlockW& w, float* x, int64_t rows, int64_
     app.out_fp16 = 1;   // hidden activations in fp16 (GELU in packed half2), fc2 runs kind::f16 on fp16 operands
     LC(CAT_FPT_FC1, launch_gemm_tcgen05(xn, w.fc1w_tc, w.fc1_bf, hid, rows, hidden, C, prec, EPI_LN_BIAS_GELU, 0, s, &app, cg));
     emit.ab_fp16 = 1;
-    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, xn, rows, C, hidden, prec, EPI_RESIDUAL_EMIT, 0, s, &emit, cg));
+    // channel-permuted stream: the head reads the first E = J * d channels only, so the last fc2 of the stack leaves the ray
+    // half of the residual as it is (half the MMAs, half the residual traffic of that launch)
+    const int n_fc2 = (last && m->perm) ? m->E : C;
+    emit.ldy = C;
+    LC(CAT_FPT_FC2, launch_gemm_tcgen05(hid, w.fc2w_tc, w.fc2b, xn, rows, n_fc2, hidden, prec, EPI_RESIDUAL_EMIT, 0, s, &emit, cg));
     return MPL_OK;
   }
   if (prec == MPL_PREC_BF16) {
@@ -616,6 +637,7 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
     ta.stats = reinterpret_cast<float2*>(w.fstats);
     ta.stat_slots = m->ln_slots;
     ta.stats_ld = (int64_t)align_up((size_t)(Bc * m->fpt_tokens), 256);
+    ta.perm_layout = m->perm ? 1 : 0;
   }
   if (!fuse_embed) LC(CAT_EMBED, launch_embed(ea, s));
   // ---- SPT blocks (multiview_mpl.py:400-410): conf-weighted pass, last block twice; then Spatial_norm (:412) ----
@@ -671,7 +693,8 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
       const int reps = 1 + (ix == m->depth - 1 ? 1 : 0);
       for (int r = 0; r < reps; ++r) {
         if (m->fpt_tc)
-          MPL_TRY(block_tc(m, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, w.fxn, w.fxl, w.fqkv, w.fatt, w.fhid, w.fstats, s));
+          MPL_TRY(block_tc(m, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, w.fxn, w.fxl, w.fqkv, w.fatt, w.fhid, w.fstats,
+                           ix == m->depth - 1 && r == reps - 1, s));
         else
           MPL_TRY(block_f32(m, true, bw, w.tok, rows, Bc, N, D, m->fpt_hidden, scale, nullptr, (float*)w.fxn, (float*)w.fqkv, (float*)w.fatt, (float*)w.fhid, s));
       }
@@ -679,7 +702,7 @@ static int forward_chunk(MplModel* m, const Packed& P, const float* const* poses
   }
   // ---- ray strip + View_norm + weighted mean + head (multiview_mpl.py:425-446, 506-523) ----
   int seg_len = E, seg_stride = E;
-  if (m->ray_layout == 1) { seg_len = dim; seg_stride = 2 * dim; }  // [J, 2d] -> first d of every joint slot
+  if (m->ray_layout == 1 && !m->perm) { seg_len = dim; seg_stride = 2 * dim; }  // [J, 2d] -> first d of every joint slot
   const int out_dim = 3 * J;
   const bool fused_head = !d.linear_weighted_mean && !d.deep_head && !d.head_kadkhod;
   // LayerNorm-fused mode: the FPT left the residual stream in two bf16 planes.  The K5 head kernel reads them directly; every
@@ -839,6 +862,22 @@ int mpl_create(const MplDesc* desc, MplModel** out) {
   m->chunk_streams = (d.chunk_streams == 2) ? 2 : 1;
   m->ln_slots = m->ln_fused ? gemm_ln_slots(m->fpt_dim) : 0;
   m->qkv_attn = m->ln_fused && d.qkv_attn_fusion != 0 && m->cta_group == 2 && qkv_attn_supports(m->fpt_dim, m->H, m->fpt_tokens);
+  {
+    // channel-permuted residual stream (see MplModel::perm): every producer and consumer of the planes must be one that
+    // knows the permutation -- the SPT epilogue, the LN-fused GEMMs and the K5 head reading the planes
+    HeadArgs probe{};
+    probe.E = m->E; probe.out_dim = 3 * m->J; probe.seg_len = m->E; probe.seg_stride = m->E; probe.tok_w = m->tok_w;
+    const bool k5 = !d.linear_weighted_mean && !d.deep_head && !d.head_kadkhod && 3 * m->J <= 64 && head_warp_supports(probe);
+    m->perm = m->ln_fused && m->ray_layout == 1 && m->spt_fused && !m->fpt_kp_fused && !d.no_transformer_fpt && m->depth > 0 &&
+              k5 && m->fpt_dim == 2 * m->E && gemm_tcgen05_supports(m->E, m->fpt_hidden, d.precision);
+    if (m->perm) {
+      m->perm_host.resize(m->fpt_dim);
+      for (int c = 0; c < m->fpt_dim; ++c) {
+        const int half = c / m->E, e = c % m->E;  // packed: [pose parts | ray parts]; reference: [x_j | ray_j] per joint
+        m->perm_host[c] = (e / m->dim) * 2 * m->dim + half * m->dim + e % m->dim;
+      }
+    }
+  }
   build_tables(m);
   *out = m;
   return MPL_OK;
@@ -997,6 +1036,12 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
   if (m->fpt_tc) {
     const bool bf = m->d.precision == MPL_PREC_BF16;
     const std::string tag = bf ? "bf16:" : "split:";
+    const int* perm = nullptr;
+    if (m->perm) {
+      int* dp = reinterpret_cast<int*>(base + m->derived[m->dindex.at("perm")].offset);
+      MPL_CUDA(cudaMemcpyAsync(dp, m->perm_host.data(), m->perm_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+      perm = dp;
+    }
     for (int l = 0; l < m->depth; ++l) {
       const std::string p = "blocks." + std::to_string(l) + ".";
       if (m->ln_fused) {
@@ -1007,17 +1052,25 @@ int mpl_pack_weights(MplModel* m, const void* const* params, int num_params, voi
           MPL_TRY(launch_qkv_attn_pack(P.f(p + "attn.qkv.weight"), m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr,
                                        P.f(p + "norm1.weight"), P.f(p + "norm1.bias"), mut("qaw:" + p + "attn.qkv"),
                                        reinterpret_cast<float*>(mut("qacs:" + p + "attn.qkv")),
-                                       reinterpret_cast<float*>(mut("qab:" + p + "attn.qkv")), m->H, D, fscale, s));
+                                       reinterpret_cast<float*>(mut("qab:" + p + "attn.qkv")), m->H, D, fscale, s, perm));
         } else {
           MPL_TRY(launch_ln_fold(P.f(p + "attn.qkv.weight"), m->d.qkv_bias ? P.f(p + "attn.qkv.bias") : nullptr, P.f(p + "norm1.weight"),
                                  P.f(p + "norm1.bias"), reinterpret_cast<__nv_bfloat16*>(mut("lnw:" + p + "attn.qkv")),
                                  reinterpret_cast<float*>(mut("lncs:" + p + "attn.qkv")),
-                                 reinterpret_cast<float*>(mut("lnb:" + p + "attn.qkv")), 3 * D, D, s));
+                                 reinterpret_cast<float*>(mut("lnb:" + p + "attn.qkv")), 3 * D, D, s, perm));
         }
         MPL_TRY(launch_ln_fold(P.f(p + "mlp.fc1.weight"), P.f(p + "mlp.fc1.bias"), P.f(p + "norm2.weight"), P.f(p + "norm2.bias"),
                                reinterpret_cast<__nv_bfloat16*>(mut("lnw:" + p + "mlp.fc1")),
                                reinterpret_cast<float*>(mut("lncs:" + p + "mlp.fc1")),
-                               reinterpret_cast<float*>(mut("lnb:" + p + "mlp.fc1")), Hf, D, s));
+                               reinterpret_cast<float*>(mut("lnb:" + p + "mlp.fc1")), Hf, D, s, perm));
+        if (perm != nullptr) {
+          // the residual-emit GEMMs write permuted channels: rows of W and entries of the bias in packed order
+          MPL_TRY(launch_to_half_rows(P.f(p + "attn.proj.weight"), mut(tag + p + "attn.proj.weight"), D, D, perm, 0, s));
+          MPL_TRY(launch_to_half_rows(P.f(p + "mlp.fc2.weight"), mut(tag + p + "mlp.fc2.weight"), D, Hf, perm, 1, s));
+          MPL_TRY(launch_gather_f32(P.f(p + "attn.proj.bias"), reinterpret_cast<float*>(mut("pb:" + p + "attn.proj.bias")), D, perm, s));
+          MPL_TRY(launch_gather_f32(P.f(p + "mlp.fc2.bias"), reinterpret_cast<float*>(mut("pb:" + p + "mlp.fc2.bias")), D, perm, s));
+          continue;
+        }
       }
       for (const char* wn : {"attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"}) {
         if (m->ln_fused && (std::string(wn) == "attn.qkv.weight" || std::string(wn) == "mlp.fc1.weight")) continue;

@@ -705,7 +705,8 @@ __device__ __forceinline__ void spt_fused_body(const SptArgs& args) {
           const float* wl = k.Wl + pos_c * 3;
           return fmaf(__ldg(wl + 2), dz * inv, fmaf(__ldg(wl + 1), dy * inv, fmaf(__ldg(wl), dx * inv, __ldg(k.bl + pos_c))));
         };
-        const int slot = (k.ray_layout == 1) ? 2 * D : D;  // channels per joint slot of the pose part
+        // channels per joint slot of the pose part; perm_layout: the interleaved row is stored as [J pose parts | J ray parts]
+        const int slot = (k.ray_layout == 1 && !k.perm_layout) ? 2 * D : D;
   #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int c = 8 * nt + 2 * t;
@@ -724,7 +725,7 @@ __device__ __forceinline__ void spt_fused_body(const SptArgs& args) {
             if (k.ray_layout == 1) {  // [x | ray] per joint, the position code spans both halves
               r0 += pos_at(D + c);
               r1 += pos_at(D + c + 1);
-              emit(trow + j * slot + D + c, r0, r1);
+              emit(trow + (k.perm_layout ? (J + j) * D : j * slot + D) + c, r0, r1);
             } else {                  // J pose tokens then J ray tokens (no position code on the ray tokens)
               emit(trow + (J + j) * D + c, r0, r1);
             }
