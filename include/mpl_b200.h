@@ -231,6 +231,10 @@ int mpl_test_gemm_ln(const void* A, const void* W, const float* bias, void* Y, i
                      const float* colsum, const void* stats_in, int slots_in, void* stats_out, void* x_lo, float eps,
                      int ab_fp16, int out_fp16, int cta_group, mpl_stream_t stream);
 int mpl_test_gemm_ln_slots(int N);
+/* Epilogue 6 on the first N columns of residual planes whose rows are `ldy` >= N elements apart (the last fc2 of the stack
+ * updates the pose half of the channel-permuted residual stream only); the other columns stay. */
+int mpl_test_gemm_emit_pitch(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, void* stats_out,
+                             void* x_lo, int ab_fp16, int ldy, int cta_group, mpl_stream_t stream);
 /* The fused QKV projection + cross-view attention kernel (multiview_mpl.py:48-64 behind the folded norm1) in isolation:
  *   xb [M, D] bf16 raw residual rows, W [3D, D] / bias [3D] (or NULL) / gamma, beta [D] fp32 on the device, stats as above,
  *   att [M, D] bf16 out; M = poses * V rows, D = H * 136 (or H * 68, H even), 2 <= V <= 8.

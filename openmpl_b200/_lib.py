@@ -28,7 +28,7 @@ EXPORTS = [
     "mpl_packed_bytes", "mpl_pack_weights", "mpl_workspace_bytes", "mpl_chunk_poses", "mpl_set_chunk_poses",
     "mpl_forward", "mpl_last_launch_count", "mpl_mpjpe_accumulate", "mpl_build_inputs", "mpl_test_gemm",
     "mpl_set_profile", "mpl_profile_categories", "mpl_profile_category_name", "mpl_profile_collect", "mpl_synth_project",
-    "mpl_pmpjpe_accumulate", "mpl_test_gemm_ln", "mpl_test_gemm_ln_slots", "mpl_set_graph_batch", "mpl_graph_stats",
+    "mpl_pmpjpe_accumulate", "mpl_test_gemm_ln", "mpl_test_gemm_ln_slots", "mpl_test_gemm_emit_pitch", "mpl_set_graph_batch", "mpl_graph_stats",
     "mpl_test_qkv_attn",
 ]
 
@@ -124,6 +124,8 @@ def lib():
         L.mpl_test_gemm_ln.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p]
         L.mpl_test_gemm_ln_slots.argtypes = [c_int]
+        L.mpl_test_gemm_emit_pitch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                               c_int, c_int, c_int, c_void_p]
         L.mpl_test_qkv_attn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p,
                                         c_int64, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
         L.mpl_set_graph_batch.argtypes = [c_void_p, c_int64]

@@ -1361,6 +1361,19 @@ int mpl_test_gemm_ln(const void* A, const void* W, const float* bias, void* Y, i
 }
 int mpl_test_gemm_ln_slots(int N) { return gemm_ln_slots(N); }
 
+int mpl_test_gemm_emit_pitch(const void* A, const void* W, const float* bias, void* Y, int64_t M, int N, int K, void* stats_out,
+                             void* x_lo, int ab_fp16, int ldy, int cta_group, mpl_stream_t stream) {
+  MPL_API_BEGIN
+  GemmLnArgs a{};
+  a.stats_out = stats_out;
+  a.x_lo = x_lo;
+  a.ab_fp16 = ab_fp16;
+  a.ldy = ldy;
+  return launch_gemm_tcgen05(A, W, bias, Y, M, N, K, MPL_PREC_BF16, EPI_RESIDUAL_EMIT, 0, reinterpret_cast<cudaStream_t>(stream), &a,
+                             cta_group);
+  MPL_API_END
+}
+
 /* The fused QKV + cross-view attention kernel in isolation.  scratch: (H * 416 * D) bf16 + 2 * (H * 416) floats, 256-aligned. */
 int mpl_test_qkv_attn(const void* xb, const float* W, const float* bias, const float* gamma, const float* beta,
                       const void* stats, int slots, float eps, float scale, void* att, int64_t M, int D, int H, int V,

@@ -105,6 +105,36 @@ def test_residual_emit_epilogue(M, N, K, fp16, cg):
     assert e1 <= 1e-5 and e2 <= 1e-5, (e1, e2)
 
 
+@pytest.mark.parametrize("M,N,K,ldy,fp16", [(777, 544, 2176, 1088, True), (4100, 544, 1088, 1088, False), (300, 64, 128, 256, False),
+                                           (33000, 544, 2176, 1088, True)])
+def test_residual_emit_on_the_leading_columns_of_wider_planes(M, N, K, ldy, fp16):
+    """The last fc2 of the FPT stack updates only the pose half of the channel-permuted residual stream: N = 544 columns of
+    planes whose rows are 1 088 elements apart.  The columns beyond N must come back bit for bit."""
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + ldy)
+    dt = torch.float16 if fp16 else torch.bfloat16
+    A = torch.randn(M, K, device="cuda", generator=g).to(dt).contiguous()
+    W = (torch.randn(N, K, device="cuda", generator=g) / np.sqrt(K)).to(dt).contiguous()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x_old = torch.randn(M, ldy, device="cuda", generator=g) * 1.5
+    hi, lo = _planes(x_old)
+    hi0, lo0 = hi.clone(), lo.clone()
+    stats = torch.full((L.mpl_test_gemm_ln_slots(N), _pad256(M), 2), float("nan"), device="cuda")
+    _lib.check(L.mpl_test_gemm_emit_pitch(A.data_ptr(), W.data_ptr(), bias.data_ptr(), hi.data_ptr(), M, N, K, stats.data_ptr(),
+                                          lo.data_ptr(), int(fp16), ldy, 2, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = (hi0.double() + lo0.double())[:, :N] + A.double() @ W.double().T + bias.double()
+    got = (hi.double() + lo.double())[:, :N]
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 2e-5, f"M={M} N={N} K={K} ldy={ldy}: {err:.3e}"
+    assert torch.equal(hi[:, N:], hi0[:, N:]) and torch.equal(lo[:, N:], lo0[:, N:])
+    s = stats[:, :M].double().sum(0)
+    assert (s[:, 0] - ref.sum(1)).abs().max().item() / ref.abs().sum(1).max().item() <= 1e-5
+    L2 = L.mpl_test_gemm_emit_pitch(A.data_ptr(), W.data_ptr(), bias.data_ptr(), hi.data_ptr(), M, N, K, stats.data_ptr(),
+                                    lo.data_ptr(), int(fp16), N - 16, 2, None)
+    assert L2 == _lib.MPL_ERR_INVALID_ARGUMENT                      # a pitch below N is refused
+
+
 @pytest.mark.parametrize("mean_over_std,bound", [(0.0, 8e-3), (1.0, 1.2e-2), (4.0, 4e-2), (16.0, 1.6e-1)])
 def test_folded_layernorm_error_grows_with_row_mean_over_std(mean_over_std, bound):
     """The folded LayerNorm multiplies the RAW residual rows rounded to bf16, so its error relative to the normalised value
