@@ -121,7 +121,8 @@ int mpl_num_params(const MplModel* m);
 int mpl_param_info(const MplModel* m, int index, const char** name, int64_t* numel, int32_t* is_int64);
 
 /* Derived dims (multiview_mpl.py:140-142,272-274): which = 0 tok_w, 1 fpt_dim, 2 fpt_tokens, 3 E, 4 spt_hidden,
- * 5 fpt_hidden, 6 outputs (1, or 3 for head_kadkhod). */
+ * 5 fpt_hidden, 6 outputs (1, or 3 for head_kadkhod), 7 output columns the LAST fc2 of the FPT stack computes (E where the
+ * residual stream is kept channel-permuted and the head reads its pose half only, else fpt_dim). */
 int64_t mpl_dim(const MplModel* m, int which);
 
 /* Weight repack: fp32 state_dict tensors (device pointers, in mpl_param_info order) -> one caller-owned blob

@@ -959,6 +959,7 @@ int64_t mpl_dim(const MplModel* m, int which) {
     case 4: return m->spt_hidden;
     case 5: return m->fpt_hidden;
     case 6: return m->n_out;
+    case 7: return m->perm ? m->E : m->fpt_dim;
     default: return -1;
   }
 }
