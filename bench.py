@@ -379,8 +379,7 @@ def run_ours(args):
                                  "frac_of_hbm_peak": gbs / pk.get("hbm_gbs", 6650.0)}
             cap = traffic.get("head_block_kernel") if k == "head" else None
             if cap and Bc == 32768 and args.precision == "bf16":
-                # what DRAM really moves for this launch (ncu capture of the same chunk size, profiles/ncu_traffic.json): the head
-                # uses the pose half of every 128-byte line of the residual planes and DRAM delivers whole lines
+                # what DRAM really moves for this launch (ncu capture of the same chunk size, profiles/ncu_traffic.json)
                 dgbs = cap["bytes_per_launch"] / (ms_l * 1e-3) / 1e9
                 memory_kernels[k].update({"dram_bytes_per_launch_ncu": cap["bytes_per_launch"], "dram_gbs": dgbs,
                                           "dram_frac_of_hbm_peak": dgbs / pk.get("hbm_gbs", 6650.0),

@@ -5,7 +5,8 @@ four FPT GEMM launches of one block, stamped with the build it was taken from.
     python scripts/ncu_traffic.py gpurun_out/<capture>.ncu-rep [arch] [profiles/<summary>.md] [gpurun_out/<head capture>.ncu-rep]
 
 The optional fourth argument is a capture of head_block_kernel: its DRAM bytes per launch are recorded next to the GEMMs'
-(the head reads the non-ray half of every 128-byte line; DRAM delivers whole lines, i.e. twice the algorithmic bytes).
+(reading the pose half of interleaved [x_j | ray_j] rows fetched whole 128-byte lines, twice the algorithmic bytes; the
+channel-permuted residual planes made the half rows contiguous).
 """
 import csv
 import hashlib
@@ -75,8 +76,9 @@ def main():
             t = sum(val2(r, "gpu__time_duration.sum") for r in heads) / len(heads)
             data[arch]["head_block_kernel"] = {"bytes_per_launch": b, "ncu_launch_s": t, "ncu_dram_gbs": b / t / 1e9,
                                                "capture": os.path.basename(sys.argv[4]),
-                                               "note": "DRAM bytes of one head launch (32768 poses): the kernel uses the pose half (64 B) of "
-                                                       "every 128-byte line of the two residual planes, DRAM delivers the whole line"}
+                                               "note": "DRAM bytes of one head launch (32768 poses), ncu --set full.  Channel-permuted "
+                                                       "residual planes: contiguous half rows, traffic = algorithmic bytes; with the "
+                                                       "reference's interleaved [x_j | ray_j] order it read whole 128-byte lines (2x)"}
     json.dump(data, open(path, "w"), indent=1)
     print(json.dumps(data[arch], indent=1))
 
