@@ -40,7 +40,7 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     p.add_argument("--precision", default=os.environ.get("MPL_BENCH_PRECISION", "bf16"), choices=["bf16", "tf32", "fp32"])
     p.add_argument("--batch", type=int, default=65536, help="poses per GPU per step")
     p.add_argument("--cpu-batch", type=int, default=1024, help="poses per CPU-baseline forward")
@@ -149,6 +149,57 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu(args):
+    """--impl reference-gpu: the second comparator of SURVEY.md section 8d -- the UNMODIFIED reference module (staged under
+    oracle/_ref/) run as PyTorch-eager library kernels (cuBLAS / ATen; the reference ships no GPU kernels of its own) on
+    cuda:0, CUDA-event timed, at its runner's own batch (256) and at the bench batch: fp32 (TF32 off), TF32 allowed, bf16
+    autocast.  `value` is the most favourable of them at the bench batch."""
+    import contextlib
+    import torch
+    from openmpl_b200 import synth
+    from oracle import ref_loader                                   # reference arm only
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if ref_loader.model_file() is None or not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "needs the staged reference module (oracle/_ref) and a GPU"}), flush=True)
+        return
+    kw, cfg = workload(args)
+    mod = ref_loader.load_model_module()
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    model = mod.MultiView_MPL(**kw).eval().to(dev)
+    V = cfg.V
+    steps, warmup = max(1, min(args.steps, 20)), max(2, min(args.warmup, 5))
+    modes = {}
+    for B in sorted({256, args.batch}):
+        batch = synth.make_batch(B, synth.make_rig(V, ARCH_RIG[args.arch]), seed=1)
+        lists = [[torch.from_numpy(np.ascontiguousarray(batch[k][:, v])).to(dev) for v in range(V)] for k in ("poses", "rays", "centers")]
+        for mode in ("fp32", "tf32", "bf16_autocast"):
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = mode == "tf32"
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16_autocast" else contextlib.nullcontext()
+            with torch.no_grad(), ctx:
+                for _ in range(warmup):
+                    model(lists[0], rays=lists[1], centers=lists[2])
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(steps):
+                    model(lists[0], rays=lists[1], centers=lists[2])
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            modes[f"{mode}_b{B}"] = {"poses_per_s": B / (ms / 1e3), "ms_per_forward": ms}
+    best = max(("fp32", "tf32", "bf16_autocast"), key=lambda m: modes[f"{m}_b{args.batch}"]["poses_per_s"])
+    line = {"impl": "reference-gpu", "metric": metric_name(args), "value": modes[f"{best}_b{args.batch}"]["poses_per_s"], "unit": "poses/s",
+            "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": modes[f"{best}_b{args.batch}"]["ms_per_forward"],
+            "higher_is_better": True, "dtype": best, "data": "synthetic",
+            "config": {"workload": workload_name(args, cfg, args.batch, f"batch {args.batch} per GPU"),
+                       "note": "the unmodified reference module (MPL/lib/models/multiview_mpl.py) as PyTorch-eager library kernels on cuda:0, "
+                               "inputs resident on the device; not the tier's reference arm (that is --impl reference, host cores)"},
+            "modes": modes, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -512,6 +563,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 
