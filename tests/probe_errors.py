@@ -1,5 +1,8 @@
+"""Checker utility (test infrastructure, not collected by pytest): error of every tensor-core mode against the goldens.
+    python tests/probe_errors.py [tf32 bf16 ...]     (PROBE_CASES=name,name to pick cases)"""
 import sys, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE)); sys.path.insert(0, _HERE)
 import numpy as np
 from conftest import load_golden
 from gpu_util import build_module, run_module, rel_err, mpjpe_mm
