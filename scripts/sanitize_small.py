@@ -13,6 +13,8 @@ from openmpl_b200.models.multiview_mpl_b200 import MultiView_MPL
 CASES = [
     dict(depth=2, num_views=4, **spec.HM0_FLAGS),
     dict(depth=2, num_views=3, **spec.CHOSEN_FLAGS),
+    dict(depth=1, num_views=5, **spec.HM0_FLAGS),        # pose-aligned tiling of the fused QKV + attention kernel, permuted planes
+    dict(depth=1, num_views=7, **spec.CHOSEN_FLAGS),     # 68-wide head pairs, 28 rows per lane quarter
     dict(depth=1, num_views=5, confidence_as_attention_uncertainty_weight=True, confidence_in_FPT=True, input_rays_as_token=True),
     dict(depth=2, num_views=2, FPT_blocks_view_keypoint_tokens=True, pose_3d_emb_learnable=True),
 ]
