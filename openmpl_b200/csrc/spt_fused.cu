@@ -2,11 +2,13 @@
 //
 // The SPT is latency / issue work, not FLOPs: 17 tokens x 32 channels per (pose, view) set, head_dim 4, depth+1 block
 // applications.  Launched layer by layer it is ~14 small kernels per application and re-reads the residual stream
-// from HBM every time; here a CTA keeps 16 sets resident for the whole stack, two CTAs per SM:
-//   * 16 sets x 17 tokens = 272 rows = 17 MMA row tiles of 16 -> 9 warps x 2 tiles (the last warp's second tile is a
+// from HBM every time; here a CTA keeps 14 sets resident for the whole stack, two CTAs per SM:
+//   * 14 sets x 17 tokens = 238 rows = 15 MMA row tiles of 16 -> 8 warps x 2 tiles (the last warp's second tile is a
 //     phantom), so every weight fragment read from shared memory feeds two MMAs (the v1 kernel, one tile per warp,
 //     was bound by the LSU pipe); the two resident CTAs run out of phase, so the attention phase of one (LSU + MUFU)
-//     overlaps the MMA / GELU phases of the other (one 544-thread CTA per SM issued only 48 % of the cycles);
+//     overlaps the MMA / GELU phases of the other (one 544-thread CTA per SM issued only 48 % of the cycles).
+//     8 warps rather than 9 x 16 sets (the first shape of this kernel): two 256-thread CTAs get 128 registers per
+//     thread instead of 96 and stop spilling -- 3-5 % faster in every mode (profiles/r2_experiments.md);
 //   * the residual stream lives in registers as mma.sync C fragments (32 fp32 per lane) across all applications;
 //   * LayerNorm is computed on the fragments (quad shuffles, one pass, gamma / beta folded into the following weights
 //     and biases at pack time); the four Linears are fp16 mma.sync m16n8k16 with fp32
@@ -32,8 +34,13 @@ namespace mpl {
 namespace {
 
 constexpr int J = 17, D = 32, HID = 64, HEADS = 8;
-constexpr int SETS = 16, ROWS = SETS * J, WARPS = 9, THREADS = WARPS * 32;  // 272 rows, one attention thread per row
-constexpr int SROWS = WARPS * 32;  // staging rows incl. the phantom tile of the last warp (rows 272..287)
+#ifndef MPL_SPT_SETS  // build-time experiment knob (MPL_SPT_DEFS, openmpl_b200/build.py)
+#define MPL_SPT_SETS 14
+#define MPL_SPT_WARPS 8
+#endif
+constexpr int SETS = MPL_SPT_SETS, ROWS = SETS * J, WARPS = MPL_SPT_WARPS, THREADS = WARPS * 32;  // 238 rows in 256 threads
+static_assert(ROWS <= WARPS * 32 && SETS * 18 <= THREADS + 17, "two row tiles per warp, 18 attention threads per set");
+constexpr int SROWS = WARPS * 32;  // staging rows incl. the phantom tile of the last warp (rows 238..255)
 constexpr int QP = 104;     // fp16 row pitch of the q|k|v staging buffer (96 + 8): 52 words -> rows g = 0..7 start on banks
                             // {0,20,8,28,16,4,24,12}: conflict-free half2 C-fragment stores, A-fragment loads and 16 B row loads
 constexpr int QPW = QP / 2;
@@ -199,7 +206,7 @@ struct SptArgs {
   int depth;
   int conf_weighted;                  // the confidence-weighted extra pass per block is live
   int group;                          // GROUPED: sets attending together (V views of a pose); 1 in the SPT
-  int rows_used;                      // rows of a CTA tile that carry data: ROWS, or (16 / group) * group * 17 when GROUPED
+  int rows_used;                      // rows of a CTA tile that carry data: ROWS, or (SETS / group) * group * 17 when GROUPED
   int final_norm;                     // apply Spatial_norm at the end (SPT) or store the residual as is (GROUPED)
   SptIo io;                           // fused K1 embedding in front, fused FPT token build behind
 };
@@ -230,7 +237,8 @@ __device__ __forceinline__ __half2 ex2_h2(__half2 x) {
   return h2(r);
 }
 
-// (measured: __maxnreg__(112) removes the spills but only one CTA then fits per SM -> 16.3 ms instead of 13.2 ms per step)
+// (measured with the 9-warp shape: __maxnreg__(112) removes the spills but only one CTA then fits per SM -> 16.3 ms instead
+// of 13.2 ms per step; the 8-warp shape gets its 128 registers with two CTAs resident)
 // PRECISE (tf32 mode): softmax / PV arithmetic in fp32 on the fp16-staged q, k, v and the exact erf GELU -- every
 // rounding left is a 2^-11 operand rounding, the same class as kind::tf32's; bf16 mode takes the packed-half2 forms.
 // GROUPED: the same block stack as the keypoint-token FPT (FPT_blocks_view_keypoint_tokens: tokens = V * 17 joints of one
@@ -241,9 +249,9 @@ __device__ __forceinline__ __half2 ex2_h2(__half2 x) {
 template <bool PRECISE, bool GROUPED>
 __device__ __forceinline__ void spt_fused_body(const SptArgs& args);
 
-// packed-half2 forms: two CTAs per SM (96 registers); PRECISE: one CTA per SM.  168 registers is the ceiling for 288 threads
-// (the register file is handed out in units of four warps: 9 warps count as 12 -> 65536 / 384; a 224-register build
-// compiles without spills but cannot launch), so the split-operand form lives with ~740 bytes of spills
+// packed-half2 forms: two CTAs of 8 warps per SM (128 registers each); PRECISE: one CTA per SM with up to 255 registers
+// (it takes 238; the 9-warp shape was capped at 168 -- the register file is handed out in units of four warps, 9 count as
+// 12 -- and spilled ~740 bytes)
 template <bool GROUPED>
 __global__ void __launch_bounds__(THREADS, 2) spt_fused_kernel_fast(const SptArgs args) { spt_fused_body<false, GROUPED>(args); }
 __global__ void __launch_bounds__(THREADS, 1) spt_fused_kernel_precise(const SptArgs args) { spt_fused_body<true, false>(args); }
