@@ -73,7 +73,10 @@ struct Cfg {
   // Register cap.  The LayerNorm-fused bf16 kernels (the bench path) need no more than 112 registers (no spills): 42 k of the
   // SM's 64 k, which leaves room for CTAs of a light kernel from another stream beside the persistent GEMM CTA; the other
   // instantiations take what a single CTA per SM may use.
-  static constexpr int MAXREG = (KIND == 0 && EPI >= 4) ? 112 : 168;
+#ifndef MPL_LN_MAXREG
+#define MPL_LN_MAXREG 112
+#endif
+  static constexpr int MAXREG = (KIND == 0 && EPI >= 4) ? MPL_LN_MAXREG : 168;
   static constexpr int SLOTS_EVEN = !RESID ? 0 : (EPI == 6 ? MPL_E6_SLOTS_EVEN : 1);  // slots of an even-group warp (odd-group warps: 1)
   static constexpr int RING_SLOTS = !RESID ? 0 : 4 * SLOTS_EVEN + 4;
   static constexpr int SLOT_BYTES = 8192;
