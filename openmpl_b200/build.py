@@ -20,6 +20,8 @@ HEADERS = ["common.cuh", "kernels.cuh", "ptx.cuh", os.path.join("..", "..", "inc
 # per-file extra nvcc flags; MPL_GEMM_DEFS="-DMPL_LN_STAGES=6 ..." builds an experiment variant of the GEMM kernel
 EXTRA_FLAGS = {"gemm_tcgen05.cu": os.environ.get("MPL_GEMM_DEFS", "").split(),
                "spt_fused.cu": os.environ.get("MPL_SPT_DEFS", "").split()}
+# second compilation of spt_fused.cu: the 16-set / 9-warp shape, exporting launch_fpt_kp_fused_alt only (see the file's header)
+VARIANTS = [("spt_fused.cu", "spt_fused_alt.o", ["-DMPL_SPT_ALT"])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -45,13 +47,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     objs, procs = [], []
-    for s in srcs:
-        o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
+    # (source, object name, extra flags): every source once, plus the second shape of the single-kernel transformer
+    units = [(s, os.path.basename(s)[:-3] + ".o", EXTRA_FLAGS.get(os.path.basename(s), [])) for s in srcs]
+    units += [(os.path.join(CSRC, s), o, f) for s, o, f in VARIANTS if os.path.isfile(os.path.join(CSRC, s))]
+    for s, oname, flags in units:
+        o = os.path.join(objdir, oname)
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             log = open(o + ".log", "w")
-            procs.append((s, log, subprocess.Popen([nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(os.path.basename(s), []), "-c", s, "-o", o],
-                                                    stdout=log, stderr=subprocess.STDOUT)))
+            procs.append((s, log, subprocess.Popen([nvcc, *NVCC_FLAGS, *flags, "-c", s, "-o", o], stdout=log, stderr=subprocess.STDOUT)))
     failed = []
     for s, log, p in procs:
         rc = p.wait()

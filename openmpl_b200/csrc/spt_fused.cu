@@ -23,6 +23,7 @@
 //   * the attention output overwrites the (already consumed) q slot of its own row and is the A operand of proj;
 //   * erf-GELU via a tanh-form fit (see gelu_tanh_fit), residual adds and the final Spatial_norm stay in fp32.
 // HBM traffic per set: 17*32*4 B in + out, nothing in between.
+#include <algorithm>
 #include <atomic>
 
 #include <cuda_fp16.h>
@@ -34,6 +35,13 @@ namespace mpl {
 namespace {
 
 constexpr int J = 17, D = 32, HID = 64, HEADS = 8;
+// This file is compiled twice (openmpl_b200/build.py): the primary object with the shape below, and -DMPL_SPT_ALT with the
+// first shape of the kernel (16 sets on 9 warps), which exports only launch_fpt_kp_fused_alt -- the keypoint-token FPT of
+// V = 5 or 8 views packs whole poses into 16 sets (15 and 16 of them) far better than into 14 (10 and 8).
+#ifdef MPL_SPT_ALT
+#define MPL_SPT_SETS 16
+#define MPL_SPT_WARPS 9
+#endif
 #ifndef MPL_SPT_SETS  // build-time experiment knob (MPL_SPT_DEFS, openmpl_b200/build.py)
 #define MPL_SPT_SETS 14
 #define MPL_SPT_WARPS 8
@@ -837,6 +845,7 @@ __global__ void spt_pack_kernel(const SptPackArgs a) {
 
 }  // namespace
 
+#ifndef MPL_SPT_ALT
 bool spt_fused_supports(int J_, int d, int H, int hidden) { return J_ == J && d == D && H == HEADS && hidden == HID; }
 size_t spt_fused_layer_bytes() { return (size_t)LAYER_WORDS_FULL * 4; }
 
@@ -888,9 +897,20 @@ int launch_spt_fused(const float* x_in, float* x_out, const void* const* wpack_p
   return MPL_OK;
 }
 
+int launch_fpt_kp_fused_alt(float* tok, const void* wpack, int V, int64_t B, int depth, cudaStream_t s);  // the 16-set object
+#endif  // !MPL_SPT_ALT
+
 // The keypoint-token FPT stack (bf16 mode) in one launch: tok [B, V * 17, 32] fp32 updated in place by depth + 1 block
 // applications (last block twice, multiview_mpl.py:420-423), attention over the V * 17 tokens of each pose.
+#ifdef MPL_SPT_ALT
+int launch_fpt_kp_fused_alt(float* tok, const void* wpack, int V, int64_t B, int depth, cudaStream_t s) {
+#else
 int launch_fpt_kp_fused(float* tok, const void* wpack, int V, int64_t B, int depth, cudaStream_t s) {
+  // whole poses per CTA tile: 14 sets hold (14 / V) * V of them, the 16-set object (16 / V) * V -- taken where that is >= 25 %
+  // more of the tile (V = 5: 15 vs 10 sets, V = 8: 16 vs 8)
+  if (4 * ((16 / std::max(V, 1)) * V) * SETS >= 5 * ((SETS / std::max(V, 1)) * V) * 16 && V <= 16)
+    return launch_fpt_kp_fused_alt(tok, wpack, V, B, depth, s);
+#endif
   if (B == 0 || depth == 0) return MPL_OK;
   if (V < 1 || V > SETS) {
     set_error("launch_fpt_kp_fused: %d views do not fit one CTA tile of %d sets", V, SETS);
