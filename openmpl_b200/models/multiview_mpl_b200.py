@@ -83,6 +83,14 @@ def _invalidate_after_load(module, incompatible_keys):
     module.invalidate()
 
 
+def pipeline_pieces(batch: int, chunk: int, first: int):
+    """[b0, b1) pose ranges of the pipelined host staging: a short first piece (at most `first` poses, never more than a
+    forward chunk), then whole chunks; every pose exactly once, in order."""
+    first = min(chunk, max(1, first))
+    bounds = [0] + list(range(first, batch, chunk)) + [batch]
+    return [(b0, b1) for b0, b1 in zip(bounds[:-1], bounds[1:]) if b1 > b0]
+
+
 class MultiView_MPL(nn.Module):
     """Same keyword arguments and defaults as the reference constructor (multiview_mpl.py:95-117)."""
 
@@ -495,9 +503,7 @@ class MultiView_MPL(nn.Module):
             side.wait_stream(main)                       # the fresh buffers may still be in use on the main stream
             # the first piece is small: its copy is the only one the forward has to wait for, every later piece arrives under
             # the kernels of the one before it
-            first = min(chunk, max(1, self.pipeline_first_poses))
-            bounds = [0] + list(range(first, B, chunk)) + [B]
-            pieces = list(zip(bounds[:-1], bounds[1:]))
+            pieces = pipeline_pieces(B, chunk, self.pipeline_first_poses)
             events = []
             with torch.cuda.stream(side):
                 for b0, b1 in pieces:

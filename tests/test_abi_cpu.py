@@ -308,3 +308,18 @@ def test_depth_zero_skips_the_head_divisibility_checks():
     h = ctypes.c_void_p()
     assert L.mpl_create(ctypes.byref(desc), ctypes.byref(h)) == 0, L.mpl_last_error()
     L.mpl_destroy(h)
+
+
+def test_pipelined_staging_pieces_cover_the_batch_once_and_in_order():
+    """Host inputs larger than a forward chunk are copied piece by piece under the kernels of the previous piece
+    (multiview_mpl_b200._forward_pipelined): a short first piece, then whole chunks."""
+    from openmpl_b200.models.multiview_mpl_b200 import pipeline_pieces
+    assert pipeline_pieces(65536, 32768, 4096) == [(0, 4096), (4096, 36864), (36864, 65536)]
+    assert pipeline_pieces(1000, 256, 100) == [(0, 100), (100, 356), (356, 612), (612, 868), (868, 1000)]
+    assert pipeline_pieces(1000, 256, 10 ** 9) == [(0, 256), (256, 512), (512, 768), (768, 1000)]      # never more than a chunk
+    assert pipeline_pieces(300, 256, 0) == [(0, 1), (1, 257), (257, 300)]
+    for B, chunk, first in [(1, 1, 1), (7, 3, 2), (32769, 32768, 4096), (4096, 32768, 4096), (5, 100, 100)]:
+        pieces = pipeline_pieces(B, chunk, first)
+        assert pieces[0][0] == 0 and pieces[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        assert all(0 < b1 - b0 <= chunk for b0, b1 in pieces)
