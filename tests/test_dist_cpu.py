@@ -74,3 +74,16 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     assert d["impl"] == "reference" and d["unit"] == "poses/s" and d["value"] > 0
     # "reference": the unmodified module (checkout mounted, or staged under oracle/_ref by build()); "port" only without it
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_reference_gpu_comparator_says_unavailable_without_a_gpu():
+    """`bench.py --impl reference-gpu` (the unmodified reference module as PyTorch-eager kernels on the B200, SURVEY §8d's second
+    comparator) needs a GPU: on a CPU-only host it prints one JSON line saying so and exits 0."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the comparator would run")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference-gpu"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["impl"] == "reference-gpu" and "unavailable" in d
